@@ -1,0 +1,113 @@
+/*
+ * lmrs_b200.h -- C ABI of liblmrs_b200.so: the Blackwell (sm_100a) implementation of the lm.rs
+ * quantized transformer forward path.
+ *
+ * The reference (samuel-vitorino/lm.rs) has no FFI/plugin interface; its drop-in boundary is the pub
+ * API of `lmrs::transformer` that the chat/backend bins call.  Every entry point
+ * below names the reference item it replaces (paths relative to the reference repo).  A Rust shim with
+ * the identical pub surface forwards to these symbols (lm.rs_b200/rust/).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types.  Every function returns 0 on success and a
+ * non-zero status on failure; lmrs_b200_last_error() then returns a thread-local message.  (The
+ * reference panics on the same conditions; the Rust shim turns a non-zero status into panic!.)
+ * There is NO CPU fallback: every call fails loudly if no sm_100 device is usable.
+ * A handle is not re-entrant (the reference takes &mut self); distinct handles are independent and may
+ * be driven from different threads (src/bin/backend.rs:87-110 creates one Transformer per connection).
+ */
+#ifndef LMRS_B200_H
+#define LMRS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* TransformerArgs, the 47-byte #[repr(C, packed)] header at file bytes 8..55
+ * (src/transformer.rs:57-74; written by export.py:54-80). */
+#pragma pack(push, 1)
+typedef struct lmrs_args {
+    uint32_t dim, hidden_dim, n_layers, n_heads, head_size, n_kv_heads, vocab_size, seq_len;
+    float    rms_norm_eps, rope_theta;
+    uint8_t  q_type;      /* QuantType: 0 None, 1 Q8_0, 2 Q4_0  (src/quantization.rs:1-6) */
+    uint8_t  model_type;  /* ModelType: 0 GEMMA, 1 LLAMA, 2 PHI (src/transformer.rs:50-55) */
+    uint32_t group_size;
+    uint8_t  multimodal;
+} lmrs_args_t;
+#pragma pack(pop)
+
+typedef struct lmrs_b200 lmrs_b200_t;
+
+/* ---- Transformer::new(&Mmap) -> (Transformer, usize)            src/transformer.rs:134-314 ------------
+ * Parses the LMRS v4 image [file, file+len), copies every tensor to HBM (no pointer into `file` is kept),
+ * allocates the f32 KV cache [n_layers][min(seq_len,8192)][kv_dim] x2, the RoPE tables and the pinned
+ * logits buffer.  *end_offset = byte offset where the vision section starts (the tuple's usize).
+ * device = CUDA ordinal (-1: current device). */
+int lmrs_b200_create(const uint8_t* file, size_t len, int device, lmrs_b200_t** out, size_t* end_offset);
+
+/* Row-sharded variant for N GPUs, one process per GPU (BASELINE north_star): rank r
+ * of world owns head-aligned output-row shards of wq/wk/wv/w1/w3 and input-column shards of wo/w2, and
+ * all-reduces the residual contribution twice per layer.  nccl_unique_id: the 128 bytes produced by
+ * lmrs_b200_nccl_unique_id() on rank 0 and broadcast by the caller (torch.distributed/MPI/...). */
+int lmrs_b200_create_sharded(const uint8_t* file, size_t len, int device, int rank, int world,
+                             const void* nccl_unique_id, lmrs_b200_t** out, size_t* end_offset);
+int lmrs_b200_nccl_unique_id(void* out128);
+
+/* impl Drop for Transformer                                      src/transformer.rs:688-711 */
+void lmrs_b200_destroy(lmrs_b200_t* m);
+
+/* pub args: TransformerArgs (vocab_size, model_type, multimodal are the pub fields the bins read:
+ * src/bin/chat.rs:85,135,158); seq_len is returned clamped to 8192 as at src/transformer.rs:158-160. */
+int lmrs_b200_args(const lmrs_b200_t* m, lmrs_args_t* out);
+
+/* ---- Transformer::forward(&mut self, token, pos) -> &mut [f32]   src/transformer.rs:316-384 -----------
+ * One decode step.  *logits_host points at library-owned PINNED host memory of vocab_size floats, fully
+ * rewritten by every call and valid until the next call; the caller may write into it (the reference's
+ * sampler does, src/sampler.rs:115-117). */
+int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, float** logits_host);
+
+/* ---- Transformer::get_embeddings(&self, &[u32]) -> Vec<f32>      src/transformer.rs:659-669 ----------- */
+int lmrs_b200_get_embeddings(const lmrs_b200_t* m, const uint32_t* tokens, size_t n_tokens, float* out);
+
+/* ---- Transformer::fill_kv_cache(&mut self, &mut [f32], pos) -> u32   src/transformer.rs:672-684 -------
+ * Batched prefill of n_floats/dim embeddings starting at pos: no final norm, no logits; the residual
+ * stream is written back into emb_inout (in-place semantics of the reference); *new_pos = pos + n. */
+int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb_inout, size_t n_floats, uint32_t pos, uint32_t* new_pos);
+
+/* ---- device-resident stepping (no reference counterpart; used by bench.py's HBM-resident `value` leg
+ * and by callers that sample on the device).  forward_device enqueues one decode step on the handle's
+ * stream and returns without synchronising or copying logits; logits stay in HBM. */
+int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t pos);
+int lmrs_b200_logits_device(lmrs_b200_t* m, float** logits_dev);
+int lmrs_b200_set_stream(lmrs_b200_t* m, void* cuda_stream); /* cudaStream_t; NULL = library-owned stream */
+int lmrs_b200_synchronize(lmrs_b200_t* m);
+/* number of CUDA kernels this handle has launched (graph replays count their kernel nodes) */
+int lmrs_b200_kernel_launches(const lmrs_b200_t* m, uint64_t* count);
+/* test access: copy K and V rows [pos0, pos0+n) of one layer to host (f32 [n][kv_dim] each) */
+int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out);
+
+/* ---- operator level: the free functions vision.rs / processor.rs import (src/vision.rs:1-3,
+ * src/processor.rs:1-3).  Host pointers in and out; each call stages through HBM and runs the same
+ * kernels the model path uses.
+ *   matmul_q8   src/functional.rs:173-214    xout[rows*o];  x {q i8[rows*n], s f32[rows*n/gs]};  w {q i8[o*n], s}
+ *   matmul_q4   src/functional.rs:216-250    4-bit x and w, two values per byte, low nibble = even index
+ *   quantize    src/quantization.rs:44-67    quantize_q4  src/quantization.rs:69-95
+ *   rmsnorm     src/functional.rs:48-78      softmax      src/functional.rs:122-140 */
+int lmrs_b200_matmul_q8(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                        int rows, int n, int o, int gs);
+int lmrs_b200_matmul_q4(float* xout, const uint8_t* xq, const float* xs, const uint8_t* wq, const float* ws,
+                        int rows, int n, int o, int gs);
+int lmrs_b200_quantize_q8(int8_t* q, float* s, const float* x, int n, int gs);
+int lmrs_b200_quantize_q4(uint8_t* q, float* s, const float* x, int n, int gs);
+int lmrs_b200_rmsnorm(float* o, const float* x, const float* w, int size, float eps, int add_unit_offset);
+int lmrs_b200_softmax(float* x, int n);
+
+const char* lmrs_b200_last_error(void);
+/* "lmrs_b200 <version> sm_100a" */
+const char* lmrs_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LMRS_B200_H */

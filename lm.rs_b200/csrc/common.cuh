@@ -1,0 +1,107 @@
+// common.cuh -- sm_100a PTX helpers shared by the lmrs_b200 kernels: mbarrier, 1-D bulk async copies
+// (TMA engine, SASS UBLKCP), programmatic dependent launch, exact-rounding float helpers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define LMRS_DEVINL __device__ __forceinline__
+
+namespace lmrs {
+
+LMRS_DEVINL uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier (shared::cta) ----------------------------------------------------------------------------
+LMRS_DEVINL void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make barrier inits (generic proxy) visible to the async proxy (bulk copies complete_tx on them)
+LMRS_DEVINL void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+LMRS_DEVINL void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+LMRS_DEVINL bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+LMRS_DEVINL void mbar_wait(uint64_t* bar, uint32_t parity) {
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+
+// ---- 1-D bulk async copy global -> shared, completion signalled on an mbarrier (cp.async.bulk) ---------
+// dst, src 16-byte aligned, bytes a multiple of 16.
+LMRS_DEVINL void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// same with an L2 eviction-priority hint (weights are streamed once per token: evict_first)
+LMRS_DEVINL uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+LMRS_DEVINL void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+            "r"(smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)), "l"(pol)
+        : "memory");
+}
+
+// ---- programmatic dependent launch ---------------------------------------------------------------------
+// pdl_wait(): block until every kernel this launch depends on has completed and flushed (no-op when the
+// kernel was launched without the PDL attribute).  pdl_launch_dependents(): allow the next kernel in the
+// stream to start its pre-wait portion (weight prefetch) now.
+LMRS_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+LMRS_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ---- integer dot products ------------------------------------------------------------------------------
+LMRS_DEVINL int dp4a_ss(int a, int b, int c) { return __dp4a(a, b, c); }
+// a: 4 x s8, b: 4 x u8
+LMRS_DEVINL int dp4a_su(int a, uint32_t b, int c) {
+    int d;
+    asm("dp4a.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// ---- Rust-semantics scalar helpers (no FMA contraction anywhere on the parity path) ---------------------
+// f32::round (half away from zero) followed by `as i8` (saturating, NaN -> 0): src/quantization.rs:63
+LMRS_DEVINL int round_sat_i8(float v) {
+    float r = roundf(v);
+    if (!(r == r)) return 0;
+    r = fminf(fmaxf(r, -128.0f), 127.0f);
+    return (int)r;
+}
+// (v + 8.0).round() as u8, clamp(0, 15): src/quantization.rs:89-90
+LMRS_DEVINL int round_sat_u4(float v) {
+    float r = roundf(__fadd_rn(v, 8.0f));
+    if (!(r == r)) return 0;
+    r = fminf(fmaxf(r, 0.0f), 15.0f);
+    return (int)r;
+}
+
+LMRS_DEVINL float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+LMRS_DEVINL float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace lmrs

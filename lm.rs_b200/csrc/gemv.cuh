@@ -1,0 +1,369 @@
+// gemv.cuh -- decode-path (seq = 1) quantized matrix-vector kernel for sm_100a.
+//
+// Replaces functional.rs::matmul_q8 / matmul_q4 (src/functional.rs:173-250) for one activation row, with the
+// surrounding glue of transformer.rs::forward_layer fused in:
+//   prologue  PRO_NORM   residual add (+ Gemma post-norm) + rmsnorm + activation quantize
+//                        (src/transformer.rs:409-411,427 / :562-580,596 / :642-656 / :343,356)
+//             PRO_QUANT  activation quantize of an f32 vector (src/transformer.rs:553,633; src/quantization.rs:44-95)
+//             PRO_RAW    pre-quantized activation given by the caller (operator-level C ABI)
+//   epilogue  EPI_STORE / EPI_QKV (q buffer, new-K staging row, V cache row) / EPI_GLU_* (act(gate)*up,
+//             src/transformer.rs:607-624) / EPI_LOGITS (Gemma soft-cap quirk, src/transformer.rs:375-381)
+//
+// Data movement (HBM-bound kernel, ~2 int-ops/byte): every warp owns two independent "streams" of
+// consecutive weight rows (one per half-warp; for GLU the halves stream the same rows of w1 and w3).  A
+// stream is a contiguous byte range of the row-major [o][n] int8 matrix plus the matching contiguous range
+// of f32 group scales, so lane 0 moves it with 1-D bulk async copies (cp.async.bulk -> SASS UBLKCP, the TMA
+// engine) into a per-warp shared-memory ring guarded by mbarriers: no registers are tied up by loads in
+// flight, and the first DEPTH stages are issued BEFORE griddepcontrol.wait so weight traffic overlaps the
+// previous kernel's tail and this kernel's own prologue (programmatic dependent launch).
+//
+// Arithmetic: a stage gives each lane one whole 128-element group (8 x LDS.128 of weights, 8 x LDS.128 of
+// the quantized activation, 32 x IDP.4A) -- the int32 group sum needs no cross-lane reduction.  The f32 part
+// follows the reference bit for bit: term = ((ival as f32) * ws) * xs, and terms are added to the row
+// accumulator in ascending group order starting from 0.0 (a 16-step shuffle scan per half-warp), so
+// matmul_q8/matmul_q4 results are BIT-IDENTICAL to the CPU path; -fmad=false keeps mul/add unfused.
+#pragma once
+#include "common.cuh"
+
+namespace lmrs {
+
+constexpr int GS = 128;          // quantization group size (elements); the exporter always writes 128 (utils/io.py:21)
+constexpr int SG = 16;           // groups per half-warp stream per stage
+constexpr int NORM_MAXC = 4;     // float4 chunks per thread kept in registers by PRO_NORM
+
+enum { PRO_NORM = 0, PRO_QUANT = 1, PRO_RAW = 2 };
+enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GLU_SILU = 2, EPI_GLU_GELU = 3, EPI_LOGITS = 4 };
+
+struct StepParams {
+    uint32_t token;      // decode: token id; serial prefill: row index into the staged embeddings
+    uint32_t pos;        // position of this step
+    uint32_t mask_base;  // Gemma window quirk: the reference tests `pos - t` with the BATCH start pos
+    uint32_t pad;        //   (src/transformer.rs:525); decode passes pos
+};
+
+struct GemvParams {
+    const uint8_t* wq_a; const float* ws_a;   // matrix A: q codes, group scales
+    const uint8_t* wq_b; const float* ws_b;   // matrix B (GLU: w3), else unused
+    int n, o, row_gran;
+    int pro;
+    const float* x_in; const float* delta; const float* w_post; const float* w_norm; float* x_out;
+    float eps; int unit_offset;
+    const float* act_in;
+    const uint8_t* raw_q; const float* raw_s;
+    int epi;
+    float* out; float* out_k; float* out_v;
+    int att_dim, kv_dim;
+    const StepParams* step;
+    int softcap_rows;
+};
+
+template <int QT> struct QTraits;
+template <> struct QTraits<1> { static constexpr int QB = 128; };  // bytes of codes per group, Q8_0
+template <> struct QTraits<2> { static constexpr int QB = 64; };   // Q4_0
+
+template <int QT> __host__ __device__ constexpr int gemv_stage_bytes() { return 2 * SG * QTraits<QT>::QB + 2 * SG * 4; }
+
+// shared-memory footprint of one CTA (must match the carve-up in the kernel)
+template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n) {
+    size_t ring = (size_t)WARPS * DEPTH * gemv_stage_bytes<QT>();
+    size_t xq = (size_t)n;                         // Q8: n codes; Q4: n/2 even + n/2 odd signed bytes
+    size_t xs = (size_t)(n / GS) * 4 * 2;          // scales + per-group code sums (Q4)
+    return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128;
+}
+
+struct RowRange { int row0, nrows; };
+LMRS_DEVINL RowRange slot_rows(int slot, int nslots, int o, int gran) {
+    int units = o / gran;
+    int a = (int)(((long long)slot * units) / nslots);
+    int b = (int)(((long long)(slot + 1) * units) / nslots);
+    return {a * gran, (b - a) * gran};
+}
+
+template <int WARPS> LMRS_DEVINL float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = lane < WARPS ? red[lane] : 0.0f;
+    t = warp_sum(t);
+    __syncthreads();
+    return t;
+}
+
+// quantize 4 consecutive activations held by each lane of a full warp == one 128-group
+// Q8: src/quantization.rs:44-67.  Q4: src/quantization.rs:69-95, stored as signed (nibble-8) bytes split
+// into even/odd element planes + the per-group sum of those bytes (used to fold the weight-side "-8").
+template <int QT>
+LMRS_DEVINL void quantize_group_to_smem(float4 y, int g, uint8_t* xq, float* xs, int* xsum, int n) {
+    const int lane = threadIdx.x & 31;
+    float m = fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w)));
+    m = warp_max(m);
+    if (QT == 1) {
+        float scale = __fdiv_rn(m, 127.0f);
+        int a = round_sat_i8(__fdiv_rn(y.x, scale)), b = round_sat_i8(__fdiv_rn(y.y, scale));
+        int c = round_sat_i8(__fdiv_rn(y.z, scale)), d = round_sat_i8(__fdiv_rn(y.w, scale));
+        uint32_t packed = (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) |
+                          ((uint32_t)(d & 0xff) << 24);
+        reinterpret_cast<uint32_t*>(xq + (size_t)g * GS)[lane] = packed;
+        if (lane == 0) xs[g] = scale;
+    } else {
+        float scale = __fdiv_rn(m, -8.0f);
+        int a = round_sat_u4(__fdiv_rn(y.x, scale)) - 8, b = round_sat_u4(__fdiv_rn(y.y, scale)) - 8;
+        int c = round_sat_u4(__fdiv_rn(y.z, scale)) - 8, d = round_sat_u4(__fdiv_rn(y.w, scale)) - 8;
+        uint8_t* xe = xq + (size_t)g * (GS / 2);
+        uint8_t* xo = xq + (size_t)(n / 2) + (size_t)g * (GS / 2);
+        reinterpret_cast<uint16_t*>(xe)[lane] = (uint16_t)((a & 0xff) | ((c & 0xff) << 8));
+        reinterpret_cast<uint16_t*>(xo)[lane] = (uint16_t)((b & 0xff) | ((d & 0xff) << 8));
+        int sum = a + b + c + d;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        if (lane == 0) { xs[g] = scale; xsum[g] = sum; }
+    }
+}
+
+template <int QT, int WARPS, int DEPTH>
+__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p) {
+    constexpr int QB = QTraits<QT>::QB;
+    constexpr int STAGE = gemv_stage_bytes<QT>();
+    constexpr int THREADS = WARPS * 32;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, l16 = lane & 15;
+    const int n = p.n, G = n / GS;
+
+    uint8_t* ring = smem;
+    uint8_t* xq = ring + (size_t)WARPS * DEPTH * STAGE;
+    float* xs = reinterpret_cast<float*>(xq + ((n + 127) / 128) * 128);
+    int* xsum = reinterpret_cast<int*>(xs + G);
+    float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + ((G * 8 + 127) / 128) * 128);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 64) + warp * DEPTH;
+
+    const bool glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
+    const int nslots = gridDim.x * WARPS * (glu ? 1 : 2);
+    const int wslot = blockIdx.x * WARPS + warp;
+    const RowRange r0 = slot_rows(glu ? wslot : wslot * 2, nslots, p.o, p.row_gran);
+    const RowRange r1 = glu ? r0 : slot_rows(wslot * 2 + 1, nslots, p.o, p.row_gran);
+    const int ng0 = r0.nrows * G, ng1 = r1.nrows * G;
+    const int nst = max((ng0 + SG - 1) / SG, (ng1 + SG - 1) / SG);
+    const uint8_t* srcq0 = p.wq_a + (size_t)r0.row0 * G * QB;
+    const float* srcs0 = p.ws_a + (size_t)r0.row0 * G;
+    const uint8_t* srcq1 = (glu ? p.wq_b : p.wq_a) + (size_t)r1.row0 * G * QB;
+    const float* srcs1 = (glu ? p.ws_b : p.ws_a) + (size_t)r1.row0 * G;
+
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+
+    auto issue = [&](int s) {  // lane 0: stream stage s of both halves into ring slot s % DEPTH
+        const int d = s % DEPTH;
+        uint8_t* buf = ring + (size_t)(warp * DEPTH + d) * STAGE;
+        const int c0 = min(SG, max(0, ng0 - SG * s)), c1 = min(SG, max(0, ng1 - SG * s));
+        mbar_expect_tx(&bars[d], (uint32_t)((c0 + c1) * (QB + 4)));
+        if (c0 > 0) {
+            bulk_g2s(buf, srcq0 + (size_t)s * SG * QB, c0 * QB, &bars[d]);
+            bulk_g2s(buf + 2 * SG * QB, srcs0 + (size_t)s * SG, c0 * 4, &bars[d]);
+        }
+        if (c1 > 0) {
+            bulk_g2s(buf + SG * QB, srcq1 + (size_t)s * SG * QB, c1 * QB, &bars[d]);
+            bulk_g2s(buf + 2 * SG * QB + SG * 4, srcs1 + (size_t)s * SG, c1 * 4, &bars[d]);
+        }
+    };
+    if (lane == 0)
+        for (int s = 0; s < DEPTH && s < nst; s++) issue(s);   // weights never depend on the previous kernel
+
+    pdl_launch_dependents();
+    pdl_wait();  // upstream activations are complete and visible from here on
+
+    // ------------------------------------------------------------------------------------------ prologue
+    if (p.pro == PRO_NORM) {
+        const int nchunks = n / 4;
+        float4 v[NORM_MAXC];
+        const float4* xin = reinterpret_cast<const float4*>(p.x_in);
+#pragma unroll
+        for (int k = 0; k < NORM_MAXC; k++) {
+            int c = tid + k * THREADS;
+            v[k] = c < nchunks ? xin[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        if (p.delta) {
+            const float4* din = reinterpret_cast<const float4*>(p.delta);
+            float4 dv[NORM_MAXC];
+            float ssd = 0.0f;
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) {
+                int c = tid + k * THREADS;
+                dv[k] = c < nchunks ? din[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                ssd += dv[k].x * dv[k].x + dv[k].y * dv[k].y + dv[k].z * dv[k].z + dv[k].w * dv[k].w;
+            }
+            if (p.w_post) {  // Gemma: x += rmsnorm(delta, w_post) with unit offset (src/transformer.rs:564,645)
+                float ss = block_sum<WARPS>(ssd, red);
+                ss = __fdiv_rn(ss, (float)n);
+                ss = __fadd_rn(ss, p.eps);
+                const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+                const float4* wp = reinterpret_cast<const float4*>(p.w_post);
+#pragma unroll
+                for (int k = 0; k < NORM_MAXC; k++) {
+                    int c = tid + k * THREADS;
+                    if (c < nchunks) {
+                        float4 w = wp[c];
+                        dv[k].x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, dv[k].x));
+                        dv[k].y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, dv[k].y));
+                        dv[k].z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, dv[k].z));
+                        dv[k].w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, dv[k].w));
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) {
+                v[k].x = __fadd_rn(v[k].x, dv[k].x); v[k].y = __fadd_rn(v[k].y, dv[k].y);
+                v[k].z = __fadd_rn(v[k].z, dv[k].z); v[k].w = __fadd_rn(v[k].w, dv[k].w);
+            }
+        }
+        if (p.x_out && blockIdx.x == 0) {  // exactly one CTA publishes the updated residual stream
+            float4* xo = reinterpret_cast<float4*>(p.x_out);
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) {
+                int c = tid + k * THREADS;
+                if (c < nchunks) xo[c] = v[k];
+            }
+        }
+        float ssq = 0.0f;
+#pragma unroll
+        for (int k = 0; k < NORM_MAXC; k++)
+            ssq += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
+        float ss = block_sum<WARPS>(ssq, red);  // src/functional.rs:48-62 (sum order differs: tolerance-level)
+        ss = __fdiv_rn(ss, (float)n);
+        ss = __fadd_rn(ss, p.eps);
+        const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+        const float4* wn = reinterpret_cast<const float4*>(p.w_norm);
+#pragma unroll
+        for (int k = 0; k < NORM_MAXC; k++) {
+            int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
+            if (c < nchunks) {
+                float4 w = wn[c], y;
+                if (p.unit_offset) {
+                    y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
+                    y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
+                    y.z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, v[k].z));
+                    y.w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, v[k].w));
+                } else {
+                    y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
+                    y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
+                }
+                quantize_group_to_smem<QT>(y, c >> 5, xq, xs, xsum, n);
+            }
+        }
+    } else if (p.pro == PRO_QUANT) {
+        const float4* ain = reinterpret_cast<const float4*>(p.act_in);
+        for (int g = warp; g < G; g += WARPS) quantize_group_to_smem<QT>(ain[g * 32 + lane], g, xq, xs, xsum, n);
+    } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
+        if (QT == 1) {
+            const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_q);
+            for (int i = tid; i < n / 4; i += THREADS) reinterpret_cast<uint32_t*>(xq)[i] = src[i];
+            for (int g = tid; g < G; g += THREADS) xs[g] = p.raw_s[g];
+        } else {
+            for (int g = warp; g < G; g += WARPS) {   // unpack one group per warp: 64 bytes = 2 per lane
+                uint16_t two = reinterpret_cast<const uint16_t*>(p.raw_q + (size_t)g * 64)[lane];
+                int b0 = two & 0xff, b1 = two >> 8;
+                int e0 = (b0 & 15) - 8, o0 = (b0 >> 4) - 8, e1 = (b1 & 15) - 8, o1 = (b1 >> 4) - 8;
+                reinterpret_cast<uint16_t*>(xq + (size_t)g * 64)[lane] = (uint16_t)((e0 & 0xff) | ((e1 & 0xff) << 8));
+                reinterpret_cast<uint16_t*>(xq + (size_t)(n / 2) + (size_t)g * 64)[lane] =
+                    (uint16_t)((o0 & 0xff) | ((o1 & 0xff) << 8));
+                int sum = e0 + o0 + e1 + o1;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+                if (lane == 0) { xs[g] = p.raw_s[g]; xsum[g] = sum; }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ----------------------------------------------------------------------------------------- main loop
+    const RowRange rr = half ? r1 : r0;
+    const int ng = half ? ng1 : ng0;
+    const uint32_t pos = (p.epi == EPI_QKV) ? p.step->pos : 0u;
+    float acc = 0.0f;
+    for (int s = 0; s < nst; s++) {
+        const int d = s % DEPTH;
+        mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
+        const uint8_t* buf = ring + (size_t)(warp * DEPTH + d) * STAGE;
+        const int f = s * SG + l16;           // index of my group inside my stream
+        const bool valid = f < ng;
+        const int row_l = f / G, g = f - row_l * G;
+        float t = 0.0f;
+        if (valid) {
+            int iv0 = 0, iv1 = 0;
+            if (QT == 1) {
+                const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+                const int4* xv = reinterpret_cast<const int4*>(xq + (size_t)g * GS);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
+                    const int c = (i + l16) & 7;
+                    const int4 w4 = wv[c], x4 = xv[c];
+                    iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
+                    iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
+                }
+                iv0 += iv1;
+            } else {
+                const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+                const int4* ev = reinterpret_cast<const int4*>(xq + (size_t)g * (GS / 2));
+                const int4* ov = reinterpret_cast<const int4*>(xq + (size_t)(n / 2) + (size_t)g * (GS / 2));
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const int c = (i + (l16 >> 1)) & 3;
+                    const int4 w4 = wv[c], e4 = ev[c], o4 = ov[c];
+                    iv0 = dp4a_su(e4.x, (uint32_t)w4.x & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.x, ((uint32_t)w4.x >> 4) & 0x0F0F0F0Fu, iv1);
+                    iv0 = dp4a_su(e4.y, (uint32_t)w4.y & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.y, ((uint32_t)w4.y >> 4) & 0x0F0F0F0Fu, iv1);
+                    iv0 = dp4a_su(e4.z, (uint32_t)w4.z & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.z, ((uint32_t)w4.z >> 4) & 0x0F0F0F0Fu, iv1);
+                    iv0 = dp4a_su(e4.w, (uint32_t)w4.w & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.w, ((uint32_t)w4.w >> 4) & 0x0F0F0F0Fu, iv1);
+                }
+                iv0 = iv0 + iv1 - 8 * xsum[g];   // sum x_s*(w_u - 8) = sum x_s*w_u - 8*sum x_s
+            }
+            const float wsc = reinterpret_cast<const float*>(buf + 2 * SG * QB)[half * SG + l16];
+            t = __fmul_rn(__fmul_rn((float)iv0, wsc), xs[g]);   // (ival*ws)*xs, src/functional.rs:207,246
+        }
+        // ordered f32 accumulation across the 16 lanes of this half-warp (ascending group index)
+        const bool is_last = valid && (g == G - 1);
+        uint32_t first_mask = __ballot_sync(0xffffffffu, valid && g == 0) >> (half * 16);
+        float mine = 0.0f;
+#pragma unroll
+        for (int j = 0; j < SG; j++) {
+            const float tj = __shfl_sync(0xffffffffu, t, j, 16);
+            acc = __fadd_rn(((first_mask >> j) & 1u) ? 0.0f : acc, tj);
+            if (j == l16) mine = acc;
+        }
+        // ------------------------------------------------------------------------------------- epilogue
+        if (glu) {
+            const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
+            if (is_last && half == 0) {
+                float val = mine;
+                if (p.epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
+                    float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
+                    float th = (float)tanh(0.7978845608028654 * (double)inner);
+                    val = __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
+                } else {                       // SiLU (src/transformer.rs:617)
+                    val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
+                }
+                p.out[rr.row0 + row_l] = __fmul_rn(val, up);
+            }
+        } else if (is_last) {
+            const int row = rr.row0 + row_l;
+            if (p.epi == EPI_QKV) {
+                if (row < p.att_dim) p.out[row] = mine;
+                else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = mine;
+                else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = mine;
+            } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
+                float v = __fdiv_rn(mine, 30.0f);   // src/transformer.rs:375-381
+                v = (float)tanh((double)v);
+                p.out[row] = __fmul_rn(v, 30.0f);
+            } else {
+                p.out[row] = mine;
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && s + DEPTH < nst) issue(s + DEPTH);
+    }
+}
+
+}  // namespace lmrs

@@ -1,0 +1,704 @@
+// lmrs_b200.cu -- host side of liblmrs_b200.so: LMRS v4 loader, HBM layout, CUDA-graph decode step and
+// the C ABI declared in include/lmrs_b200.h.  Mirrors src/transformer.rs of samuel-vitorino/lm.rs:
+//   Transformer::new :134-314, forward :316-384, forward_layer :388-657, get_embeddings :659-669,
+//   fill_kv_cache :672-684, Drop :688-711.
+// There is no CPU fallback: every entry point fails with a message when CUDA/sm_100 is unavailable.
+#include "../../include/lmrs_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc.cuh"
+#include "shard.h"
+
+using namespace lmrs;
+
+static thread_local std::string g_err;
+extern "C" const char* lmrs_b200_last_error(void) { return g_err.c_str(); }
+extern "C" const char* lmrs_b200_version(void) { return "lmrs_b200 0.1 sm_100a"; }
+static int fail(const std::string& m) { g_err = m; return 1; }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(std::string(#call) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +   \
+                        std::to_string(__LINE__) + ")");                                           \
+    } while (0)
+
+static int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+// ---- device matrix views ---------------------------------------------------------------------------------
+struct Mat {
+    const uint8_t* q = nullptr;
+    const float* s = nullptr;
+    int o = 0, n = 0, gran = 1;
+};
+struct Layer {
+    Mat qkv, wo, w1, w3, w2;
+    const float *rms_att = nullptr, *rms_post_att = nullptr, *rms_pre_ffn = nullptr, *rms_post_ffn = nullptr;
+};
+
+struct lmrs_b200 {
+    lmrs_args_t args{};
+    int device = 0, sms = 148;
+    int rank = 0, world = 1;
+    // per-rank shard geometry (== full model when world == 1)
+    int l_heads = 0, l_kv_heads = 0, l_att_dim = 0, l_kv_dim = 0, l_hidden = 0, l_vocab = 0, vocab_off = 0;
+    uint8_t* d_arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<Layer> layers;
+    Mat emb, cls;
+    const float* rms_final = nullptr;
+    float *d_kcache = nullptr, *d_vcache = nullptr, *d_rope_cos = nullptr, *d_rope_sin = nullptr;
+    float *d_x[2] = {nullptr, nullptr}, *d_q = nullptr, *d_knew = nullptr, *d_att = nullptr, *d_wo_out = nullptr;
+    float *d_h = nullptr, *d_down_out = nullptr, *d_logits = nullptr, *d_part = nullptr, *d_rows = nullptr;
+    size_t rows_cap = 0;
+    unsigned* d_tickets = nullptr;
+    StepParams* d_step = nullptr;
+    StepParams* h_step_ring = nullptr;  // pinned
+    int step_slot = 0;
+    float* h_logits = nullptr;  // pinned
+    cudaStream_t stream = nullptr, own_stream = nullptr;
+    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr;
+    cudaStream_t g_decode_stream = nullptr, g_prefill_stream = nullptr;
+    int n_decode_kernels = 0, n_prefill_kernels = 0;
+    uint64_t launches = 0;
+    int nsplit = 16, att_chunks = 1;
+    bool use_graph = true, use_pdl = true;
+    int gemv_cfg = 0, gemv_ctas_per_sm = 1;
+    Shard shard;  // multi-GPU exchange (shard.h); inert when world == 1
+};
+
+// ---- kernel launch helper (optionally with the programmatic-dependent-launch attribute) -------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(lmrs_b200* m, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = m->use_pdl ? 1 : 0;
+    m->launches++;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
+// ---- GEMV dispatch ----------------------------------------------------------------------------------------
+struct GemvCfg { int warps, depth; };
+static const GemvCfg kGemvCfgs[] = {{8, 2}, {8, 3}, {16, 2}, {8, 4}, {4, 4}};
+typedef void (*gemv_fn)(const GemvParams);
+template <int QT> static gemv_fn gemv_kernel_for(int cfg) {
+    switch (cfg) {
+        case 0: return gemv_kernel<QT, 8, 2>;
+        case 1: return gemv_kernel<QT, 8, 3>;
+        case 2: return gemv_kernel<QT, 16, 2>;
+        case 3: return gemv_kernel<QT, 8, 4>;
+        default: return gemv_kernel<QT, 4, 4>;
+    }
+}
+template <int QT> static size_t gemv_smem_for(int cfg, int n) {
+    switch (cfg) {
+        case 0: return gemv_smem_bytes<QT, 8, 2>(n);
+        case 1: return gemv_smem_bytes<QT, 8, 3>(n);
+        case 2: return gemv_smem_bytes<QT, 16, 2>(n);
+        case 3: return gemv_smem_bytes<QT, 8, 4>(n);
+        default: return gemv_smem_bytes<QT, 4, 4>(n);
+    }
+}
+static int gran_for(int n) {
+    int G = n / GS;
+    for (int r = 1; r <= 4; r *= 2)
+        if ((r * G) % 4 == 0) return r;
+    return 4;
+}
+
+static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
+    const GemvCfg c = kGemvCfgs[m->gemv_cfg];
+    gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(m->gemv_cfg) : gemv_kernel_for<2>(m->gemv_cfg);
+    size_t smem = q_type == 1 ? gemv_smem_for<1>(m->gemv_cfg, p.n) : gemv_smem_for<2>(m->gemv_cfg, p.n);
+    static thread_local size_t max_set[2][8] = {};
+    if (smem > max_set[q_type - 1][m->gemv_cfg]) {
+        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        max_set[q_type - 1][m->gemv_cfg] = smem;
+    }
+    int grid = m->sms * m->gemv_ctas_per_sm;
+    // never launch more CTAs than there are row units to hand out (tiny matrices)
+    const bool glu = p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU;
+    int units = p.o / p.row_gran, slots_per_cta = c.warps * (glu ? 1 : 2);
+    int need = (units + slots_per_cta - 1) / slots_per_cta;
+    if (grid > need) grid = need < 1 ? 1 : need;
+    return launch(m, fn, dim3(grid), dim3(c.warps * 32), smem, p);
+}
+
+static GemvParams gemv_base(const Mat& a, const Mat* b) {
+    GemvParams p{};
+    p.wq_a = a.q; p.ws_a = a.s;
+    if (b) { p.wq_b = b->q; p.ws_b = b->s; }
+    p.n = a.n; p.o = a.o; p.row_gran = a.gran;
+    return p;
+}
+
+template <int HS> static cudaError_t launch_attn_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
+    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, p.nsplit), dim3(ATT_WARPS * 32), 0, p);
+}
+static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
+    switch (m->args.head_size) {
+        case 64: return launch_attn_hs<64>(m, p, n_kv_heads);
+        case 96: return launch_attn_hs<96>(m, p, n_kv_heads);
+        case 128: return launch_attn_hs<128>(m, p, n_kv_heads);
+        case 256: return launch_attn_hs<256>(m, p, n_kv_heads);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+// ---- RoPE frequency (src/transformer.rs:445-478), evaluated on the host with libm like the reference -------
+static void rope_freq(int model_type, float rope_theta, int head_size, int j, float* freq_out, float* mscale) {
+    static const double short_factor[48] = {
+        1.08, 1.1, 1.1300000000000001, 1.2800000000000002, 1.3100000000000003, 1.4500000000000004,
+        1.4500000000000004, 1.9500000000000008, 2.030000000000001, 2.4299999999999926, 2.5699999999999896,
+        2.9499999999999815, 3.729999999999965, 3.869999999999962, 4.189999999999955, 4.43999999999995,
+        4.6399999999999455, 4.979999999999938, 5.159999999999934, 5.279999999999932, 5.759999999999922,
+        5.889999999999919, 5.889999999999919, 5.969999999999917, 6.089999999999915, 6.2799999999999105,
+        6.7699999999999, 6.8899999999998975, 7.109999999999893, 7.129999999999892, 7.179999999999891,
+        7.289999999999889, 7.339999999999888, 7.559999999999883, 7.619999999999882, 7.69999999999988,
+        7.879999999999876, 7.879999999999876, 7.879999999999876, 7.939999999999875, 7.949999999999875,
+        7.979999999999874, 8.19999999999987, 8.439999999999864, 8.469999999999864, 8.589999999999861,
+        8.809999999999857, 8.999999999999853};
+    volatile float fj = (float)(2 * j) / (float)head_size;
+    volatile float freq = 1.0f / powf(rope_theta, fj);
+    float scaling = 1.0f;
+    if (model_type == 1) {  // LLAMA: llama-3 scaling constants hard-coded in the reference (:451-470)
+        volatile float wavelen = (2.0f * 3.14159265358979323846f) / freq;
+        const float factor = 32.0f, low = 1.0f, high = 4.0f, old_ctx = 8192.0f;
+        volatile float low_wl = old_ctx / low, high_wl = old_ctx / high;
+        if (wavelen > low_wl) {
+            freq = freq / factor;
+        } else if (wavelen <= low_wl && wavelen >= high_wl) {
+            volatile float a = old_ctx / wavelen;
+            volatile float smooth = (a - low) / (high - low);
+            volatile float t1 = (1.0f - smooth) * freq;
+            volatile float t2 = t1 / factor;
+            volatile float t3 = smooth * freq;
+            freq = t2 + t3;
+        }
+    }
+    if (model_type == 2) {  // PHI (:472-478)
+        volatile float inv = (float)(1.0 / short_factor[j % 48]);
+        freq = freq * inv;
+        volatile float scale = 131072.0f / 4096.0f;
+        volatile float r = logf(scale) / logf(4096.0f);
+        scaling = sqrtf(1.0f + r);
+    }
+    *freq_out = freq;
+    *mscale = scaling;
+}
+
+// ---- loader ----------------------------------------------------------------------------------------------
+struct FileTensor { size_t q_off, s_off, q_bytes, s_bytes; };   // one quantized tensor of one layer
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* end_offset) {
+    if (len < 256 || file[0] != 0x6c || file[1] != 0x6d || file[2] != 0x72 || file[3] != 0x73)
+        return fail("Model not in lm.rs format.");  // src/transformer.rs:135
+    memcpy(&m->args, file + 8, sizeof(lmrs_args_t));
+    lmrs_args_t& a = m->args;
+    if (a.seq_len > 8192) a.seq_len = 8192;  // :158-160
+    if (a.q_type != 1 && a.q_type != 2)
+        return fail("lmrs_b200: only Q8_0 / Q4_0 models are supported on the B200 path (q_type=" + std::to_string(a.q_type) + ")");
+    if (a.model_type > 2) return fail("unknown model_type");
+    if (a.group_size != GS) return fail("lmrs_b200: group_size must be 128 (the exporter always quantizes with 128, utils/io.py:21)");
+    const size_t dim = a.dim, hd = a.hidden_dim, L = a.n_layers, hs = a.head_size;
+    const size_t att_dim = (size_t)a.n_heads * hs, kv_dim = (size_t)a.n_kv_heads * hs;
+    if (dim % GS || hd % GS || att_dim % GS) return fail("dim/hidden_dim/att_dim must be multiples of the group size");
+    if (hs != 64 && hs != 96 && hs != 128 && hs != 256) return fail("unsupported head_size (64/96/128/256)");
+    if (a.n_heads % a.n_kv_heads) return fail("n_heads must be a multiple of n_kv_heads");
+    if (a.model_type == 2 && hs != 96) return fail("PHI requires head_size 96 (48 rope short factors, src/transformer.rs:473)");
+    if (a.vocab_size % 4 || kv_dim % 4) return fail("row counts must be multiples of 4 (src/functional.rs:179)");
+    const int W = m->world, R = m->rank;
+    if (a.n_kv_heads % W || (hd / GS) % W || (a.vocab_size / 4) % W)
+        return fail("world size must divide n_kv_heads, hidden_dim/128 and vocab_size/4");
+    m->l_kv_heads = a.n_kv_heads / W;
+    m->l_heads = a.n_heads / W;
+    m->l_att_dim = m->l_heads * hs;
+    m->l_kv_dim = m->l_kv_heads * hs;
+    m->l_hidden = hd / W;
+    m->l_vocab = a.vocab_size / W;
+    m->vocab_off = R * m->l_vocab;
+    if (W > 1 && (m->l_att_dim % GS)) return fail("sharded att_dim must stay a multiple of 128");
+    const int qdiv = a.q_type == 2 ? 2 : 1;
+
+    // walk the file exactly like src/transformer.rs:241-270
+    size_t off = 256;
+    auto take_q = [&](size_t n_layers, size_t elems, std::vector<FileTensor>& out) -> bool {
+        for (size_t l = 0; l < n_layers; l++) {
+            FileTensor t;
+            t.q_off = off; t.q_bytes = elems / qdiv; off += t.q_bytes;
+            t.s_off = off; t.s_bytes = elems / GS * 4; off += t.s_bytes;
+            if (off > len) return false;
+            out.push_back(t);
+        }
+        return true;
+    };
+    auto take_f = [&](size_t n_layers, size_t elems, std::vector<size_t>& out) -> bool {
+        for (size_t l = 0; l < n_layers; l++) { out.push_back(off); off += elems * 4; if (off > len) return false; }
+        return true;
+    };
+    std::vector<FileTensor> f_emb, f_wq, f_wk, f_wv, f_wo, f_w1, f_w2, f_w3, f_head;
+    std::vector<size_t> f_rms_att, f_rms_post, f_rms_pre, f_rms_postffn, f_rms_final;
+    bool ok = take_q(1, (size_t)a.vocab_size * dim, f_emb) && take_f(L, dim, f_rms_att) &&
+              take_q(L, dim * att_dim, f_wq) && take_q(L, dim * kv_dim, f_wk) && take_q(L, dim * kv_dim, f_wv) &&
+              take_q(L, dim * att_dim, f_wo) && take_f(L, dim, f_rms_post);
+    if (ok && a.model_type == 0) ok = take_f(L, dim, f_rms_pre);
+    ok = ok && take_q(L, dim * hd, f_w1) && take_q(L, dim * hd, f_w2) && take_q(L, dim * hd, f_w3);
+    if (ok && a.model_type == 0) ok = take_f(L, dim, f_rms_postffn);
+    ok = ok && take_f(1, dim, f_rms_final);
+    if (ok && a.model_type == 2) ok = take_q(1, dim * a.vocab_size, f_head);
+    if (!ok) return fail("file truncated");
+    if (end_offset) *end_offset = off;
+
+    // ---- plan the HBM arena: everything 256-byte aligned, QKV rows concatenated per layer --------------------
+    struct Piece { size_t dst; const uint8_t* src; size_t bytes; size_t src_stride, dst_stride, rows; };
+    std::vector<Piece> pieces;
+    size_t cur = 0;
+    auto place = [&](size_t bytes) { size_t o = cur; cur = align_up(cur + bytes, 256); return o; };
+    // rows [r0, r0+nr) of a row-major [o][n] quantized tensor (contiguous)
+    auto add_rows = [&](size_t dst_q, size_t dst_s, const FileTensor& t, size_t n, size_t r0, size_t nr) {
+        pieces.push_back({dst_q, file + t.q_off + r0 * (n / qdiv), nr * (n / qdiv), 0, 0, 1});
+        pieces.push_back({dst_s, file + t.s_off + r0 * (n / GS) * 4, nr * (n / GS) * 4, 0, 0, 1});
+    };
+    // columns [c0, c0+nc) of every row (K-shard for wo / w2): strided gather
+    auto add_cols = [&](size_t dst_q, size_t dst_s, const FileTensor& t, size_t n, size_t o, size_t c0, size_t nc) {
+        pieces.push_back({dst_q, file + t.q_off + c0 / qdiv, nc / qdiv, n / qdiv, nc / qdiv, o});
+        pieces.push_back({dst_s, file + t.s_off + (c0 / GS) * 4, (nc / GS) * 4, (n / GS) * 4, (nc / GS) * 4, o});
+    };
+    struct MatPlan { size_t q, s; int o, n; };
+    auto plan_mat = [&](int o, int n) { MatPlan p; p.o = o; p.n = n; p.q = place((size_t)o * n / qdiv); p.s = place((size_t)o * n / GS * 4); return p; };
+    auto plan_vec = [&](size_t file_off) { size_t d = place(dim * 4); pieces.push_back({d, file + file_off, dim * 4, 0, 0, 1}); return d; };
+
+    struct LayerPlan { MatPlan qkv, wo, w1, w3, w2; size_t rms_att, rms_post, rms_pre, rms_postffn; };
+    std::vector<LayerPlan> lp(L);
+    const size_t la = m->l_att_dim, lk = m->l_kv_dim, lh = m->l_hidden;
+    for (size_t l = 0; l < L; l++) {
+        LayerPlan& P = lp[l];
+        P.qkv = plan_mat((int)(la + 2 * lk), (int)dim);
+        add_rows(P.qkv.q, P.qkv.s, f_wq[l], dim, R * la, la);
+        add_rows(P.qkv.q + la * dim / qdiv, P.qkv.s + la * (dim / GS) * 4, f_wk[l], dim, R * lk, lk);
+        add_rows(P.qkv.q + (la + lk) * dim / qdiv, P.qkv.s + (la + lk) * (dim / GS) * 4, f_wv[l], dim, R * lk, lk);
+        P.wo = plan_mat((int)dim, (int)la);
+        if (W == 1) add_rows(P.wo.q, P.wo.s, f_wo[l], att_dim, 0, dim); else add_cols(P.wo.q, P.wo.s, f_wo[l], att_dim, dim, R * la, la);
+        P.w1 = plan_mat((int)lh, (int)dim);
+        add_rows(P.w1.q, P.w1.s, f_w1[l], dim, R * lh, lh);
+        P.w3 = plan_mat((int)lh, (int)dim);
+        add_rows(P.w3.q, P.w3.s, f_w3[l], dim, R * lh, lh);
+        P.w2 = plan_mat((int)dim, (int)lh);
+        if (W == 1) add_rows(P.w2.q, P.w2.s, f_w2[l], hd, 0, dim); else add_cols(P.w2.q, P.w2.s, f_w2[l], hd, dim, R * lh, lh);
+        P.rms_att = plan_vec(f_rms_att[l]);
+        P.rms_post = plan_vec(f_rms_post[l]);
+        P.rms_pre = a.model_type == 0 ? plan_vec(f_rms_pre[l]) : 0;
+        P.rms_postffn = a.model_type == 0 ? plan_vec(f_rms_postffn[l]) : 0;
+    }
+    MatPlan p_emb = plan_mat((int)a.vocab_size, (int)dim);   // full table on every rank (row gather)
+    add_rows(p_emb.q, p_emb.s, f_emb[0], dim, 0, a.vocab_size);
+    MatPlan p_cls = p_emb;
+    if (a.model_type == 2) {
+        p_cls = plan_mat(m->l_vocab, (int)dim);
+        add_rows(p_cls.q, p_cls.s, f_head[0], dim, m->vocab_off, m->l_vocab);
+    } else if (W > 1) {  // tied classifier: this rank's vocab rows are a sub-range of the table
+        p_cls.o = m->l_vocab;
+        p_cls.q = p_emb.q + (size_t)m->vocab_off * dim / qdiv;
+        p_cls.s = p_emb.s + (size_t)m->vocab_off * (dim / GS) * 4;
+    }
+    size_t rms_final = plan_vec(f_rms_final[0]);
+    m->arena_bytes = cur;
+
+    CK(cudaMalloc(&m->d_arena, m->arena_bytes));
+    for (const Piece& pc : pieces) {
+        if (pc.rows <= 1) CK(cudaMemcpy(m->d_arena + pc.dst, pc.src, pc.bytes, cudaMemcpyHostToDevice));
+        else CK(cudaMemcpy2D(m->d_arena + pc.dst, pc.dst_stride, pc.src, pc.src_stride, pc.bytes, pc.rows, cudaMemcpyHostToDevice));
+    }
+    auto mk = [&](const MatPlan& p) { Mat x; x.q = m->d_arena + p.q; x.s = (const float*)(m->d_arena + p.s); x.o = p.o; x.n = p.n; x.gran = gran_for(p.n); return x; };
+    auto fp = [&](size_t o) { return (const float*)(m->d_arena + o); };
+    m->layers.resize(L);
+    for (size_t l = 0; l < L; l++) {
+        Layer& Y = m->layers[l];
+        Y.qkv = mk(lp[l].qkv); Y.wo = mk(lp[l].wo); Y.w1 = mk(lp[l].w1); Y.w3 = mk(lp[l].w3); Y.w2 = mk(lp[l].w2);
+        Y.rms_att = fp(lp[l].rms_att); Y.rms_post_att = fp(lp[l].rms_post);
+        if (a.model_type == 0) { Y.rms_pre_ffn = fp(lp[l].rms_pre); Y.rms_post_ffn = fp(lp[l].rms_postffn); }
+    }
+    m->emb = mk(p_emb);
+    m->cls = mk(p_cls);
+    m->rms_final = fp(rms_final);
+    for (const Layer& Y : m->layers)
+        for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
+            if (x->o % x->gran) return fail("row count not divisible by the stream granularity");
+    if (m->cls.o % m->cls.gran) return fail("vocab shard not divisible by the stream granularity");
+
+    // ---- state: f32 KV cache (src/transformer.rs:302-303), RoPE tables, activations ---------------------------
+    const size_t kv_elems = L * (size_t)a.seq_len * lk;
+    CK(cudaMalloc(&m->d_kcache, kv_elems * 4));
+    CK(cudaMalloc(&m->d_vcache, kv_elems * 4));
+    CK(cudaMemset(m->d_kcache, 0, kv_elems * 4));
+    CK(cudaMemset(m->d_vcache, 0, kv_elems * 4));
+    {
+        std::vector<float> cs((size_t)a.seq_len * (hs / 2)), sn((size_t)a.seq_len * (hs / 2));
+        for (size_t j = 0; j < hs / 2; j++) {
+            float freq, ms;
+            rope_freq(a.model_type, a.rope_theta, (int)hs, (int)j, &freq, &ms);
+            for (size_t p = 0; p < a.seq_len; p++) {
+                volatile float val = (float)(uint32_t)p * freq;       // :480
+                volatile float c = cosf(val), s = sinf(val);
+                cs[p * (hs / 2) + j] = c * ms;                        // :481-482
+                sn[p * (hs / 2) + j] = s * ms;
+            }
+        }
+        CK(cudaMalloc(&m->d_rope_cos, cs.size() * 4));
+        CK(cudaMalloc(&m->d_rope_sin, sn.size() * 4));
+        CK(cudaMemcpy(m->d_rope_cos, cs.data(), cs.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(m->d_rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
+    }
+    m->att_chunks = (a.n_heads / a.n_kv_heads + ATT_QH - 1) / ATT_QH;
+    {
+        int target = m->sms / (m->l_kv_heads * m->att_chunks);
+        int ns = 1;
+        while (ns * 2 <= target && ns < 32) ns *= 2;
+        m->nsplit = env_int("LMRS_B200_NSPLIT", ns);
+    }
+    CK(cudaMalloc(&m->d_x[0], dim * 4));
+    CK(cudaMalloc(&m->d_x[1], dim * 4));
+    CK(cudaMalloc(&m->d_q, la * 4));
+    CK(cudaMalloc(&m->d_knew, lk * 4));
+    CK(cudaMalloc(&m->d_att, la * 4));
+    CK(cudaMalloc(&m->d_wo_out, dim * 4));
+    CK(cudaMalloc(&m->d_h, lh * 4));
+    CK(cudaMalloc(&m->d_down_out, dim * 4));
+    CK(cudaMalloc(&m->d_logits, (size_t)a.vocab_size * 4));
+    CK(cudaMalloc(&m->d_part, (size_t)m->l_heads * m->nsplit * (hs + 2) * 4));
+    CK(cudaMalloc(&m->d_tickets, (size_t)m->l_kv_heads * m->att_chunks * 4));
+    CK(cudaMemset(m->d_tickets, 0, (size_t)m->l_kv_heads * m->att_chunks * 4));
+    CK(cudaMalloc(&m->d_step, sizeof(StepParams)));
+    CK(cudaMallocHost(&m->h_step_ring, sizeof(StepParams) * 64));
+    CK(cudaMallocHost(&m->h_logits, (size_t)a.vocab_size * 4));
+    CK(cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking));
+    m->stream = m->own_stream;
+    return 0;
+}
+
+// ---- one transformer block, decode shape (src/transformer.rs:388-657 with sl = 1) ---------------------------
+static int enqueue_layers(lmrs_b200* m, bool with_classifier, float* finalize_rows) {
+    const lmrs_args_t& a = m->args;
+    const int qt = a.q_type;
+    const bool gemma = a.model_type == 0;
+    const size_t L = a.n_layers;
+    const float* delta = nullptr;       // pending residual contribution
+    const float* w_post = nullptr;      // Gemma: norm applied to it before the add
+    for (size_t l = 0; l < L; l++) {
+        const Layer& Y = m->layers[l];
+        float* kc = m->d_kcache + l * (size_t)a.seq_len * m->l_kv_dim;
+        float* vc = m->d_vcache + l * (size_t)a.seq_len * m->l_kv_dim;
+        {   // x(+delta) -> rmsnorm(w_rms_att) -> quantize -> [Wq;Wk;Wv]   (:409-431)
+            GemvParams p = gemv_base(Y.qkv, nullptr);
+            p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
+            p.x_out = m->d_x[1]; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
+            p.epi = EPI_QKV; p.out = m->d_q; p.out_k = m->d_knew; p.out_v = vc;
+            p.att_dim = m->l_att_dim; p.kv_dim = m->l_kv_dim; p.step = m->d_step;
+            CK(launch_gemv(m, qt, p));
+        }
+        {   // RoPE + attention (:443-544)
+            AttnParams p{};
+            p.q = m->d_q; p.k_new = m->d_knew; p.kcache = kc; p.vcache = vc;
+            p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = m->d_att; p.part = m->d_part;
+            p.tickets = m->d_tickets; p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
+            p.nsplit = m->nsplit; p.chunks = m->att_chunks; p.gemma = gemma;
+            p.inv_sqrt_hs_den = sqrtf((float)a.head_size); p.step = m->d_step;
+            CK(launch_attn(m, p, m->l_kv_heads));
+        }
+        {   // quantize(att) -> Wo (:546-560)
+            GemvParams p = gemv_base(Y.wo, nullptr);
+            p.pro = PRO_QUANT; p.act_in = m->d_att; p.epi = EPI_STORE; p.out = m->d_wo_out;
+            CK(launch_gemv(m, qt, p));
+            if (m->world > 1) { if (shard_allreduce(m->shard, m->d_wo_out, a.dim, m->stream)) return fail(shard_error()); m->launches++; }
+        }
+        {   // x += wo_out (Gemma: normed) -> rmsnorm -> quantize -> gate/up -> act*up (:562-624)
+            GemvParams p = gemv_base(Y.w1, &Y.w3);
+            p.pro = PRO_NORM; p.x_in = m->d_x[1]; p.delta = m->d_wo_out; p.w_post = gemma ? Y.rms_post_att : nullptr;
+            p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_x[0]; p.eps = a.rms_norm_eps;
+            p.unit_offset = gemma; p.epi = gemma ? EPI_GLU_GELU : EPI_GLU_SILU; p.out = m->d_h;
+            CK(launch_gemv(m, qt, p));
+        }
+        {   // quantize(hidden) -> W2 (:626-640)
+            GemvParams p = gemv_base(Y.w2, nullptr);
+            p.pro = PRO_QUANT; p.act_in = m->d_h; p.epi = EPI_STORE; p.out = m->d_down_out;
+            CK(launch_gemv(m, qt, p));
+            if (m->world > 1) { if (shard_allreduce(m->shard, m->d_down_out, a.dim, m->stream)) return fail(shard_error()); m->launches++; }
+        }
+        delta = m->d_down_out;
+        w_post = gemma ? Y.rms_post_ffn : nullptr;   // (:642-656) applied by the next prologue
+    }
+    if (with_classifier) {   // final rmsnorm + classifier (:343-371) + Gemma soft-cap quirk (:375-381)
+        GemvParams p = gemv_base(m->cls, nullptr);
+        p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = m->rms_final;
+        p.x_out = nullptr; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
+        p.epi = EPI_LOGITS; p.out = m->d_logits + m->vocab_off;
+        int cap = gemma ? (int)a.dim - m->vocab_off : 0;
+        p.softcap_rows = cap < 0 ? 0 : (cap > m->l_vocab ? m->l_vocab : cap);
+        CK(launch_gemv(m, qt, p));
+        if (m->world > 1) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
+    }
+    if (finalize_rows) {     // fill_kv_cache returns the residual stream: apply the pending add (:642-656)
+        ResidualParams p{};
+        p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.n = a.dim; p.eps = a.rms_norm_eps;
+        p.rows = finalize_rows; p.step = m->d_step;
+        CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, p));
+    }
+    return 0;
+}
+
+static int enqueue_embed(lmrs_b200* m, const float* rows_src) {
+    const lmrs_args_t& a = m->args;
+    EmbedParams p{};
+    p.dim = a.dim; p.step = m->d_step; p.out = m->d_x[0]; p.tokens = nullptr;
+    if (rows_src) { p.q_type = 0; p.f32_table = rows_src; p.apply_scale = 0; }   // prefill: row `token` of the staged embeddings
+    else {
+        p.q_type = a.q_type; p.q = m->emb.q; p.s = m->emb.s;
+        p.apply_scale = a.model_type == 0; p.scale_mul = sqrtf((float)a.dim);      // :327-332
+    }
+    CK(launch(m, embed_kernel, dim3(1), dim3(256), 0, p));
+    return 0;
+}
+
+// build (once) and replay the whole decode step as a CUDA graph; kernels keep their PDL edges inside it
+static int run_graph(lmrs_b200* m, cudaGraphExec_t* exec, cudaStream_t* built_on, int* n_kernels, bool decode) {
+    if (!m->use_graph) {
+        if (enqueue_embed(m, decode ? nullptr : m->d_rows)) return 1;
+        return enqueue_layers(m, decode, decode ? nullptr : m->d_rows);
+    }
+    if (!*exec || *built_on != m->stream) {
+        if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
+        cudaGraph_t graph;
+        uint64_t before = m->launches;
+        CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_embed(m, decode ? nullptr : m->d_rows);
+        if (!rc) rc = enqueue_layers(m, decode, decode ? nullptr : m->d_rows);
+        cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
+        if (rc) return 1;
+        if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        *n_kernels = (int)(m->launches - before);
+        m->launches = before;
+        CK(cudaGraphInstantiate(exec, graph, 0));
+        CK(cudaGraphDestroy(graph));
+        *built_on = m->stream;
+    }
+    CK(cudaGraphLaunch(*exec, m->stream));
+    m->launches += *n_kernels;
+    return 0;
+}
+
+static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_base) {
+    if (m->step_slot == 64) { CK(cudaStreamSynchronize(m->stream)); m->step_slot = 0; }
+    StepParams* s = &m->h_step_ring[m->step_slot++];
+    s->token = token; s->pos = pos; s->mask_base = mask_base; s->pad = 0;
+    CK(cudaMemcpyAsync(m->d_step, s, sizeof(StepParams), cudaMemcpyHostToDevice, m->stream));
+    return 0;
+}
+
+// fill_kv_cache, first implementation: the decode-shaped block chain once per token.  For LLAMA/PHI this is
+// mathematically the reference's batched forward_layer (every token attends to positions <= its own, whose
+// K/V are identical in both schedules); the Gemma window quirk is reproduced through mask_base.
+static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
+    for (size_t i = 0; i < n; i++) {
+        if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos)) return 1;
+        if (run_graph(m, &m->g_prefill, &m->g_prefill_stream, &m->n_prefill_kernels, false)) return 1;
+    }
+    return 0;
+}
+
+// ---- C ABI -----------------------------------------------------------------------------------------------
+static int create_common(const uint8_t* file, size_t len, int device, int rank, int world, const void* nccl_id,
+                         lmrs_b200_t** out, size_t* end_offset) {
+    if (!file || !out) return fail("null argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("lmrs_b200: no CUDA device available (this library has no CPU fallback)");
+    if (device < 0) CK(cudaGetDevice(&device));
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(std::string("lmrs_b200: device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                    "; this library contains sm_100a code only");
+    lmrs_b200* m = new lmrs_b200();
+    m->device = device;
+    m->sms = prop.multiProcessorCount;
+    m->rank = rank; m->world = world;
+    m->use_graph = env_int("LMRS_B200_GRAPH", 1) != 0;
+    m->use_pdl = env_int("LMRS_B200_PDL", 1) != 0;
+    m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 0);
+    if (m->gemv_cfg < 0 || m->gemv_cfg > 4) m->gemv_cfg = 0;
+    m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
+    if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
+    if ((int)m->args.dim > NORM_MAXC * 4 * kGemvCfgs[m->gemv_cfg].warps * 32) {
+        lmrs_b200_destroy(m);
+        return fail("dim too large for the fused norm prologue of this GEMV configuration");
+    }
+    if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
+    *out = m;
+    return 0;
+}
+
+extern "C" int lmrs_b200_create(const uint8_t* file, size_t len, int device, lmrs_b200_t** out, size_t* end_offset) {
+    return create_common(file, len, device, 0, 1, nullptr, out, end_offset);
+}
+extern "C" int lmrs_b200_create_sharded(const uint8_t* file, size_t len, int device, int rank, int world,
+                                        const void* nccl_unique_id, lmrs_b200_t** out, size_t* end_offset) {
+    if (world < 1 || rank < 0 || rank >= world) return fail("bad rank/world");
+    if (world > 1 && !nccl_unique_id) return fail("nccl_unique_id required when world > 1");
+    return create_common(file, len, device, rank, world, nccl_unique_id, out, end_offset);
+}
+extern "C" int lmrs_b200_nccl_unique_id(void* out128) {
+    if (shard_unique_id(out128)) return fail(shard_error());
+    return 0;
+}
+
+extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->own_stream) cudaStreamSynchronize(m->own_stream);
+    if (m->g_decode) cudaGraphExecDestroy(m->g_decode);
+    if (m->g_prefill) cudaGraphExecDestroy(m->g_prefill);
+    shard_destroy(m->shard);
+    cudaFree(m->d_arena); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
+    cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
+    cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_part);
+    cudaFree(m->d_tickets); cudaFree(m->d_step); cudaFree(m->d_rows);
+    if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
+    if (m->h_logits) cudaFreeHost(m->h_logits);
+    if (m->own_stream) cudaStreamDestroy(m->own_stream);
+    delete m;
+}
+
+extern "C" int lmrs_b200_args(const lmrs_b200_t* m, lmrs_args_t* out) {
+    if (!m || !out) return fail("null argument");
+    *out = m->args;
+    return 0;
+}
+
+extern "C" int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t pos) {
+    if (!m) return fail("null handle");
+    if (token >= m->args.vocab_size) return fail("token out of range");
+    if (pos >= m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
+    CK(cudaSetDevice(m->device));
+    if (push_step(m, token, pos, pos)) return 1;
+    return run_graph(m, &m->g_decode, &m->g_decode_stream, &m->n_decode_kernels, true);
+}
+
+extern "C" int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, float** logits_host) {
+    if (!logits_host) return fail("null argument");
+    if (lmrs_b200_forward_device(m, token, pos)) return 1;
+    CK(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t)m->args.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *logits_host = m->h_logits;
+    return 0;
+}
+
+extern "C" int lmrs_b200_logits_device(lmrs_b200_t* m, float** logits_dev) {
+    if (!m || !logits_dev) return fail("null argument");
+    *logits_dev = m->d_logits;
+    return 0;
+}
+extern "C" int lmrs_b200_set_stream(lmrs_b200_t* m, void* s) {
+    if (!m) return fail("null handle");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    m->stream = s ? (cudaStream_t)s : m->own_stream;
+    return 0;
+}
+extern "C" int lmrs_b200_synchronize(lmrs_b200_t* m) {
+    if (!m) return fail("null handle");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    return 0;
+}
+extern "C" int lmrs_b200_kernel_launches(const lmrs_b200_t* m, uint64_t* count) {
+    if (!m || !count) return fail("null argument");
+    *count = m->launches;
+    return 0;
+}
+
+extern "C" int lmrs_b200_get_embeddings(const lmrs_b200_t* cm, const uint32_t* tokens, size_t n, float* out) {
+    lmrs_b200* m = const_cast<lmrs_b200*>(cm);
+    if (!m || !tokens || !out) return fail("null argument");
+    if (n == 0) return 0;
+    for (size_t i = 0; i < n; i++)
+        if (tokens[i] >= m->args.vocab_size) return fail("token out of range");
+    CK(cudaSetDevice(m->device));
+    uint32_t* d_tok; float* d_out;
+    CK(cudaMalloc(&d_tok, n * 4));
+    CK(cudaMalloc(&d_out, n * (size_t)m->args.dim * 4));
+    CK(cudaMemcpyAsync(d_tok, tokens, n * 4, cudaMemcpyHostToDevice, m->stream));
+    EmbedParams p{};
+    p.dim = m->args.dim; p.q_type = m->args.q_type; p.q = m->emb.q; p.s = m->emb.s; p.apply_scale = 0;   // :659-669: no Gemma scaling
+    p.tokens = d_tok; p.step = m->d_step; p.out = d_out;
+    bool pdl = m->use_pdl; m->use_pdl = false;
+    cudaError_t e = launch(m, embed_kernel, dim3((unsigned)n), dim3(256), 0, p);
+    m->use_pdl = pdl;
+    CK(e);
+    CK(cudaMemcpyAsync(out, d_out, n * (size_t)m->args.dim * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    cudaFree(d_tok); cudaFree(d_out);
+    return 0;
+}
+
+extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floats, uint32_t pos, uint32_t* new_pos) {
+    if (!m || !emb || !new_pos) return fail("null argument");
+    const size_t dim = m->args.dim;
+    const size_t n = n_floats / dim;
+    if (pos + n > m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
+    if (n > 1 && (size_t)m->args.n_heads * m->args.head_size < dim)
+        return fail("sl>1 with att_dim<dim is out of bounds in the reference (src/transformer.rs:501-503)");
+    CK(cudaSetDevice(m->device));
+    if (n == 0) { *new_pos = pos; return 0; }
+    if (m->rows_cap < n * dim) {
+        cudaFree(m->d_rows);
+        m->d_rows = nullptr;
+        CK(cudaMalloc(&m->d_rows, n * dim * 4));
+        m->rows_cap = n * dim;
+        if (m->g_prefill) { cudaGraphExecDestroy(m->g_prefill); m->g_prefill = nullptr; }
+    }
+    CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));
+    if (prefill_batched(m, n, pos)) return 1;
+    CK(cudaMemcpyAsync(emb, m->d_rows, n * dim * 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *new_pos = pos + (uint32_t)n;
+    return 0;
+}
+
+extern "C" int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out) {
+    if (!m || !k_out || !v_out) return fail("null argument");
+    if (layer >= m->args.n_layers || pos0 + n > m->args.seq_len) return fail("out of range");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    size_t base = ((size_t)layer * m->args.seq_len + pos0) * m->l_kv_dim;
+    CK(cudaMemcpy(k_out, m->d_kcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v_out, m->d_vcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+#include "ops_abi.inc"

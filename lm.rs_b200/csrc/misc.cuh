@@ -1,0 +1,95 @@
+// misc.cuh -- small kernels around the hot path: pending-residual finalize for fill_kv_cache and the
+// stand-alone operator kernels behind the operator-level C ABI (quantize / rmsnorm / softmax).
+#pragma once
+#include "common.cuh"
+#include "gemv.cuh"
+
+namespace lmrs {
+
+// x_row = x_in + delta  (Gemma: + rmsnorm(delta, w_post) with unit offset) -- the residual add that closes a
+// transformer block (src/transformer.rs:642-656); in the decode chain it is folded into the next GEMV prologue,
+// fill_kv_cache needs it materialised because the caller gets the residual stream back (:678).
+struct ResidualParams {
+    const float* x_in; const float* delta; const float* w_post;
+    int n; float eps;
+    float* rows;               // [n_rows][n]; row index = step->token
+    const StepParams* step;
+};
+__global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualParams p) {
+    __shared__ float red[32];
+    pdl_launch_dependents();
+    pdl_wait();
+    float* out = p.rows + (size_t)p.step->token * p.n;
+    float r = 1.0f;
+    if (p.w_post) {
+        float ss = 0.0f;
+        for (int i = threadIdx.x; i < p.n; i += 256) ss += p.delta[i] * p.delta[i];
+        ss = block_sum<8>(ss, red);
+        ss = __fadd_rn(__fdiv_rn(ss, (float)p.n), p.eps);
+        r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+    }
+    for (int i = threadIdx.x; i < p.n; i += 256) {
+        float d = p.delta[i];
+        if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
+        out[i] = __fadd_rn(p.x_in[i], d);
+    }
+}
+
+// ---- operator-level kernels (any group size; one thread walks one group serially like the reference) -------
+// src/quantization.rs:44-67
+__global__ void quantize_q8_kernel(int8_t* q, float* s, const float* x, int n_groups, int gs) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const float* xg = x + (size_t)g * gs;
+    float wmax = 0.0f;
+    for (int i = 0; i < gs; i++) wmax = fmaxf(wmax, fabsf(xg[i]));
+    const float scale = __fdiv_rn(wmax, 127.0f);
+    s[g] = scale;
+    for (int i = 0; i < gs; i++) q[(size_t)g * gs + i] = (int8_t)round_sat_i8(__fdiv_rn(xg[i], scale));
+}
+// src/quantization.rs:69-95
+__global__ void quantize_q4_kernel(uint8_t* q, float* s, const float* x, int n_groups, int gs) {
+    int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const float* xg = x + (size_t)g * gs;
+    float wmax = 0.0f;
+    for (int i = 0; i < gs; i++) wmax = fmaxf(wmax, fabsf(xg[i]));
+    const float scale = __fdiv_rn(wmax, -8.0f);
+    s[g] = scale;
+    for (int i = 0; i < gs / 2; i++) {
+        int a = round_sat_u4(__fdiv_rn(xg[2 * i], scale)), b = round_sat_u4(__fdiv_rn(xg[2 * i + 1], scale));
+        q[(size_t)g * gs / 2 + i] = (uint8_t)(a | (b << 4));
+    }
+}
+// src/functional.rs:48-78 (single CTA; the sum of squares is a tree reduction: tolerance-level vs the reference)
+__global__ void __launch_bounds__(256) rmsnorm_kernel(float* o, const float* x, const float* w, int size, float eps, int unit) {
+    __shared__ float red[32];
+    const int n8 = size / 8 * 8;
+    float ss = 0.0f;
+    for (int i = threadIdx.x; i < n8; i += 256) ss += x[i] * x[i];
+    ss = block_sum<8>(ss, red);
+    ss = __fadd_rn(__fdiv_rn(ss, (float)size), eps);
+    const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+    for (int i = threadIdx.x; i < n8; i += 256) {
+        const float t = __fmul_rn(r, x[i]);
+        o[i] = unit ? __fmul_rn(__fadd_rn(1.0f, w[i]), t) : __fmul_rn(w[i], t);
+    }
+}
+// src/functional.rs:122-140
+__global__ void __launch_bounds__(256) softmax_kernel(float* x, int n) {
+    __shared__ float red[32];
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, x[i]);
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = red[0];
+    for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
+    __syncthreads();
+    float sum = 0.0f;
+    for (int i = threadIdx.x; i < n; i += 256) { float e = expf(x[i] - mx); x[i] = e; sum += e; }
+    sum = block_sum<8>(sum, red);
+    for (int i = threadIdx.x; i < n; i += 256) x[i] = __fdiv_rn(x[i], sum);
+}
+
+}  // namespace lmrs

@@ -1,0 +1,121 @@
+"""Model-level parity on the GPU: Transformer.{new, forward, get_embeddings, fill_kv_cache} through the C ABI
+against the CPU oracle on identical synthetic LMRS files and prompts.
+
+Tolerance: BASELINE.json north_star -- logits within 1e-3 max-abs of the CPU path on identical prompts."""
+import numpy as np
+import pytest
+
+from conftest import prompt_tokens
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-3
+
+TINY = [("tiny-llama", 1), ("tiny-llama", 2), ("tiny-gemma", 1), ("tiny-gemma", 2), ("tiny-gemma-narrow", 1),
+        ("tiny-phi", 1), ("tiny-phi", 2), ("small-llama", 1)]
+
+
+@pytest.mark.parametrize("name,q_type", TINY)
+def test_forward_logits_match_oracle(gpu_lib, ref, synth, name, q_type):
+    buf = synth(name, q_type)
+    cpu = ref.RefTransformer(buf)
+    gpu, end = gpu_lib.Transformer.new(buf)
+    assert end == cpu.end_offset == buf.size
+    assert bytes(gpu.args) == bytes(cpu.args)
+    toks = prompt_tokens(gpu.args.vocab_size, 24)
+    worst = 0.0
+    for pos, t in enumerate(toks):
+        lg = gpu.forward(int(t), pos)
+        le = cpu.forward(int(t), pos)
+        assert np.isfinite(lg).all()
+        worst = max(worst, float(np.abs(lg - le).max()))
+        assert int(np.argmax(lg)) == int(np.argmax(le)) or worst < TOL
+    assert worst <= TOL, f"max-abs logits diff {worst}"
+    # KV cache: V rows bit-exact chain is not guaranteed (norm reductions), so tolerance
+    kc, vc = cpu.kv_cache()
+    for l in range(gpu.args.n_layers):
+        k, v = gpu.read_kv(l, 0, len(toks))
+        np.testing.assert_allclose(k, kc[l, :len(toks)], atol=TOL, rtol=0)
+        np.testing.assert_allclose(v, vc[l, :len(toks)], atol=TOL, rtol=0)
+    gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name,q_type", [("tiny-llama", 1), ("tiny-gemma", 1), ("tiny-phi", 2)])
+def test_get_embeddings_bit_exact(gpu_lib, ref, synth, name, q_type):
+    buf = synth(name, q_type)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    toks = prompt_tokens(gpu.args.vocab_size, 9)
+    assert np.array_equal(gpu.get_embeddings(toks), cpu.get_embeddings(toks))
+    assert gpu.get_embeddings(np.zeros(0, np.uint32)).size == 0
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu.get_embeddings([gpu.args.vocab_size])
+
+
+@pytest.mark.parametrize("name,q_type", [("tiny-llama", 1), ("tiny-gemma", 1), ("tiny-phi", 1), ("tiny-llama", 2)])
+def test_fill_kv_cache_then_decode(gpu_lib, ref, synth, name, q_type):
+    """The multimodal path of the bins: get_embeddings ++ features -> fill_kv_cache -> forward (chat.rs:110-119)."""
+    buf = synth(name, q_type)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    # 3 decode steps first so the batch starts at pos 3 (exercises pos offset and the Gemma mask_base quirk)
+    for pos, t in enumerate([5, 6, 7]):
+        gpu.forward(t, pos); cpu.forward(t, pos)
+    toks = prompt_tokens(gpu.args.vocab_size, 17, seed=3)
+    eg, ec = gpu.get_embeddings(toks), cpu.get_embeddings(toks)
+    pg, pc = gpu.fill_kv_cache(eg, 3), cpu.fill_kv_cache(ec, 3)
+    assert pg == pc == 20
+    np.testing.assert_allclose(eg, ec, atol=TOL, rtol=1e-4)      # residual stream returned in place
+    lg, le = gpu.forward(11, pg), cpu.forward(11, pc)
+    assert float(np.abs(lg - le).max()) <= TOL
+
+
+def test_errors_where_the_reference_panics(gpu_lib, synth):
+    buf = synth("tiny-llama", 1)
+    bad = buf.copy(); bad[0] = 0
+    with pytest.raises(gpu_lib.LmrsError, match="lm.rs format"):
+        gpu_lib.Transformer.new(bad)
+    with pytest.raises(gpu_lib.LmrsError, match="truncated"):
+        gpu_lib.Transformer.new(buf[: buf.size // 2])
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu.forward(gpu.args.vocab_size, 0)
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu.forward(0, gpu.args.seq_len)
+
+
+def test_seq_len_clamped_to_8192(gpu_lib, lf):
+    a = lf.model_args("tiny-llama", 1, seq_len=131072)
+    gpu, _ = gpu_lib.Transformer.new(lf.write_synthetic(a))
+    assert gpu.args.seq_len == 8192      # src/transformer.rs:158-160
+
+
+def test_two_handles_are_independent(gpu_lib, ref, synth):
+    """backend.rs creates one Transformer per connection (src/bin/backend.rs:87-110)."""
+    buf = synth("tiny-llama", 1)
+    a, _ = gpu_lib.Transformer.new(buf)
+    b, _ = gpu_lib.Transformer.new(buf)
+    cpu = ref.RefTransformer(buf)
+    la0 = a.forward(3, 0).copy()
+    lb0 = b.forward(9, 0).copy()
+    la1 = a.forward(4, 1).copy()
+    e0 = cpu.forward(3, 0).copy(); e1 = cpu.forward(4, 1).copy()
+    assert np.abs(la0 - e0).max() <= TOL and np.abs(la1 - e1).max() <= TOL
+    assert not np.array_equal(la0, lb0)
+
+
+def test_llama_1b_q8_full_shape(gpu_lib, ref, lf):
+    """BASELINE config 2 shape (Llama-3.2-1B Q8_0, synthetic weights): logits within 1e-3 at a few positions, incl.
+    after a 96-embedding fill_kv_cache."""
+    buf = lf.write_synthetic(lf.model_args("llama-3.2-1b", 1), seed=0, mode="fast")
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    toks = prompt_tokens(gpu.args.vocab_size, 100, seed=1)
+    eg, ec = gpu.get_embeddings(toks[:96]), cpu.get_embeddings(toks[:96])
+    assert np.array_equal(eg, ec)
+    pg, pc = gpu.fill_kv_cache(eg, 0), cpu.fill_kv_cache(ec, 0)
+    assert pg == pc == 96
+    worst = 0.0
+    for i, t in enumerate(toks[96:]):
+        lg, le = gpu.forward(int(t), 96 + i), cpu.forward(int(t), 96 + i)
+        worst = max(worst, float(np.abs(lg - le).max()))
+    assert worst <= TOL, f"max-abs logits diff {worst}"

@@ -1,0 +1,100 @@
+"""GPU operator parity (through the C ABI) against the CPU oracle.
+
+Bars: integer/byte results and the two quantized matmuls are BIT-EXACT (the kernels reproduce the reference's
+f32 operation order); rmsnorm/softmax use tree reductions -> tolerance written in each test."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+class QT:
+    def __init__(self, q, s):
+        self.q, self.s = q, s
+
+
+def _rand_q8(rng, rows, n, scale):
+    q = rng.integers(-127, 128, size=rows * n, dtype=np.int8)
+    s = (rng.uniform(0.5, 1.5, rows * n // 128) * scale).astype(np.float32)
+    return q, s
+
+
+@pytest.mark.parametrize("n,o,rows", [(128, 4, 1), (256, 8, 1), (2048, 2048, 1), (2048, 512, 2), (8192, 2048, 1),
+                                      (3072, 1024, 1), (2304, 64, 1), (3584, 4096, 1), (2048, 3072, 3),
+                                      (14336, 256, 1), (384, 128256 // 32, 1)])
+def test_matmul_q8_bit_exact(gpu_lib, ref, n, o, rows):
+    rng = np.random.default_rng(n * 7 + o)
+    xq, xs = _rand_q8(rng, rows, n, 0.01)
+    wq, ws = _rand_q8(rng, o, n, 0.002)
+    exp = ref.matmul_q8(xq, xs, wq, ws, rows, n, o, 128)
+    got = np.full(rows * o, np.nan, np.float32)
+    gpu_lib.functional.matmul_q8(got, QT(xq, xs), QT(wq, ws), n, o, 128)
+    assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
+
+
+@pytest.mark.parametrize("n,o,rows", [(128, 4, 1), (256, 8, 1), (3072, 3072, 1), (8192, 3072, 1), (3072, 1024, 2),
+                                      (2304, 64, 1), (2048, 2048, 1)])
+def test_matmul_q4_bit_exact(gpu_lib, ref, n, o, rows):
+    rng = np.random.default_rng(n * 11 + o)
+    xq = rng.integers(0, 256, size=rows * n // 2, dtype=np.uint8)
+    xs = (-rng.uniform(0.5, 1.5, rows * n // 128) * 0.1).astype(np.float32)   # runtime scales are negative (max/-8)
+    wq = rng.integers(0, 256, size=o * n // 2, dtype=np.uint8)
+    ws = (-rng.uniform(0.5, 1.5, o * n // 128) * 0.02).astype(np.float32)
+    exp = ref.matmul_q4(xq, xs, wq, ws, rows, n, o, 128)
+    got = np.full(rows * o, np.nan, np.float32)
+    gpu_lib.functional.matmul_q4(got, QT(xq, xs), QT(wq, ws), n, o, 128)
+    assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
+
+
+def test_matmul_rejects_bad_shapes(gpu_lib):
+    out = np.zeros(4, np.float32)
+    z8, zf = np.zeros(128, np.int8), np.zeros(1, np.float32)
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu_lib.functional.matmul_q8(out, QT(z8, zf), QT(np.zeros(512, np.int8), np.zeros(4, np.float32)), 128, 4, 64)
+    with pytest.raises(gpu_lib.LmrsError):   # o % 4 != 0: the reference silently drops rows (functional.rs:179); we refuse
+        gpu_lib.functional.matmul_q8(np.zeros(3, np.float32), QT(z8, zf), QT(np.zeros(384, np.int8), np.zeros(3, np.float32)), 128, 3, 128)
+
+
+@pytest.mark.parametrize("gs", [8, 32, 128])
+def test_quantize_q8_bit_exact(gpu_lib, ref, gs):
+    rng = np.random.default_rng(gs)
+    x = (rng.standard_normal(gs * 257) * 3).astype(np.float32)
+    x[gs:2 * gs] = 0.0                                  # all-zero group: scale 0, NaN -> 0 (quantization.rs:57-64)
+    x[2 * gs:2 * gs + 8] = [127, -127, 63.5, -63.5, 0.5, -0.5, 2.5, 0]   # half-away-from-zero ties
+    eq, es = ref.quantize_q8(x, gs)
+    q = gpu_lib.quantization.QuantizedTensor(np.zeros(x.size, np.int8), np.zeros(x.size // gs, np.float32))
+    gpu_lib.quantization.quantize(q, x, x.size, gs)
+    assert np.array_equal(q.q, eq) and np.array_equal(q.s.view(np.uint32), es.view(np.uint32))
+
+
+@pytest.mark.parametrize("gs", [8, 32, 128])
+def test_quantize_q4_bit_exact(gpu_lib, ref, gs):
+    rng = np.random.default_rng(gs + 1)
+    x = (rng.standard_normal(gs * 129) * 2).astype(np.float32)
+    x[gs:2 * gs] = 0.0
+    x[2 * gs:2 * gs + 8] = [8, -8, 4, -4, 0, 1, -1, 7.5]
+    eq, es = ref.quantize_q4(x, gs)
+    q = gpu_lib.quantization.QuantizedTensor(np.zeros(x.size // 2, np.uint8), np.zeros(x.size // gs, np.float32))
+    gpu_lib.quantization.quantize_q4(q, x, x.size, gs)
+    assert np.array_equal(q.q, eq) and np.array_equal(q.s.view(np.uint32), es.view(np.uint32))
+
+
+@pytest.mark.parametrize("size,unit", [(256, False), (2048, False), (3584, True), (4096, True)])
+def test_rmsnorm(gpu_lib, ref, size, unit):
+    rng = np.random.default_rng(size)
+    x = rng.standard_normal(size).astype(np.float32) * 3
+    w = (1 + 0.1 * rng.standard_normal(size)).astype(np.float32)
+    exp = ref.rmsnorm(x, w, 1e-5, unit)
+    got = np.zeros(size, np.float32)
+    gpu_lib.functional.rmsnorm(got, x, w, size, 1e-5, unit)
+    # tree reduction vs 8-lane partial sums: the sum of squares differs by a few ulp -> 1e-6 relative
+    np.testing.assert_allclose(got, exp, rtol=2e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("n", [1, 7, 513, 8192])
+def test_softmax(gpu_lib, ref, n):
+    x = (np.random.default_rng(n).standard_normal(n) * 4).astype(np.float32)
+    exp = ref.softmax(x)
+    got = x.copy()
+    gpu_lib.functional.softmax(got)
+    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-9)   # expf 2 ulp + parallel sum
