@@ -86,6 +86,10 @@ int lmrs_b200_synchronize(lmrs_b200_t* m);
 int lmrs_b200_kernel_launches(const lmrs_b200_t* m, uint64_t* count);
 /* test access: copy K and V rows [pos0, pos0+n) of one layer to host (f32 [n][kv_dim] each) */
 int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out);
+/* test access: copy one activation buffer of the LAST executed block to host.  name: "x0","x1" (residual
+ * ping-pong, dim), "q" (un-rotated, att_dim), "k_new" (kv_dim), "att" (att_dim), "wo_out" (dim), "h"
+ * (hidden_dim), "down_out" (dim).  Returns the element count through *n (capacity in, count out). */
+int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* out, size_t* n);
 
 /* ---- operator level: the free functions vision.rs / processor.rs import (src/vision.rs:1-3,
  * src/processor.rs:1-3).  Host pointers in and out; each call stages through HBM and runs the same

@@ -1,24 +1,20 @@
 // attention.cuh -- decode-step attention for sm_100a: RoPE + QK^T + soft-cap/window + softmax + .V in ONE
 // kernel over the HBM-resident f32 KV cache.  Replaces src/transformer.rs:443-544 for sl = 1.
 //
-// Grid (n_kv_heads * head_chunks, NSPLIT): a CTA serves up to 4 query heads that share one KV head (GQA:
-// K/V rows are read once for all of them) over one slice of the cached positions (split-T, flash-decoding
-// style); the last CTA to finish a KV head merges the slices (threadfence + atomic ticket), so no second
-// kernel is needed.  RoPE uses cos/sin tables computed at load time on the HOST with the same libm calls as
-// the reference (powf/cosf/sinf, src/transformer.rs:447-482), so rotated q/k are bit-identical given
-// bit-identical inputs.  The new K row arrives un-rotated in a staging row (written by the QKV GEMV); every
-// CTA that needs position `pos` rotates it locally, and exactly one CTA per KV head stores the rotated row
-// into the cache (no read/write race between CTAs).
-// Softmax / A.V use a parallel, online formulation: summation order differs from the reference's serial
-// loops (f32 rounding only; covered by the 1e-3 logits tolerance).
+// Grid n_kv_heads * head_chunks: a CTA serves up to 4 query heads that share one KV head (GQA: K rows are
+// staged once for all of them).  RoPE uses cos/sin tables computed at load time on the HOST with the same libm
+// calls as the reference (powf/cosf/sinf, src/transformer.rs:447-482).  The new K row arrives un-rotated in a
+// staging row written by the QKV GEMV; the CTA rotates it, uses it from shared memory and stores it into the
+// cache.  All f32 arithmetic follows the reference's operation order exactly (see the kernel comment).
 #pragma once
 #include "common.cuh"
+#include "exact_math.cuh"
 #include "gemv.cuh"
 
 namespace lmrs {
 
-constexpr int ATT_WARPS = 8;
-constexpr int ATT_QH = 4;  // query heads per CTA
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_QH = 4;      // query heads per CTA (all sharing one KV head)
 
 struct AttnParams {
     const float* q;        // [att_dim] un-rotated
@@ -28,24 +24,28 @@ struct AttnParams {
     const float* rope_cos; // [seq_len][hs/2]
     const float* rope_sin;
     float* out;            // [att_dim]
-    float* part;           // [n_heads][nsplit][hs + 2]   (o[hs], m, l)
-    unsigned* tickets;     // [n_kv_heads * chunks]
-    int kv_dim, kv_mul, nsplit, chunks, gemma;
-    float inv_sqrt_hs_den; // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
+    float* scores;         // scratch [n_heads][seq_len]: scores -> exp -> probabilities
+    int kv_dim, kv_mul, chunks, gemma, seq_len;
+    float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
     const StepParams* step;
 };
 
+// Bit-exact restatement of src/transformer.rs:501-544 for one token: every f32 operation happens in the
+// reference's order (serial dot over d, serial softmax sum over t, serial a*v accumulation over t, separate
+// mul and add, exp = glibc expf), only independent chains run in parallel.  One CTA per KV head (x chunks of 4
+// query heads): the latency is that of the two T-long dependent add chains (~4 cycles per cached position
+// each), which is the price of reproducing the CPU path's rounding exactly -- see exact_math.cuh for why.
 template <int HS>
-__global__ void __launch_bounds__(ATT_WARPS * 32) attn_decode_kernel(const AttnParams p) {
-    constexpr int VPL = (HS + 31) / 32;       // dims per lane (strided: d = lane + 32*i)
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnParams p) {
+    constexpr int ATT_TILE = HS > 128 ? 32 : 64;   // cached positions staged per K tile (static smem <= 48 KB)
     __shared__ float q_s[ATT_QH][HS];
     __shared__ float k_s[HS];
-    __shared__ float o_s[ATT_WARPS][ATT_QH][HS];
-    __shared__ float m_s[ATT_WARPS][ATT_QH], l_s[ATT_WARPS][ATT_QH];
-    __shared__ int is_last_cta;
+    __shared__ float ktile[ATT_TILE][HS + 1];
+    __shared__ float red[ATT_THREADS / 32];
+    __shared__ float stat[ATT_QH];
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks, split = blockIdx.y;
+    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
     const int h0 = kvh * p.kv_mul + chunk * ATT_QH;                  // first query head of this CTA
     const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
     pdl_launch_dependents();
@@ -53,137 +53,106 @@ __global__ void __launch_bounds__(ATT_WARPS * 32) attn_decode_kernel(const AttnP
     const int pos = (int)p.step->pos;
     const uint32_t mask_base = p.step->mask_base;
     const int T = pos + 1;
-    int per = (T + p.nsplit - 1) / p.nsplit;
-    per = (per + ATT_WARPS - 1) / ATT_WARPS * ATT_WARPS;
-    const int t0 = split * per, t1 = min(T, t0 + per);
-    const bool owns_pos = (pos >= t0 && pos < t1);
 
-    // RoPE on q (always) and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
+    // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492; tables hold
+    // cos/sin(pos*freq)*scale computed on the host with the reference's libm calls.
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
     const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
-    for (int i = tid; i < nh * (HS / 2); i += ATT_WARPS * 32) {
+    for (int i = tid; i < nh * (HS / 2); i += ATT_THREADS) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
         const float v0 = p.q[(size_t)(h0 + h) * HS + j], v1 = p.q[(size_t)(h0 + h) * HS + j + HS / 2];
         q_s[h][j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         q_s[h][j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
     }
-    if (owns_pos) {
-        for (int j = tid; j < HS / 2; j += ATT_WARPS * 32) {
-            const float fcr = cs[j], fci = sn[j];
-            const float v0 = p.k_new[(size_t)kvh * HS + j], v1 = p.k_new[(size_t)kvh * HS + j + HS / 2];
-            const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-            const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
-            k_s[j] = r0; k_s[j + HS / 2] = r1;
-            if (chunk == 0) {
-                p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = r0;
-                p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j + HS / 2] = r1;
-            }
+    for (int j = tid; j < HS / 2; j += ATT_THREADS) {
+        const float fcr = cs[j], fci = sn[j];
+        const float v0 = p.k_new[(size_t)kvh * HS + j], v1 = p.k_new[(size_t)kvh * HS + j + HS / 2];
+        const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+        k_s[j] = r0; k_s[j + HS / 2] = r1;
+        if (chunk == 0) {   // exactly one CTA per KV head publishes the rotated row into the cache
+            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = r0;
+            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j + HS / 2] = r1;
         }
     }
     __syncthreads();
 
-    float qr[ATT_QH][VPL], o[ATT_QH][VPL], m[ATT_QH], l[ATT_QH];
-#pragma unroll
-    for (int h = 0; h < ATT_QH; h++) {
-        m[h] = -INFINITY; l[h] = 0.0f;
-#pragma unroll
-        for (int i = 0; i < VPL; i++) {
-            const int d = lane + 32 * i;
-            qr[h][i] = (h < nh && d < HS) ? q_s[h][d] : 0.0f;
-            o[h][i] = 0.0f;
+    // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
+    for (int tile0 = 0; tile0 < T; tile0 += ATT_TILE) {
+        const int rows = min(ATT_TILE, T - tile0);
+        for (int idx = tid; idx < rows * HS; idx += ATT_THREADS) {     // coalesced K rows -> padded smem tile
+            const int r = idx / HS, d = idx - r * HS, t = tile0 + r;
+            ktile[r][d] = (t == pos) ? k_s[d] : p.kcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d];
         }
+        __syncthreads();
+        for (int idx = tid; idx < rows * nh; idx += ATT_THREADS) {
+            const int h = idx / rows, r = idx - h * rows, t = tile0 + r;
+            float score = 0.0f;
+#pragma unroll 8
+            for (int d = 0; d < HS; d++) score = __fadd_rn(score, __fmul_rn(q_s[h][d], ktile[r][d]));
+            score = __fdiv_rn(score, p.sqrt_hs);
+            if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
+                score = __fdiv_rn(score, 50.0f);
+                score = (float)tanh((double)score);
+                score = __fmul_rn(score, 50.0f);
+                score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
+            }
+            p.scores[(size_t)(h0 + h) * p.seq_len + t] = score;
+        }
+        __syncthreads();
     }
 
-    for (int t = t0 + warp; t < t1; t += ATT_WARPS) {
-        float kr[VPL], vr[VPL];
-        const float* vrow = p.vcache + (size_t)t * p.kv_dim + (size_t)kvh * HS;
-        if (t == pos) {
+    // ---- softmax (src/functional.rs:122-140): max, exp(x-max), serial sum, divide ---------------------------
+    for (int h = 0; h < nh; h++) {
+        float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
+        float mx = sc[0];
+        for (int t = tid; t < T; t += ATT_THREADS) mx = fmaxf(mx, sc[t]);
+        mx = warp_max(mx);
+        if (lane == 0) red[warp] = mx;
+        __syncthreads();
+        mx = red[0];
 #pragma unroll
-            for (int i = 0; i < VPL; i++) { const int d = lane + 32 * i; kr[i] = d < HS ? k_s[d] : 0.0f; }
-        } else {
-            const float* krow = p.kcache + (size_t)t * p.kv_dim + (size_t)kvh * HS;
-#pragma unroll
-            for (int i = 0; i < VPL; i++) { const int d = lane + 32 * i; kr[i] = d < HS ? krow[d] : 0.0f; }
-        }
-#pragma unroll
-        for (int i = 0; i < VPL; i++) { const int d = lane + 32 * i; vr[i] = d < HS ? vrow[d] : 0.0f; }
-#pragma unroll
-        for (int h = 0; h < ATT_QH; h++) {
-            if (h < nh) {
-                float s = 0.0f;
-#pragma unroll
-                for (int i = 0; i < VPL; i++) s = fmaf(qr[h][i], kr[i], s);
-                s = warp_sum(s);
-                s = __fdiv_rn(s, p.inv_sqrt_hs_den);
-                if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window 4096 on every layer (src/transformer.rs:518-526)
-                    s = __fdiv_rn(s, 50.0f);
-                    s = (float)tanh((double)s);
-                    s = __fmul_rn(s, 50.0f);
-                    s = __fadd_rn(s, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);  // u32 wrap kept
-                }
-                const float mn = fmaxf(m[h], s);
-                const float corr = expf(m[h] - mn), pr = expf(s - mn);
-                l[h] = fmaf(l[h], corr, pr);
-#pragma unroll
-                for (int i = 0; i < VPL; i++) o[h][i] = fmaf(o[h][i], corr, pr * vr[i]);
-                m[h] = mn;
-            }
-        }
+        for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[w]);
+        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
+        __syncthreads();
     }
-    // merge the warps of this CTA
-#pragma unroll
-    for (int h = 0; h < ATT_QH; h++) {
-        if (lane == 0) { m_s[warp][h] = m[h]; l_s[warp][h] = l[h]; }
-#pragma unroll
-        for (int i = 0; i < VPL; i++) { const int d = lane + 32 * i; if (d < HS) o_s[warp][h][d] = o[h][i]; }
+    if (tid < nh) {   // the reference's `sum += x[i]` chain, one thread per head
+        const float* sc = p.scores + (size_t)(h0 + tid) * p.seq_len;
+        float sum = 0.0f;
+        int t = 0;
+        for (; t + 8 <= T; t += 8) {
+            const float4 a = *reinterpret_cast<const float4*>(sc + t), b = *reinterpret_cast<const float4*>(sc + t + 4);
+            sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
+            sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
+        }
+        for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
+        stat[tid] = sum;
     }
     __syncthreads();
-    const int stride = HS + 2;
-    for (int e = tid; e < nh * HS; e += ATT_WARPS * 32) {
-        const int h = e / HS, d = e - h * HS;
-        float M = -INFINITY;
-#pragma unroll
-        for (int w = 0; w < ATT_WARPS; w++) M = fmaxf(M, m_s[w][h]);
-        float L = 0.0f, O = 0.0f;
-        if (M > -INFINITY) {
-#pragma unroll
-            for (int w = 0; w < ATT_WARPS; w++) {
-                const float sc = expf(m_s[w][h] - M);
-                L = fmaf(l_s[w][h], sc, L);
-                O = fmaf(o_s[w][h][d], sc, O);
-            }
-        }
-        float* dst = p.part + ((size_t)(h0 + h) * p.nsplit + split) * stride;
-        dst[d] = O;
-        if (d == 0) { dst[HS] = M; dst[HS + 1] = L; }
-    }
-    // ticket: the last CTA of this (kv head, chunk) merges all splits
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-        const unsigned prev = atomicAdd(&p.tickets[blockIdx.x], 1u);
-        is_last_cta = (prev == (unsigned)p.nsplit - 1u);
-        if (is_last_cta) p.tickets[blockIdx.x] = 0u;   // re-arm for the next launch
+    for (int h = 0; h < nh; h++) {
+        float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
+        const float sum = stat[h];
+        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = __fdiv_rn(sc[t], sum);
     }
     __syncthreads();
-    if (!is_last_cta) return;
-    __threadfence();
-    for (int e = tid; e < nh * HS; e += ATT_WARPS * 32) {
-        const int h = e / HS, d = e - h * HS;
-        const float* src = p.part + (size_t)(h0 + h) * p.nsplit * stride;
-        float M = -INFINITY;
-        for (int s = 0; s < p.nsplit; s++) M = fmaxf(M, __ldcg(src + (size_t)s * stride + HS));
-        float L = 0.0f, O = 0.0f;
-        for (int s = 0; s < p.nsplit; s++) {
-            const float ms = __ldcg(src + (size_t)s * stride + HS);
-            if (ms > -INFINITY) {
-                const float sc = expf(ms - M);
-                L = fmaf(__ldcg(src + (size_t)s * stride + HS + 1), sc, L);
-                O = fmaf(__ldcg(src + (size_t)s * stride + d), sc, O);
-            }
+
+    // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542) --------------------------------------
+    for (int idx = tid; idx < nh * HS; idx += ATT_THREADS) {
+        const int h = idx / HS, d = idx - h * HS;
+        const float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
+        const float* vcol = p.vcache + (size_t)kvh * HS + d;
+        float acc = 0.0f;
+        int t = 0;
+        for (; t + 4 <= T; t += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(sc + t);
+            const float v0 = vcol[(size_t)t * p.kv_dim], v1 = vcol[(size_t)(t + 1) * p.kv_dim];
+            const float v2 = vcol[(size_t)(t + 2) * p.kv_dim], v3 = vcol[(size_t)(t + 3) * p.kv_dim];
+            acc = __fadd_rn(acc, __fmul_rn(a.x, v0)); acc = __fadd_rn(acc, __fmul_rn(a.y, v1));
+            acc = __fadd_rn(acc, __fmul_rn(a.z, v2)); acc = __fadd_rn(acc, __fmul_rn(a.w, v3));
         }
-        p.out[(size_t)(h0 + h) * HS + d] = __fdiv_rn(O, L);
+        for (; t < T; t++) acc = __fadd_rn(acc, __fmul_rn(sc[t], vcol[(size_t)t * p.kv_dim]));
+        p.out[(size_t)(h0 + h) * HS + d] = acc;
     }
 }
 

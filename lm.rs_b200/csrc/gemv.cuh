@@ -24,6 +24,7 @@
 // matmul_q8/matmul_q4 results are BIT-IDENTICAL to the CPU path; -fmad=false keeps mul/add unfused.
 #pragma once
 #include "common.cuh"
+#include "exact_math.cuh"
 
 namespace lmrs {
 
@@ -64,11 +65,12 @@ template <> struct QTraits<2> { static constexpr int QB = 64; };   // Q4_0
 template <int QT> __host__ __device__ constexpr int gemv_stage_bytes() { return 2 * SG * QTraits<QT>::QB + 2 * SG * 4; }
 
 // shared-memory footprint of one CTA (must match the carve-up in the kernel)
-template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n) {
+template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n, bool norm) {
     size_t ring = (size_t)WARPS * DEPTH * gemv_stage_bytes<QT>();
     size_t xq = (size_t)n;                         // Q8: n codes; Q4: n/2 even + n/2 odd signed bytes
     size_t xs = (size_t)(n / GS) * 4 * 2;          // scales + per-group code sums (Q4)
-    return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128;
+    size_t xf = norm ? (size_t)n * 4 : 0;          // PRO_NORM: f32 staging of the vector being normed
+    return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128 + xf;
 }
 
 struct RowRange { int row0, nrows; };
@@ -88,6 +90,41 @@ template <int WARPS> LMRS_DEVINL float block_sum(float v, float* red) {
     t = warp_sum(t);
     __syncthreads();
     return t;
+}
+
+// 1/sqrt(mean(x^2)+eps) with the reference's exact summation order (src/functional.rs:49-62): eight lane
+// accumulators ss[k] += x[8j+k]*x[8j+k] walked serially over j (mul and add unfused), then wide's
+// f32x8::reduce_add order ((a0+a4)+(a2+a6))+((a1+a5)+(a3+a7)) (see oracle/lmrs_ref.c header), /size, +eps,
+// 1/sqrt.  Eight threads walk the chains (size/8 dependent adds, ~4 cycles each); everybody gets the result.
+LMRS_DEVINL float exact_rnorm(const float* xf, int n, float eps, float* red) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float s = 0.0f;
+        if (lane < 8) {
+            const int steps = n / 8;
+            int j = 0;
+            for (; j + 8 <= steps; j += 8) {
+                float x[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) x[u] = xf[8 * (j + u) + lane];
+#pragma unroll
+                for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(x[u], x[u]));
+            }
+            for (; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
+        }
+        const float t = __fadd_rn(s, __shfl_sync(0xffffffffu, s, (lane + 4) & 31));   // lanes 0..3: a_l + a_{l+4}
+        const float u = __fadd_rn(t, __shfl_sync(0xffffffffu, t, (lane + 2) & 31));   // lane 0: s0+s2, lane 1: s1+s3
+        float ss = __fadd_rn(u, __shfl_sync(0xffffffffu, u, (lane + 1) & 31));        // lane 0: (s0+s2)+(s1+s3)
+        if (lane == 0) {
+            ss = __fdiv_rn(ss, (float)n);
+            ss = __fadd_rn(ss, eps);
+            red[0] = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+        }
+    }
+    __syncthreads();
+    const float r = red[0];
+    __syncthreads();
+    return r;
 }
 
 // quantize 4 consecutive activations held by each lane of a full warp == one 128-group
@@ -136,6 +173,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     int* xsum = reinterpret_cast<int*>(xs + G);
     float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + ((G * 8 + 127) / 128) * 128);
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + 64) + warp * DEPTH;
+    float* xf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(red + 64) + WARPS * DEPTH * 8 + 64);   // PRO_NORM only
 
     const bool glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
     const int nslots = gridDim.x * WARPS * (glu ? 1 : 2);
@@ -189,18 +227,19 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
         if (p.delta) {
             const float4* din = reinterpret_cast<const float4*>(p.delta);
             float4 dv[NORM_MAXC];
-            float ssd = 0.0f;
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 int c = tid + k * THREADS;
                 dv[k] = c < nchunks ? din[c] : make_float4(0.f, 0.f, 0.f, 0.f);
-                ssd += dv[k].x * dv[k].x + dv[k].y * dv[k].y + dv[k].z * dv[k].z + dv[k].w * dv[k].w;
             }
             if (p.w_post) {  // Gemma: x += rmsnorm(delta, w_post) with unit offset (src/transformer.rs:564,645)
-                float ss = block_sum<WARPS>(ssd, red);
-                ss = __fdiv_rn(ss, (float)n);
-                ss = __fadd_rn(ss, p.eps);
-                const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+#pragma unroll
+                for (int k = 0; k < NORM_MAXC; k++) {
+                    int c = tid + k * THREADS;
+                    if (c < nchunks) reinterpret_cast<float4*>(xf)[c] = dv[k];
+                }
+                __syncthreads();
+                const float r = exact_rnorm(xf, n, p.eps, red);
                 const float4* wp = reinterpret_cast<const float4*>(p.w_post);
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
@@ -228,14 +267,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
                 if (c < nchunks) xo[c] = v[k];
             }
         }
-        float ssq = 0.0f;
 #pragma unroll
-        for (int k = 0; k < NORM_MAXC; k++)
-            ssq += v[k].x * v[k].x + v[k].y * v[k].y + v[k].z * v[k].z + v[k].w * v[k].w;
-        float ss = block_sum<WARPS>(ssq, red);  // src/functional.rs:48-62 (sum order differs: tolerance-level)
-        ss = __fdiv_rn(ss, (float)n);
-        ss = __fadd_rn(ss, p.eps);
-        const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+        for (int k = 0; k < NORM_MAXC; k++) {
+            int c = tid + k * THREADS;
+            if (c < nchunks) reinterpret_cast<float4*>(xf)[c] = v[k];
+        }
+        __syncthreads();
+        const float r = exact_rnorm(xf, n, p.eps, red);   // src/functional.rs:48-62, exact order
         const float4* wn = reinterpret_cast<const float4*>(p.w_norm);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
@@ -343,7 +381,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
                     float th = (float)tanh(0.7978845608028654 * (double)inner);
                     val = __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
                 } else {                       // SiLU (src/transformer.rs:617)
-                    val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-val))));
+                    val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));
                 }
                 p.out[rr.row0 + row_l] = __fmul_rn(val, up);
             }

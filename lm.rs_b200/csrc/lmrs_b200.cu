@@ -64,9 +64,8 @@ struct lmrs_b200 {
     const float* rms_final = nullptr;
     float *d_kcache = nullptr, *d_vcache = nullptr, *d_rope_cos = nullptr, *d_rope_sin = nullptr;
     float *d_x[2] = {nullptr, nullptr}, *d_q = nullptr, *d_knew = nullptr, *d_att = nullptr, *d_wo_out = nullptr;
-    float *d_h = nullptr, *d_down_out = nullptr, *d_logits = nullptr, *d_part = nullptr, *d_rows = nullptr;
+    float *d_h = nullptr, *d_down_out = nullptr, *d_logits = nullptr, *d_scores = nullptr, *d_rows = nullptr;
     size_t rows_cap = 0;
-    unsigned* d_tickets = nullptr;
     StepParams* d_step = nullptr;
     StepParams* h_step_ring = nullptr;  // pinned
     int step_slot = 0;
@@ -76,7 +75,7 @@ struct lmrs_b200 {
     cudaStream_t g_decode_stream = nullptr, g_prefill_stream = nullptr;
     int n_decode_kernels = 0, n_prefill_kernels = 0;
     uint64_t launches = 0;
-    int nsplit = 16, att_chunks = 1;
+    int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
     int gemv_cfg = 0, gemv_ctas_per_sm = 1;
     Shard shard;  // multi-GPU exchange (shard.h); inert when world == 1
@@ -112,13 +111,13 @@ template <int QT> static gemv_fn gemv_kernel_for(int cfg) {
         default: return gemv_kernel<QT, 4, 4>;
     }
 }
-template <int QT> static size_t gemv_smem_for(int cfg, int n) {
+template <int QT> static size_t gemv_smem_for(int cfg, int n, bool norm) {
     switch (cfg) {
-        case 0: return gemv_smem_bytes<QT, 8, 2>(n);
-        case 1: return gemv_smem_bytes<QT, 8, 3>(n);
-        case 2: return gemv_smem_bytes<QT, 16, 2>(n);
-        case 3: return gemv_smem_bytes<QT, 8, 4>(n);
-        default: return gemv_smem_bytes<QT, 4, 4>(n);
+        case 0: return gemv_smem_bytes<QT, 8, 2>(n, norm);
+        case 1: return gemv_smem_bytes<QT, 8, 3>(n, norm);
+        case 2: return gemv_smem_bytes<QT, 16, 2>(n, norm);
+        case 3: return gemv_smem_bytes<QT, 8, 4>(n, norm);
+        default: return gemv_smem_bytes<QT, 4, 4>(n, norm);
     }
 }
 static int gran_for(int n) {
@@ -131,7 +130,7 @@ static int gran_for(int n) {
 static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
     const GemvCfg c = kGemvCfgs[m->gemv_cfg];
     gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(m->gemv_cfg) : gemv_kernel_for<2>(m->gemv_cfg);
-    size_t smem = q_type == 1 ? gemv_smem_for<1>(m->gemv_cfg, p.n) : gemv_smem_for<2>(m->gemv_cfg, p.n);
+    size_t smem = q_type == 1 ? gemv_smem_for<1>(m->gemv_cfg, p.n, p.pro == PRO_NORM) : gemv_smem_for<2>(m->gemv_cfg, p.n, p.pro == PRO_NORM);
     static thread_local size_t max_set[2][8] = {};
     if (smem > max_set[q_type - 1][m->gemv_cfg]) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -141,9 +140,9 @@ static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
     int grid = m->sms * m->gemv_ctas_per_sm;
     // never launch more CTAs than there are row units to hand out (tiny matrices)
     const bool glu = p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU;
-    int units = p.o / p.row_gran, slots_per_cta = c.warps * (glu ? 1 : 2);
-    int need = (units + slots_per_cta - 1) / slots_per_cta;
-    if (grid > need) grid = need < 1 ? 1 : need;
+    (void)glu;
+    int units = p.o / p.row_gran;
+    if (grid > units) grid = units < 1 ? 1 : units;   // at least one row unit per CTA; otherwise every SM takes part
     return launch(m, fn, dim3(grid), dim3(c.warps * 32), smem, p);
 }
 
@@ -156,7 +155,7 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
 }
 
 template <int HS> static cudaError_t launch_attn_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
-    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, p.nsplit), dim3(ATT_WARPS * 32), 0, p);
+    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks), dim3(ATT_THREADS), 0, p);
 }
 static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
     switch (m->args.head_size) {
@@ -375,12 +374,6 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
         CK(cudaMemcpy(m->d_rope_sin, sn.data(), sn.size() * 4, cudaMemcpyHostToDevice));
     }
     m->att_chunks = (a.n_heads / a.n_kv_heads + ATT_QH - 1) / ATT_QH;
-    {
-        int target = m->sms / (m->l_kv_heads * m->att_chunks);
-        int ns = 1;
-        while (ns * 2 <= target && ns < 32) ns *= 2;
-        m->nsplit = env_int("LMRS_B200_NSPLIT", ns);
-    }
     CK(cudaMalloc(&m->d_x[0], dim * 4));
     CK(cudaMalloc(&m->d_x[1], dim * 4));
     CK(cudaMalloc(&m->d_q, la * 4));
@@ -390,9 +383,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     CK(cudaMalloc(&m->d_h, lh * 4));
     CK(cudaMalloc(&m->d_down_out, dim * 4));
     CK(cudaMalloc(&m->d_logits, (size_t)a.vocab_size * 4));
-    CK(cudaMalloc(&m->d_part, (size_t)m->l_heads * m->nsplit * (hs + 2) * 4));
-    CK(cudaMalloc(&m->d_tickets, (size_t)m->l_kv_heads * m->att_chunks * 4));
-    CK(cudaMemset(m->d_tickets, 0, (size_t)m->l_kv_heads * m->att_chunks * 4));
+    CK(cudaMalloc(&m->d_scores, (size_t)m->l_heads * align_up(a.seq_len, 4) * 4));
     CK(cudaMalloc(&m->d_step, sizeof(StepParams)));
     CK(cudaMallocHost(&m->h_step_ring, sizeof(StepParams) * 64));
     CK(cudaMallocHost(&m->h_logits, (size_t)a.vocab_size * 4));
@@ -424,10 +415,10 @@ static int enqueue_layers(lmrs_b200* m, bool with_classifier, float* finalize_ro
         {   // RoPE + attention (:443-544)
             AttnParams p{};
             p.q = m->d_q; p.k_new = m->d_knew; p.kcache = kc; p.vcache = vc;
-            p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = m->d_att; p.part = m->d_part;
-            p.tickets = m->d_tickets; p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
-            p.nsplit = m->nsplit; p.chunks = m->att_chunks; p.gemma = gemma;
-            p.inv_sqrt_hs_den = sqrtf((float)a.head_size); p.step = m->d_step;
+            p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = m->d_att; p.scores = m->d_scores;
+            p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
+            p.chunks = m->att_chunks; p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4);
+            p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
             CK(launch_attn(m, p, m->l_kv_heads));
         }
         {   // quantize(att) -> Wo (:546-560)
@@ -586,8 +577,8 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
-    cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_part);
-    cudaFree(m->d_tickets); cudaFree(m->d_step); cudaFree(m->d_rows);
+    cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
+    cudaFree(m->d_step); cudaFree(m->d_rows);
     if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -698,6 +689,28 @@ extern "C" int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, 
     size_t base = ((size_t)layer * m->args.seq_len + pos0) * m->l_kv_dim;
     CK(cudaMemcpy(k_out, m->d_kcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(v_out, m->d_vcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* out, size_t* n) {
+    if (!m || !name || !out || !n) return fail("null argument");
+    const std::string nm(name);
+    const float* src = nullptr;
+    size_t cnt = 0;
+    if (nm == "x0") { src = m->d_x[0]; cnt = m->args.dim; }
+    else if (nm == "x1") { src = m->d_x[1]; cnt = m->args.dim; }
+    else if (nm == "q") { src = m->d_q; cnt = m->l_att_dim; }
+    else if (nm == "k_new") { src = m->d_knew; cnt = m->l_kv_dim; }
+    else if (nm == "att") { src = m->d_att; cnt = m->l_att_dim; }
+    else if (nm == "wo_out") { src = m->d_wo_out; cnt = m->args.dim; }
+    else if (nm == "h") { src = m->d_h; cnt = m->l_hidden; }
+    else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
+    else return fail("unknown buffer name");
+    if (*n < cnt) return fail("buffer too small");
+    CK(cudaSetDevice(m->device));
+    CK(cudaStreamSynchronize(m->stream));
+    CK(cudaMemcpy(out, src, cnt * 4, cudaMemcpyDeviceToHost));
+    *n = cnt;
     return 0;
 }
 

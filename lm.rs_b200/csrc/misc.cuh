@@ -2,6 +2,7 @@
 // stand-alone operator kernels behind the operator-level C ABI (quantize / rmsnorm / softmax).
 #pragma once
 #include "common.cuh"
+#include "exact_math.cuh"
 #include "gemv.cuh"
 
 namespace lmrs {
@@ -21,13 +22,7 @@ __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualPa
     pdl_wait();
     float* out = p.rows + (size_t)p.step->token * p.n;
     float r = 1.0f;
-    if (p.w_post) {
-        float ss = 0.0f;
-        for (int i = threadIdx.x; i < p.n; i += 256) ss += p.delta[i] * p.delta[i];
-        ss = block_sum<8>(ss, red);
-        ss = __fadd_rn(__fdiv_rn(ss, (float)p.n), p.eps);
-        r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
-    }
+    if (p.w_post) r = exact_rnorm(p.delta, p.n, p.eps, red);   // chains read global memory directly
     for (int i = threadIdx.x; i < p.n; i += 256) {
         float d = p.delta[i];
         if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
@@ -61,24 +56,35 @@ __global__ void quantize_q4_kernel(uint8_t* q, float* s, const float* x, int n_g
         q[(size_t)g * gs / 2 + i] = (uint8_t)(a | (b << 4));
     }
 }
-// src/functional.rs:48-78 (single CTA; the sum of squares is a tree reduction: tolerance-level vs the reference)
+// src/functional.rs:48-78, exact summation order (exact_rnorm)
 __global__ void __launch_bounds__(256) rmsnorm_kernel(float* o, const float* x, const float* w, int size, float eps, int unit) {
     __shared__ float red[32];
     const int n8 = size / 8 * 8;
-    float ss = 0.0f;
-    for (int i = threadIdx.x; i < n8; i += 256) ss += x[i] * x[i];
-    ss = block_sum<8>(ss, red);
-    ss = __fadd_rn(__fdiv_rn(ss, (float)size), eps);
-    const float r = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+    // exact_rnorm divides by its n argument: the reference divides by `size` but sums n8 elements
+    float r;
+    {
+        if (threadIdx.x < 32) {
+            const int lane = threadIdx.x;
+            float s = 0.0f;
+            if (lane < 8)
+                for (int j = 0; j < n8 / 8; j++) { const float v = x[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(v, v)); }
+            const float t = __fadd_rn(s, __shfl_sync(0xffffffffu, s, (lane + 4) & 31));
+            const float u = __fadd_rn(t, __shfl_sync(0xffffffffu, t, (lane + 2) & 31));
+            float ss = __fadd_rn(u, __shfl_sync(0xffffffffu, u, (lane + 1) & 31));
+            if (lane == 0) red[0] = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(__fdiv_rn(ss, (float)size), eps)));
+        }
+        __syncthreads();
+        r = red[0];
+    }
     for (int i = threadIdx.x; i < n8; i += 256) {
         const float t = __fmul_rn(r, x[i]);
         o[i] = unit ? __fmul_rn(__fadd_rn(1.0f, w[i]), t) : __fmul_rn(w[i], t);
     }
 }
-// src/functional.rs:122-140
+// src/functional.rs:122-140: max, exp(x-max) with glibc's expf, SERIAL sum, divide -- bit-exact
 __global__ void __launch_bounds__(256) softmax_kernel(float* x, int n) {
     __shared__ float red[32];
-    float mx = -INFINITY;
+    float mx = x[0];
     for (int i = threadIdx.x; i < n; i += 256) mx = fmaxf(mx, x[i]);
     mx = warp_max(mx);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
@@ -86,9 +92,15 @@ __global__ void __launch_bounds__(256) softmax_kernel(float* x, int n) {
     mx = red[0];
     for (int w = 1; w < 8; w++) mx = fmaxf(mx, red[w]);
     __syncthreads();
-    float sum = 0.0f;
-    for (int i = threadIdx.x; i < n; i += 256) { float e = expf(x[i] - mx); x[i] = e; sum += e; }
-    sum = block_sum<8>(sum, red);
+    for (int i = threadIdx.x; i < n; i += 256) x[i] = expf_glibc(__fsub_rn(x[i], mx));
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float sum = 0.0f;
+        for (int i = 0; i < n; i++) sum = __fadd_rn(sum, x[i]);
+        red[0] = sum;
+    }
+    __syncthreads();
+    const float sum = red[0];
     for (int i = threadIdx.x; i < n; i += 256) x[i] = __fdiv_rn(x[i], sum);
 }
 

@@ -104,6 +104,12 @@ class Transformer:
         check(lib().lmrs_b200_read_kv(self._h, layer, pos0, n, _vp(k), _vp(v)))
         return k, v
 
+    def debug_buffer(self, name: str) -> np.ndarray:
+        cap = max(self.args.hidden_dim, self.args.dim, self.args.n_heads * self.args.head_size)
+        out, n = np.zeros(cap, np.float32), C.c_size_t(cap)
+        check(lib().lmrs_b200_debug_buffer(self._h, name.encode(), _vp(out), C.byref(n)))
+        return out[: n.value].copy()
+
     def close(self):  # impl Drop
         if self._h:
             lib().lmrs_b200_destroy(self._h)

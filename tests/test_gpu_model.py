@@ -1,7 +1,11 @@
 """Model-level parity on the GPU: Transformer.{new, forward, get_embeddings, fill_kv_cache} through the C ABI
 against the CPU oracle on identical synthetic LMRS files and prompts.
 
-Tolerance: BASELINE.json north_star -- logits within 1e-3 max-abs of the CPU path on identical prompts."""
+Bar: BASELINE.json north_star asks for logits within 1e-3 max-abs of the CPU path.  Because the path re-quantizes
+activations (discontinuous rounding), that is only reliably achievable by reproducing every f32 operation bit for
+bit (see lm.rs_b200/csrc/exact_math.cuh), so LLAMA/PHI logits, KV rows and residual streams are compared for
+EXACT equality; GEMMA goes through an f64 tanh (CUDA libdevice vs glibc) and keeps the 1e-3 tolerance."""
+import os
 import numpy as np
 import pytest
 
@@ -22,21 +26,39 @@ def test_forward_logits_match_oracle(gpu_lib, ref, synth, name, q_type):
     assert end == cpu.end_offset == buf.size
     assert bytes(gpu.args) == bytes(cpu.args)
     toks = prompt_tokens(gpu.args.vocab_size, 24)
+    exact = gpu.args.model_type != 0
     worst = 0.0
     for pos, t in enumerate(toks):
         lg = gpu.forward(int(t), pos)
         le = cpu.forward(int(t), pos)
         assert np.isfinite(lg).all()
         worst = max(worst, float(np.abs(lg - le).max()))
-        assert int(np.argmax(lg)) == int(np.argmax(le)) or worst < TOL
+        if exact:
+            assert np.array_equal(lg, le), f"pos {pos}: logits differ (max abs {np.abs(lg - le).max()})"
     assert worst <= TOL, f"max-abs logits diff {worst}"
-    # KV cache: V rows bit-exact chain is not guaranteed (norm reductions), so tolerance
     kc, vc = cpu.kv_cache()
     for l in range(gpu.args.n_layers):
         k, v = gpu.read_kv(l, 0, len(toks))
-        np.testing.assert_allclose(k, kc[l, :len(toks)], atol=TOL, rtol=0)
-        np.testing.assert_allclose(v, vc[l, :len(toks)], atol=TOL, rtol=0)
+        if exact:
+            assert np.array_equal(k, kc[l, :len(toks)]) and np.array_equal(v, vc[l, :len(toks)])
+        else:
+            np.testing.assert_allclose(k, kc[l, :len(toks)], atol=TOL, rtol=0)
+            np.testing.assert_allclose(v, vc[l, :len(toks)], atol=TOL, rtol=0)
     gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("name", ["ref_llama_q8", "ref_gemma_q4", "ref_phi_q8"])
+def test_files_written_by_the_reference_exporter(gpu_lib, ref, name):
+    """tests/golden/*.lmrs come from /root/reference/export.py itself (tests/golden/make_golden.py)."""
+    buf = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", name + ".lmrs"), dtype=np.uint8)
+    cpu = ref.RefTransformer(buf)
+    gpu, end = gpu_lib.Transformer.new(buf)
+    assert end == buf.size
+    for pos, t in enumerate(prompt_tokens(gpu.args.vocab_size, 12, seed=5)):
+        lg, le = gpu.forward(int(t), pos), cpu.forward(int(t), pos)
+        if gpu.args.model_type != 0:
+            assert np.array_equal(lg, le)
+        assert float(np.abs(lg - le).max()) <= TOL
 
 
 @pytest.mark.parametrize("name,q_type", [("tiny-llama", 1), ("tiny-gemma", 1), ("tiny-phi", 2)])
@@ -64,8 +86,11 @@ def test_fill_kv_cache_then_decode(gpu_lib, ref, synth, name, q_type):
     eg, ec = gpu.get_embeddings(toks), cpu.get_embeddings(toks)
     pg, pc = gpu.fill_kv_cache(eg, 3), cpu.fill_kv_cache(ec, 3)
     assert pg == pc == 20
-    np.testing.assert_allclose(eg, ec, atol=TOL, rtol=1e-4)      # residual stream returned in place
     lg, le = gpu.forward(11, pg), cpu.forward(11, pc)
+    if gpu.args.model_type != 0:
+        assert np.array_equal(eg, ec)                             # residual stream returned in place
+        assert np.array_equal(lg, le)
+    np.testing.assert_allclose(eg, ec, atol=TOL, rtol=1e-4)
     assert float(np.abs(lg - le).max()) <= TOL
 
 
@@ -114,8 +139,7 @@ def test_llama_1b_q8_full_shape(gpu_lib, ref, lf):
     assert np.array_equal(eg, ec)
     pg, pc = gpu.fill_kv_cache(eg, 0), cpu.fill_kv_cache(ec, 0)
     assert pg == pc == 96
-    worst = 0.0
+    assert np.array_equal(eg, ec)
     for i, t in enumerate(toks[96:]):
         lg, le = gpu.forward(int(t), 96 + i), cpu.forward(int(t), 96 + i)
-        worst = max(worst, float(np.abs(lg - le).max()))
-    assert worst <= TOL, f"max-abs logits diff {worst}"
+        assert np.array_equal(lg, le), f"pos {96 + i}: max abs {np.abs(lg - le).max()}"

@@ -1,7 +1,7 @@
 """GPU operator parity (through the C ABI) against the CPU oracle.
 
-Bars: integer/byte results and the two quantized matmuls are BIT-EXACT (the kernels reproduce the reference's
-f32 operation order); rmsnorm/softmax use tree reductions -> tolerance written in each test."""
+Bar: BIT-EXACT for every operator -- the kernels reproduce the reference's f32 operation order (ascending
+group accumulation, 8-lane rmsnorm partial sums, serial softmax sum) and glibc's expf algorithm."""
 import numpy as np
 import pytest
 
@@ -87,8 +87,7 @@ def test_rmsnorm(gpu_lib, ref, size, unit):
     exp = ref.rmsnorm(x, w, 1e-5, unit)
     got = np.zeros(size, np.float32)
     gpu_lib.functional.rmsnorm(got, x, w, size, 1e-5, unit)
-    # tree reduction vs 8-lane partial sums: the sum of squares differs by a few ulp -> 1e-6 relative
-    np.testing.assert_allclose(got, exp, rtol=2e-6, atol=1e-7)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
 
 
 @pytest.mark.parametrize("n", [1, 7, 513, 8192])
@@ -97,4 +96,4 @@ def test_softmax(gpu_lib, ref, n):
     exp = ref.softmax(x)
     got = x.copy()
     gpu_lib.functional.softmax(got)
-    np.testing.assert_allclose(got, exp, rtol=1e-5, atol=1e-9)   # expf 2 ulp + parallel sum
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
