@@ -14,7 +14,8 @@
 namespace lmrs {
 
 constexpr int ATT_THREADS = 256;
-constexpr int ATT_QH = 4;      // query heads per CTA (all sharing one KV head)
+constexpr int ATT_QH = 4;        // query heads per CTA (all sharing one KV head)
+constexpr int ATT_SC_CAP = 2048; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
 
 struct AttnParams {
     const float* q;        // [att_dim] un-rotated
@@ -24,25 +25,35 @@ struct AttnParams {
     const float* rope_cos; // [seq_len][hs/2]
     const float* rope_sin;
     float* out;            // [att_dim]
-    float* scores;         // scratch [n_heads][seq_len]: scores -> exp -> probabilities
+    float* scores;         // scratch [n_heads][seq_len] used when pos+1 > ATT_SC_CAP
     int kv_dim, kv_mul, chunks, gemma, seq_len;
     float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
     const StepParams* step;
 };
 
+template <int HS> __host__ __device__ constexpr int att_tile_rows() { return HS > 128 ? 32 : 64; }
+template <int HS> __host__ __device__ constexpr size_t attn_smem_bytes() {
+    return (size_t)(ATT_QH * HS + HS + 2 * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 64) * 4;
+}
+
 // Bit-exact restatement of src/transformer.rs:501-544 for one token: every f32 operation happens in the
 // reference's order (serial dot over d, serial softmax sum over t, serial a*v accumulation over t, separate
-// mul and add, exp = glibc expf), only independent chains run in parallel.  One CTA per KV head (x chunks of 4
-// query heads): the latency is that of the two T-long dependent add chains (~4 cycles per cached position
-// each), which is the price of reproducing the CPU path's rounding exactly -- see exact_math.cuh for why.
+// mul and add, exp = glibc expf); only independent chains run in parallel.  One CTA per KV head (x chunks of 4
+// query heads).  K and V tiles are register-prefetched (next tile's global loads are in flight while the
+// current tile's dependent-add chains run from shared memory); the K tile is stored column-rotated so that
+// the per-position dot products read it conflict-free without breaking the ascending-d summation order.
+// Latency floor: the two T-long dependent add chains (softmax sum, a*v) -- the price of exact parity, see
+// exact_math.cuh.
 template <int HS>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnParams p) {
-    constexpr int ATT_TILE = HS > 128 ? 32 : 64;   // cached positions staged per K tile (static smem <= 48 KB)
-    __shared__ float q_s[ATT_QH][HS];
-    __shared__ float k_s[HS];
-    __shared__ float ktile[ATT_TILE][HS + 1];
-    __shared__ float red[ATT_THREADS / 32];
-    __shared__ float stat[ATT_QH];
+    constexpr int TILE = att_tile_rows<HS>();
+    constexpr int PER = TILE * HS / ATT_THREADS;      // tile elements per thread (16 or 32)
+    extern __shared__ __align__(16) float att_smem[];
+    float* q_s = att_smem;                             // [ATT_QH][HS]
+    float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
+    float* tile = k_s + HS;                            // [2][TILE][HS]
+    float* sc_s = tile + 2 * TILE * HS;                // [ATT_QH][ATT_SC_CAP]
+    float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [64]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
@@ -53,17 +64,19 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     const int pos = (int)p.step->pos;
     const uint32_t mask_base = p.step->mask_base;
     const int T = pos + 1;
+    const bool in_smem = T <= ATT_SC_CAP;
+    float* sc_base = in_smem ? sc_s : p.scores + (size_t)h0 * p.seq_len;
+    const int sc_stride = in_smem ? ATT_SC_CAP : p.seq_len;
 
-    // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492; tables hold
-    // cos/sin(pos*freq)*scale computed on the host with the reference's libm calls.
+    // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
     const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
     for (int i = tid; i < nh * (HS / 2); i += ATT_THREADS) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
         const float v0 = p.q[(size_t)(h0 + h) * HS + j], v1 = p.q[(size_t)(h0 + h) * HS + j + HS / 2];
-        q_s[h][j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-        q_s[h][j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+        q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
     }
     for (int j = tid; j < HS / 2; j += ATT_THREADS) {
         const float fcr = cs[j], fci = sn[j];
@@ -78,19 +91,39 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     }
     __syncthreads();
 
+    const int ntiles = (T + TILE - 1) / TILE;
+    float pre[PER];
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
-    for (int tile0 = 0; tile0 < T; tile0 += ATT_TILE) {
-        const int rows = min(ATT_TILE, T - tile0);
-        for (int idx = tid; idx < rows * HS; idx += ATT_THREADS) {     // coalesced K rows -> padded smem tile
-            const int r = idx / HS, d = idx - r * HS, t = tile0 + r;
-            ktile[r][d] = (t == pos) ? k_s[d] : p.kcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d];
+    auto load_k = [&](int tl) {      // tile element e = tid + i*256 -> row e/HS, col e%HS (coalesced rows)
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
+            pre[i] = (t < T && t != pos) ? p.kcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d] : (t == pos ? k_s[d] : 0.0f);
+        }
+    };
+    load_k(0);
+    for (int tl = 0; tl < ntiles; tl++) {
+        float* tb = tile + (tl & 1) * TILE * HS;
+#pragma unroll
+        for (int i = 0; i < PER; i++) {   // column-rotated store: (r, d) -> r*HS + (d + r) % HS
+            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS;
+            int c = d + r; if (c >= HS) c -= HS;
+            tb[r * HS + c] = pre[i];
         }
         __syncthreads();
+        if (tl + 1 < ntiles) load_k(tl + 1);          // next tile's loads fly during this tile's chains
+        const int rows = min(TILE, T - tl * TILE);
         for (int idx = tid; idx < rows * nh; idx += ATT_THREADS) {
-            const int h = idx / rows, r = idx - h * rows, t = tile0 + r;
+            const int h = idx / rows, r = idx - h * rows, t = tl * TILE + r;
+            const float* qh = q_s + h * HS;
+            const float* kr = tb + r * HS;
             float score = 0.0f;
+            int c = r;                                  // column of d = 0
 #pragma unroll 8
-            for (int d = 0; d < HS; d++) score = __fadd_rn(score, __fmul_rn(q_s[h][d], ktile[r][d]));
+            for (int d = 0; d < HS; d++) {
+                score = __fadd_rn(score, __fmul_rn(qh[d], kr[c]));
+                c = (c + 1 == HS) ? 0 : c + 1;
+            }
             score = __fdiv_rn(score, p.sqrt_hs);
             if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
                 score = __fdiv_rn(score, 50.0f);
@@ -98,27 +131,42 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
                 score = __fmul_rn(score, 50.0f);
                 score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
             }
-            p.scores[(size_t)(h0 + h) * p.seq_len + t] = score;
+            sc_base[(size_t)h * sc_stride + t] = score;
         }
-        __syncthreads();
+        // no second barrier needed: the next iteration writes the OTHER buffer, and its __syncthreads orders
+        // this tile's reads before the buffer is overwritten two iterations later
     }
+    __syncthreads();
+
+    // prefetch the first V tile while the softmax runs
+    auto load_v = [&](int tl) {
+#pragma unroll
+        for (int i = 0; i < PER; i++) {
+            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
+            pre[i] = t < T ? p.vcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d] : 0.0f;
+        }
+    };
+    load_v(0);
 
     // ---- softmax (src/functional.rs:122-140): max, exp(x-max), serial sum, divide ---------------------------
     for (int h = 0; h < nh; h++) {
-        float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
+        float* sc = sc_base + (size_t)h * sc_stride;
         float mx = sc[0];
         for (int t = tid; t < T; t += ATT_THREADS) mx = fmaxf(mx, sc[t]);
         mx = warp_max(mx);
-        if (lane == 0) red[warp] = mx;
-        __syncthreads();
-        mx = red[0];
-#pragma unroll
-        for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[w]);
-        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
-        __syncthreads();
+        if (lane == 0) red[h * 8 + warp] = mx;
     }
-    if (tid < nh) {   // the reference's `sum += x[i]` chain, one thread per head
-        const float* sc = p.scores + (size_t)(h0 + tid) * p.seq_len;
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+        float* sc = sc_base + (size_t)h * sc_stride;
+        float mx = red[h * 8];
+#pragma unroll
+        for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[h * 8 + w]);
+        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
+    }
+    __syncthreads();
+    if (lane == 0 && warp < nh) {   // the reference's `sum += x[i]` chain: one thread per head, in different warps
+        const float* sc = sc_base + (size_t)warp * sc_stride;
         float sum = 0.0f;
         int t = 0;
         for (; t + 8 <= T; t += 8) {
@@ -127,32 +175,45 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
             sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
         }
         for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
-        stat[tid] = sum;
+        red[32 + warp] = sum;
     }
     __syncthreads();
     for (int h = 0; h < nh; h++) {
-        float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
-        const float sum = stat[h];
+        float* sc = sc_base + (size_t)h * sc_stride;
+        const float sum = red[32 + h];
         for (int t = tid; t < T; t += ATT_THREADS) sc[t] = __fdiv_rn(sc[t], sum);
     }
-    __syncthreads();
+    // (the barrier inside the first V-tile iteration orders these writes before the chains read them)
 
     // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542) --------------------------------------
-    for (int idx = tid; idx < nh * HS; idx += ATT_THREADS) {
-        const int h = idx / HS, d = idx - h * HS;
-        const float* sc = p.scores + (size_t)(h0 + h) * p.seq_len;
-        const float* vcol = p.vcache + (size_t)kvh * HS + d;
-        float acc = 0.0f;
-        int t = 0;
-        for (; t + 4 <= T; t += 4) {
-            const float4 a = *reinterpret_cast<const float4*>(sc + t);
-            const float v0 = vcol[(size_t)t * p.kv_dim], v1 = vcol[(size_t)(t + 1) * p.kv_dim];
-            const float v2 = vcol[(size_t)(t + 2) * p.kv_dim], v3 = vcol[(size_t)(t + 3) * p.kv_dim];
-            acc = __fadd_rn(acc, __fmul_rn(a.x, v0)); acc = __fadd_rn(acc, __fmul_rn(a.y, v1));
-            acc = __fadd_rn(acc, __fmul_rn(a.z, v2)); acc = __fadd_rn(acc, __fmul_rn(a.w, v3));
+    constexpr int MAXCH = (ATT_QH * HS + ATT_THREADS - 1) / ATT_THREADS;   // chains per thread
+    float acc[MAXCH];
+#pragma unroll
+    for (int k = 0; k < MAXCH; k++) acc[k] = 0.0f;
+    for (int tl = 0; tl < ntiles; tl++) {
+        float* tb = tile + (tl & 1) * TILE * HS;
+#pragma unroll
+        for (int i = 0; i < PER; i++) tb[tid + i * ATT_THREADS] = pre[i];
+        __syncthreads();
+        if (tl + 1 < ntiles) load_v(tl + 1);
+        const int rows = min(TILE, T - tl * TILE);
+#pragma unroll
+        for (int k = 0; k < MAXCH; k++) {
+            const int idx = tid + k * ATT_THREADS;
+            if (idx < nh * HS) {
+                const int h = idx / HS, d = idx - h * HS;
+                const float* a = sc_base + (size_t)h * sc_stride + tl * TILE;
+                float x = acc[k];
+#pragma unroll 8
+                for (int r = 0; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
+                acc[k] = x;
+            }
         }
-        for (; t < T; t++) acc = __fadd_rn(acc, __fmul_rn(sc[t], vcol[(size_t)t * p.kv_dim]));
-        p.out[(size_t)(h0 + h) * HS + d] = acc;
+    }
+#pragma unroll
+    for (int k = 0; k < MAXCH; k++) {
+        const int idx = tid + k * ATT_THREADS;
+        if (idx < nh * HS) p.out[(size_t)h0 * HS + idx] = acc[k];
     }
 }
 

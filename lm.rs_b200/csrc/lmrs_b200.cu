@@ -155,7 +155,13 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
 }
 
 template <int HS> static cudaError_t launch_attn_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
-    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks), dim3(ATT_THREADS), 0, p);
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
 }
 static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
     switch (m->args.head_size) {
