@@ -45,10 +45,10 @@ template <int HS> __host__ __device__ constexpr size_t attn_smem_bytes() {
 // Latency floor: the two T-long dependent add chains (softmax sum, a*v) -- the price of exact parity, see
 // exact_math.cuh.
 template <int HS>
-__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnParams p) {
+LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const int kvh, const int h0, const int nh,
+                                  const bool write_k) {
     constexpr int TILE = att_tile_rows<HS>();
     constexpr int PER = TILE * HS / ATT_THREADS;      // tile elements per thread (16 or 32)
-    extern __shared__ __align__(16) float att_smem[];
     float* q_s = att_smem;                             // [ATT_QH][HS]
     float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
     float* tile = k_s + HS;                            // [2][TILE][HS]
@@ -56,11 +56,6 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [64]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
-    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;                  // first query head of this CTA
-    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
-    pdl_launch_dependents();
-    pdl_wait();
     const int pos = (int)p.step->pos;
     const uint32_t mask_base = p.step->mask_base;
     const int T = pos + 1;
@@ -74,17 +69,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     for (int i = tid; i < nh * (HS / 2); i += ATT_THREADS) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
-        const float v0 = p.q[(size_t)(h0 + h) * HS + j], v1 = p.q[(size_t)(h0 + h) * HS + j + HS / 2];
+        const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
         q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
     }
     for (int j = tid; j < HS / 2; j += ATT_THREADS) {
         const float fcr = cs[j], fci = sn[j];
-        const float v0 = p.k_new[(size_t)kvh * HS + j], v1 = p.k_new[(size_t)kvh * HS + j + HS / 2];
+        const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
         const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
         k_s[j] = r0; k_s[j + HS / 2] = r1;
-        if (chunk == 0) {   // exactly one CTA per KV head publishes the rotated row into the cache
+        if (write_k) {   // exactly one CTA per KV head publishes the rotated row into the cache
             p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = r0;
             p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j + HS / 2] = r1;
         }
@@ -98,7 +93,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
-            pre[i] = (t < T && t != pos) ? p.kcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d] : (t == pos ? k_s[d] : 0.0f);
+            pre[i] = (t < T && t != pos) ? __ldcg(p.kcache + (size_t)t * p.kv_dim + (size_t)kvh * HS + d) : (t == pos ? k_s[d] : 0.0f);
         }
     };
     load_k(0);
@@ -143,7 +138,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
 #pragma unroll
         for (int i = 0; i < PER; i++) {
             const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
-            pre[i] = t < T ? p.vcache[(size_t)t * p.kv_dim + (size_t)kvh * HS + d] : 0.0f;
+            pre[i] = t < T ? __ldcg(p.vcache + (size_t)t * p.kv_dim + (size_t)kvh * HS + d) : 0.0f;
         }
     };
     load_v(0);
@@ -215,6 +210,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
         const int idx = tid + k * ATT_THREADS;
         if (idx < nh * HS) p.out[(size_t)h0 * HS + idx] = acc[k];
     }
+}
+
+template <int HS>
+__global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) float att_smem_dyn[];
+    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;                  // first query head of this CTA
+    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
+    pdl_launch_dependents();
+    pdl_wait();
+    attn_decode_body<HS>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
 }
 
 // ---- embedding row gather: the reference dequantizes the whole table at load (src/transformer.rs:243-245,

@@ -39,7 +39,7 @@ struct StepParams {
     uint32_t token;      // decode: token id; serial prefill: row index into the staged embeddings
     uint32_t pos;        // position of this step
     uint32_t mask_base;  // Gemma window quirk: the reference tests `pos - t` with the BATCH start pos
-    uint32_t pad;        //   (src/transformer.rs:525); decode passes pos
+    uint32_t seq;        //   (src/transformer.rs:525); decode passes pos.  seq: launch number (grid-barrier base)
 };
 
 struct GemvParams {
@@ -48,7 +48,10 @@ struct GemvParams {
     int n, o, row_gran;
     int pro;
     const float* x_in; const float* delta; const float* w_post; const float* w_norm; float* x_out;
+    int x_in_stride;   // serial prefill: x_in += step->token * x_in_stride (row of the staged embeddings)
     float eps; int unit_offset;
+    // PRO_NORM may take x_in from the embedding table instead (decode step, src/transformer.rs:324-332):
+    const uint8_t* emb_q; const float* emb_s; int emb_qtype; float emb_mul; int emb_apply_mul;
     const float* act_in;
     const uint8_t* raw_q; const float* raw_s;
     int epi;
@@ -158,94 +161,117 @@ LMRS_DEVINL void quantize_group_to_smem(float4 y, int g, uint8_t* xq, float* xs,
     }
 }
 
-template <int QT, int WARPS, int DEPTH>
-__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p) {
+
+// ---- shared-memory views of one CTA -----------------------------------------------------------------------------
+struct GemvSmem {
+    uint8_t* xq;    // quantized activation (Q8: n codes; Q4: n/2 even + n/2 odd signed bytes)
+    float* xs;      // [G] activation scales
+    int* xsum;      // [G] per-group sums of the signed activation bytes (Q4)
+    float* red;     // [64] reduction scratch
+    float* xf;      // [n] f32 staging for the exact rmsnorm chains (PRO_NORM)
+};
+
+// ---- one warp's two weight streams for one matrix -------------------------------------------------------------------
+template <int QT> struct WarpStreams {
+    RowRange r0, r1;
+    int ng0, ng1, nst, G;
+    const uint8_t *srcq0, *srcq1;
+    const float *srcs0, *srcs1;
+    bool glu;
+};
+template <int QT>
+LMRS_DEVINL WarpStreams<QT> make_streams(const GemvParams& p, int wslot, int n_wslots) {
     constexpr int QB = QTraits<QT>::QB;
-    constexpr int STAGE = gemv_stage_bytes<QT>();
-    constexpr int THREADS = WARPS * 32;
-    extern __shared__ __align__(128) uint8_t smem[];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, half = lane >> 4, l16 = lane & 15;
-    const int n = p.n, G = n / GS;
-
-    uint8_t* ring = smem;
-    uint8_t* xq = ring + (size_t)WARPS * DEPTH * STAGE;
-    float* xs = reinterpret_cast<float*>(xq + ((n + 127) / 128) * 128);
-    int* xsum = reinterpret_cast<int*>(xs + G);
-    float* red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(xs) + ((G * 8 + 127) / 128) * 128);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(red + 64) + warp * DEPTH;
-    float* xf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(red + 64) + WARPS * DEPTH * 8 + 64);   // PRO_NORM only
-
-    const bool glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
-    const int nslots = gridDim.x * WARPS * (glu ? 1 : 2);
-    const int wslot = blockIdx.x * WARPS + warp;
-    const RowRange r0 = slot_rows(glu ? wslot : wslot * 2, nslots, p.o, p.row_gran);
-    const RowRange r1 = glu ? r0 : slot_rows(wslot * 2 + 1, nslots, p.o, p.row_gran);
-    const int ng0 = r0.nrows * G, ng1 = r1.nrows * G;
-    const int nst = max((ng0 + SG - 1) / SG, (ng1 + SG - 1) / SG);
-    const uint8_t* srcq0 = p.wq_a + (size_t)r0.row0 * G * QB;
-    const float* srcs0 = p.ws_a + (size_t)r0.row0 * G;
-    const uint8_t* srcq1 = (glu ? p.wq_b : p.wq_a) + (size_t)r1.row0 * G * QB;
-    const float* srcs1 = (glu ? p.ws_b : p.ws_a) + (size_t)r1.row0 * G;
-
-    if (lane == 0) {
-#pragma unroll
-        for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d], 1);
-        fence_barrier_init();
+    WarpStreams<QT> w;
+    w.glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
+    w.G = p.n / GS;
+    const int nslots = n_wslots * (w.glu ? 1 : 2);
+    w.r0 = slot_rows(w.glu ? wslot : wslot * 2, nslots, p.o, p.row_gran);
+    w.r1 = w.glu ? w.r0 : slot_rows(wslot * 2 + 1, nslots, p.o, p.row_gran);
+    w.ng0 = w.r0.nrows * w.G; w.ng1 = w.r1.nrows * w.G;
+    w.nst = max((w.ng0 + SG - 1) / SG, (w.ng1 + SG - 1) / SG);
+    w.srcq0 = p.wq_a + (size_t)w.r0.row0 * w.G * QB;
+    w.srcs0 = p.ws_a + (size_t)w.r0.row0 * w.G;
+    w.srcq1 = (w.glu ? p.wq_b : p.wq_a) + (size_t)w.r1.row0 * w.G * QB;
+    w.srcs1 = (w.glu ? p.ws_b : p.ws_a) + (size_t)w.r1.row0 * w.G;
+    return w;
+}
+// lane 0: stream stage s of both halves into one ring slot (4 bulk copies, one mbarrier)
+template <int QT>
+LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint64_t* bar) {
+    constexpr int QB = QTraits<QT>::QB;
+    const int c0 = min(SG, max(0, w.ng0 - SG * s)), c1 = min(SG, max(0, w.ng1 - SG * s));
+    mbar_expect_tx(bar, (uint32_t)((c0 + c1) * (QB + 4)));
+    if (c0 > 0) {
+        bulk_g2s(buf, w.srcq0 + (size_t)s * SG * QB, c0 * QB, bar);
+        bulk_g2s(buf + 2 * SG * QB, w.srcs0 + (size_t)s * SG, c0 * 4, bar);
     }
-    __syncwarp();
+    if (c1 > 0) {
+        bulk_g2s(buf + SG * QB, w.srcq1 + (size_t)s * SG * QB, c1 * QB, bar);
+        bulk_g2s(buf + 2 * SG * QB + SG * 4, w.srcs1 + (size_t)s * SG, c1 * 4, bar);
+    }
+}
 
-    auto issue = [&](int s) {  // lane 0: stream stage s of both halves into ring slot s % DEPTH
-        const int d = s % DEPTH;
-        uint8_t* buf = ring + (size_t)(warp * DEPTH + d) * STAGE;
-        const int c0 = min(SG, max(0, ng0 - SG * s)), c1 = min(SG, max(0, ng1 - SG * s));
-        mbar_expect_tx(&bars[d], (uint32_t)((c0 + c1) * (QB + 4)));
-        if (c0 > 0) {
-            bulk_g2s(buf, srcq0 + (size_t)s * SG * QB, c0 * QB, &bars[d]);
-            bulk_g2s(buf + 2 * SG * QB, srcs0 + (size_t)s * SG, c0 * 4, &bars[d]);
-        }
-        if (c1 > 0) {
-            bulk_g2s(buf + SG * QB, srcq1 + (size_t)s * SG * QB, c1 * QB, &bars[d]);
-            bulk_g2s(buf + 2 * SG * QB + SG * 4, srcs1 + (size_t)s * SG, c1 * 4, &bars[d]);
-        }
-    };
-    if (lane == 0)
-        for (int s = 0; s < DEPTH && s < nst; s++) issue(s);   // weights never depend on the previous kernel
-
-    pdl_launch_dependents();
-    pdl_wait();  // upstream activations are complete and visible from here on
-
-    // ------------------------------------------------------------------------------------------ prologue
+// ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
+template <int QT, int WARPS>
+LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
+    constexpr int THREADS = WARPS * 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = p.n, G = n / GS;
     if (p.pro == PRO_NORM) {
         const int nchunks = n / 4;
         float4 v[NORM_MAXC];
-        const float4* xin = reinterpret_cast<const float4*>(p.x_in);
+        if (p.emb_q) {   // embedding row dequantized on the fly: code as f32 * scale (src/quantization.rs:25-42)
+            const uint32_t tok = p.step->token;
 #pragma unroll
-        for (int k = 0; k < NORM_MAXC; k++) {
-            int c = tid + k * THREADS;
-            v[k] = c < nchunks ? xin[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int k = 0; k < NORM_MAXC; k++) {
+                const int c = tid + k * THREADS;
+                float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (c < nchunks) {
+                    const size_t e = (size_t)tok * n + (size_t)c * 4;
+                    const float sc = p.emb_s[e / GS];
+                    if (p.emb_qtype == 1) {
+                        const char4 q4 = *reinterpret_cast<const char4*>(p.emb_q + e);
+                        t = make_float4(__fmul_rn((float)q4.x, sc), __fmul_rn((float)q4.y, sc), __fmul_rn((float)q4.z, sc), __fmul_rn((float)q4.w, sc));
+                    } else {
+                        const uchar2 b = *reinterpret_cast<const uchar2*>(p.emb_q + (e >> 1));
+                        t = make_float4(__fmul_rn((float)((b.x & 15) - 8), sc), __fmul_rn((float)((b.x >> 4) - 8), sc),
+                                        __fmul_rn((float)((b.y & 15) - 8), sc), __fmul_rn((float)((b.y >> 4) - 8), sc));
+                    }
+                    if (p.emb_apply_mul) { t.x = __fmul_rn(t.x, p.emb_mul); t.y = __fmul_rn(t.y, p.emb_mul); t.z = __fmul_rn(t.z, p.emb_mul); t.w = __fmul_rn(t.w, p.emb_mul); }
+                }
+                v[k] = t;
+            }
+        } else {
+            const float4* xin = reinterpret_cast<const float4*>(p.x_in + (size_t)(p.x_in_stride ? p.step->token : 0u) * p.x_in_stride);
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) {
+                const int c = tid + k * THREADS;
+                v[k] = c < nchunks ? __ldcg(&xin[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         if (p.delta) {
             const float4* din = reinterpret_cast<const float4*>(p.delta);
             float4 dv[NORM_MAXC];
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
-                int c = tid + k * THREADS;
-                dv[k] = c < nchunks ? din[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+                const int c = tid + k * THREADS;
+                dv[k] = c < nchunks ? __ldcg(&din[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (p.w_post) {  // Gemma: x += rmsnorm(delta, w_post) with unit offset (src/transformer.rs:564,645)
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
-                    int c = tid + k * THREADS;
-                    if (c < nchunks) reinterpret_cast<float4*>(xf)[c] = dv[k];
+                    const int c = tid + k * THREADS;
+                    if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = dv[k];
                 }
                 __syncthreads();
-                const float r = exact_rnorm(xf, n, p.eps, red);
+                const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);
                 const float4* wp = reinterpret_cast<const float4*>(p.w_post);
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
-                    int c = tid + k * THREADS;
+                    const int c = tid + k * THREADS;
                     if (c < nchunks) {
-                        float4 w = wp[c];
+                        const float4 w = wp[c];
                         dv[k].x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, dv[k].x));
                         dv[k].y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, dv[k].y));
                         dv[k].z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, dv[k].z));
@@ -263,23 +289,24 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
             float4* xo = reinterpret_cast<float4*>(p.x_out);
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
-                int c = tid + k * THREADS;
+                const int c = tid + k * THREADS;
                 if (c < nchunks) xo[c] = v[k];
             }
         }
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
-            int c = tid + k * THREADS;
-            if (c < nchunks) reinterpret_cast<float4*>(xf)[c] = v[k];
+            const int c = tid + k * THREADS;
+            if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = v[k];
         }
         __syncthreads();
-        const float r = exact_rnorm(xf, n, p.eps, red);   // src/functional.rs:48-62, exact order
+        const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
         const float4* wn = reinterpret_cast<const float4*>(p.w_norm);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
-            int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
+            const int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
             if (c < nchunks) {
-                float4 w = wn[c], y;
+                const float4 w = wn[c];
+                float4 y;
                 if (p.unit_offset) {
                     y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
                     y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
@@ -289,118 +316,161 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
                     y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
                     y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
                 }
-                quantize_group_to_smem<QT>(y, c >> 5, xq, xs, xsum, n);
+                quantize_group_to_smem<QT>(y, c >> 5, sm.xq, sm.xs, sm.xsum, n);
             }
         }
     } else if (p.pro == PRO_QUANT) {
         const float4* ain = reinterpret_cast<const float4*>(p.act_in);
-        for (int g = warp; g < G; g += WARPS) quantize_group_to_smem<QT>(ain[g * 32 + lane], g, xq, xs, xsum, n);
+        for (int g = warp; g < G; g += WARPS) quantize_group_to_smem<QT>(__ldcg(&ain[g * 32 + lane]), g, sm.xq, sm.xs, sm.xsum, n);
     } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
         if (QT == 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_q);
-            for (int i = tid; i < n / 4; i += THREADS) reinterpret_cast<uint32_t*>(xq)[i] = src[i];
-            for (int g = tid; g < G; g += THREADS) xs[g] = p.raw_s[g];
+            for (int i = tid; i < n / 4; i += THREADS) reinterpret_cast<uint32_t*>(sm.xq)[i] = src[i];
+            for (int g = tid; g < G; g += THREADS) sm.xs[g] = p.raw_s[g];
         } else {
             for (int g = warp; g < G; g += WARPS) {   // unpack one group per warp: 64 bytes = 2 per lane
-                uint16_t two = reinterpret_cast<const uint16_t*>(p.raw_q + (size_t)g * 64)[lane];
-                int b0 = two & 0xff, b1 = two >> 8;
-                int e0 = (b0 & 15) - 8, o0 = (b0 >> 4) - 8, e1 = (b1 & 15) - 8, o1 = (b1 >> 4) - 8;
-                reinterpret_cast<uint16_t*>(xq + (size_t)g * 64)[lane] = (uint16_t)((e0 & 0xff) | ((e1 & 0xff) << 8));
-                reinterpret_cast<uint16_t*>(xq + (size_t)(n / 2) + (size_t)g * 64)[lane] =
+                const uint16_t two = reinterpret_cast<const uint16_t*>(p.raw_q + (size_t)g * 64)[lane];
+                const int b0 = two & 0xff, b1 = two >> 8;
+                const int e0 = (b0 & 15) - 8, o0 = (b0 >> 4) - 8, e1 = (b1 & 15) - 8, o1 = (b1 >> 4) - 8;
+                reinterpret_cast<uint16_t*>(sm.xq + (size_t)g * 64)[lane] = (uint16_t)((e0 & 0xff) | ((e1 & 0xff) << 8));
+                reinterpret_cast<uint16_t*>(sm.xq + (size_t)(n / 2) + (size_t)g * 64)[lane] =
                     (uint16_t)((o0 & 0xff) | ((o1 & 0xff) << 8));
                 int sum = e0 + o0 + e1 + o1;
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-                if (lane == 0) { xs[g] = p.raw_s[g]; xsum[g] = sum; }
+                if (lane == 0) { sm.xs[g] = p.raw_s[g]; sm.xsum[g] = sum; }
             }
         }
     }
     __syncthreads();
+}
 
-    // ----------------------------------------------------------------------------------------- main loop
-    const RowRange rr = half ? r1 : r0;
-    const int ng = half ? ng1 : ng0;
+// ---- one stage of one warp: 32 group dot products, ordered f32 accumulation, epilogue -------------------------------
+template <int QT>
+LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, int s, const uint8_t* buf, const GemvSmem& sm,
+                               float& acc, uint32_t pos) {
+    constexpr int QB = QTraits<QT>::QB;
+    const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
+    const int n = p.n, G = w.G;
+    const RowRange rr = half ? w.r1 : w.r0;
+    const int ng = half ? w.ng1 : w.ng0;
+    const int f = s * SG + l16;           // index of my group inside my stream
+    const bool valid = f < ng;
+    const int row_l = f / G, g = f - row_l * G;
+    float t = 0.0f;
+    if (valid) {
+        int iv0 = 0, iv1 = 0;
+        if (QT == 1) {
+            const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+            const int4* xv = reinterpret_cast<const int4*>(sm.xq + (size_t)g * GS);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
+                const int c = (i + l16) & 7;
+                const int4 w4 = wv[c], x4 = xv[c];
+                iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
+                iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
+            }
+            iv0 += iv1;
+        } else {
+            const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+            const int4* ev = reinterpret_cast<const int4*>(sm.xq + (size_t)g * (GS / 2));
+            const int4* ov = reinterpret_cast<const int4*>(sm.xq + (size_t)(n / 2) + (size_t)g * (GS / 2));
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int c = (i + (l16 >> 1)) & 3;
+                const int4 w4 = wv[c], e4 = ev[c], o4 = ov[c];
+                iv0 = dp4a_su(e4.x, (uint32_t)w4.x & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.x, ((uint32_t)w4.x >> 4) & 0x0F0F0F0Fu, iv1);
+                iv0 = dp4a_su(e4.y, (uint32_t)w4.y & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.y, ((uint32_t)w4.y >> 4) & 0x0F0F0F0Fu, iv1);
+                iv0 = dp4a_su(e4.z, (uint32_t)w4.z & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.z, ((uint32_t)w4.z >> 4) & 0x0F0F0F0Fu, iv1);
+                iv0 = dp4a_su(e4.w, (uint32_t)w4.w & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.w, ((uint32_t)w4.w >> 4) & 0x0F0F0F0Fu, iv1);
+            }
+            iv0 = iv0 + iv1 - 8 * sm.xsum[g];   // sum x_s*(w_u - 8) = sum x_s*w_u - 8*sum x_s
+        }
+        const float wsc = reinterpret_cast<const float*>(buf + 2 * SG * QB)[half * SG + l16];
+        t = __fmul_rn(__fmul_rn((float)iv0, wsc), sm.xs[g]);   // (ival*ws)*xs, src/functional.rs:207,246
+    }
+    // ordered f32 accumulation across the 16 lanes of this half-warp (ascending group index)
+    const bool is_last = valid && (g == G - 1);
+    const uint32_t first_mask = __ballot_sync(0xffffffffu, valid && g == 0) >> (half * 16);
+    float mine = 0.0f;
+#pragma unroll
+    for (int j = 0; j < SG; j++) {
+        const float tj = __shfl_sync(0xffffffffu, t, j, 16);
+        acc = __fadd_rn(((first_mask >> j) & 1u) ? 0.0f : acc, tj);
+        if (j == l16) mine = acc;
+    }
+    if (w.glu) {
+        const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
+        if (is_last && half == 0) {
+            float val = mine;
+            if (p.epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
+                const float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
+                const float th = (float)tanh(0.7978845608028654 * (double)inner);
+                val = __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
+            } else {                       // SiLU (src/transformer.rs:617), exp = glibc expf
+                val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));
+            }
+            p.out[rr.row0 + row_l] = __fmul_rn(val, up);
+        }
+    } else if (is_last) {
+        const int row = rr.row0 + row_l;
+        if (p.epi == EPI_QKV) {
+            if (row < p.att_dim) p.out[row] = mine;
+            else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = mine;
+            else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = mine;
+        } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
+            float v = __fdiv_rn(mine, 30.0f);   // src/transformer.rs:375-381
+            v = (float)tanh((double)v);
+            p.out[row] = __fmul_rn(v, 30.0f);
+        } else {
+            p.out[row] = mine;
+        }
+    }
+}
+
+// carve one CTA's activation area (after the ring) -- must match gemv_smem_bytes
+LMRS_DEVINL GemvSmem carve_gemv_smem(uint8_t* base, int n, int n_bars) {
+    GemvSmem sm;
+    const int G = n / GS;
+    sm.xq = base;
+    sm.xs = reinterpret_cast<float*>(sm.xq + ((n + 127) / 128) * 128);
+    sm.xsum = reinterpret_cast<int*>(sm.xs + G);
+    sm.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.xs) + ((G * 8 + 127) / 128) * 128);
+    sm.xf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.red + 64) + n_bars * 8 + 64);
+    return sm;
+}
+
+template <int QT, int WARPS, int DEPTH>
+__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p) {
+    constexpr int STAGE = gemv_stage_bytes<QT>();
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t* ring = smem;
+    const GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm.red + 64) + warp * DEPTH;
+    const WarpStreams<QT> w = make_streams<QT>(p, blockIdx.x * WARPS + warp, gridDim.x * WARPS);
+
+    if (lane == 0) {
+#pragma unroll
+        for (int d = 0; d < DEPTH; d++) mbar_init(&bars[d], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+    if (lane == 0)   // weights never depend on the previous kernel: start streaming before griddepcontrol.wait
+        for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s]);
+    pdl_launch_dependents();
+    pdl_wait();  // upstream activations are complete and visible from here on
+
+    gemv_prologue<QT, WARPS>(p, sm);
+
     const uint32_t pos = (p.epi == EPI_QKV) ? p.step->pos : 0u;
     float acc = 0.0f;
-    for (int s = 0; s < nst; s++) {
+    for (int s = 0; s < w.nst; s++) {
         const int d = s % DEPTH;
         mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
-        const uint8_t* buf = ring + (size_t)(warp * DEPTH + d) * STAGE;
-        const int f = s * SG + l16;           // index of my group inside my stream
-        const bool valid = f < ng;
-        const int row_l = f / G, g = f - row_l * G;
-        float t = 0.0f;
-        if (valid) {
-            int iv0 = 0, iv1 = 0;
-            if (QT == 1) {
-                const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
-                const int4* xv = reinterpret_cast<const int4*>(xq + (size_t)g * GS);
-#pragma unroll
-                for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
-                    const int c = (i + l16) & 7;
-                    const int4 w4 = wv[c], x4 = xv[c];
-                    iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
-                    iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
-                }
-                iv0 += iv1;
-            } else {
-                const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
-                const int4* ev = reinterpret_cast<const int4*>(xq + (size_t)g * (GS / 2));
-                const int4* ov = reinterpret_cast<const int4*>(xq + (size_t)(n / 2) + (size_t)g * (GS / 2));
-#pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const int c = (i + (l16 >> 1)) & 3;
-                    const int4 w4 = wv[c], e4 = ev[c], o4 = ov[c];
-                    iv0 = dp4a_su(e4.x, (uint32_t)w4.x & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.x, ((uint32_t)w4.x >> 4) & 0x0F0F0F0Fu, iv1);
-                    iv0 = dp4a_su(e4.y, (uint32_t)w4.y & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.y, ((uint32_t)w4.y >> 4) & 0x0F0F0F0Fu, iv1);
-                    iv0 = dp4a_su(e4.z, (uint32_t)w4.z & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.z, ((uint32_t)w4.z >> 4) & 0x0F0F0F0Fu, iv1);
-                    iv0 = dp4a_su(e4.w, (uint32_t)w4.w & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.w, ((uint32_t)w4.w >> 4) & 0x0F0F0F0Fu, iv1);
-                }
-                iv0 = iv0 + iv1 - 8 * xsum[g];   // sum x_s*(w_u - 8) = sum x_s*w_u - 8*sum x_s
-            }
-            const float wsc = reinterpret_cast<const float*>(buf + 2 * SG * QB)[half * SG + l16];
-            t = __fmul_rn(__fmul_rn((float)iv0, wsc), xs[g]);   // (ival*ws)*xs, src/functional.rs:207,246
-        }
-        // ordered f32 accumulation across the 16 lanes of this half-warp (ascending group index)
-        const bool is_last = valid && (g == G - 1);
-        uint32_t first_mask = __ballot_sync(0xffffffffu, valid && g == 0) >> (half * 16);
-        float mine = 0.0f;
-#pragma unroll
-        for (int j = 0; j < SG; j++) {
-            const float tj = __shfl_sync(0xffffffffu, t, j, 16);
-            acc = __fadd_rn(((first_mask >> j) & 1u) ? 0.0f : acc, tj);
-            if (j == l16) mine = acc;
-        }
-        // ------------------------------------------------------------------------------------- epilogue
-        if (glu) {
-            const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
-            if (is_last && half == 0) {
-                float val = mine;
-                if (p.epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
-                    float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
-                    float th = (float)tanh(0.7978845608028654 * (double)inner);
-                    val = __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
-                } else {                       // SiLU (src/transformer.rs:617)
-                    val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));
-                }
-                p.out[rr.row0 + row_l] = __fmul_rn(val, up);
-            }
-        } else if (is_last) {
-            const int row = rr.row0 + row_l;
-            if (p.epi == EPI_QKV) {
-                if (row < p.att_dim) p.out[row] = mine;
-                else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = mine;
-                else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = mine;
-            } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
-                float v = __fdiv_rn(mine, 30.0f);   // src/transformer.rs:375-381
-                v = (float)tanh((double)v);
-                p.out[row] = __fmul_rn(v, 30.0f);
-            } else {
-                p.out[row] = mine;
-            }
-        }
+        consume_stage<QT>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, acc, pos);
         __syncwarp();
-        if (lane == 0 && s + DEPTH < nst) issue(s + DEPTH);
+        if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d]);
     }
 }
 

@@ -12,11 +12,13 @@
 #include <string.h>
 
 #include <string>
+#include <algorithm>
 #include <vector>
 
 #include "attention.cuh"
 #include "common.cuh"
 #include "gemv.cuh"
+#include "mega.cuh"
 #include "misc.cuh"
 #include "shard.h"
 
@@ -71,6 +73,13 @@ struct lmrs_b200 {
     int step_slot = 0;
     float* h_logits = nullptr;  // pinned
     cudaStream_t stream = nullptr, own_stream = nullptr;
+    MegaPhase *d_ph_decode = nullptr, *d_ph_prefill = nullptr;   // device copies of the phase tables
+    std::vector<MegaPhase> ph_decode, ph_prefill;
+    unsigned long long* d_bar = nullptr;      // [2] grid-barrier counters (decode, prefill variants)
+    uint32_t seq_decode = 0, seq_prefill = 0;
+    bool use_mega = true;
+    int mega_depth = 4;
+    size_t mega_smem = 0;
     cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr;
     cudaStream_t g_decode_stream = nullptr, g_prefill_stream = nullptr;
     int n_decode_kernels = 0, n_prefill_kernels = 0;
@@ -398,102 +407,176 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     return 0;
 }
 
-// ---- one transformer block, decode shape (src/transformer.rs:388-657 with sl = 1) ---------------------------
-static int enqueue_layers(lmrs_b200* m, bool with_classifier, float* finalize_rows) {
+// ---- the decode step as a table of phases (src/transformer.rs:316-384 + :388-657 with sl = 1) -----------------
+// One table drives both execution modes: the persistent megakernel (mega.cuh) and the one-kernel-per-phase path
+// (multi-GPU, debugging).  `serial_prefill`: x comes from row `token` of the staged embeddings, no classifier, and
+// a final phase writes the residual stream back (fill_kv_cache semantics).
+static std::vector<MegaPhase> make_phases(lmrs_b200* m, bool serial_prefill) {
     const lmrs_args_t& a = m->args;
-    const int qt = a.q_type;
     const bool gemma = a.model_type == 0;
     const size_t L = a.n_layers;
+    std::vector<MegaPhase> ph;
     const float* delta = nullptr;       // pending residual contribution
     const float* w_post = nullptr;      // Gemma: norm applied to it before the add
+    auto gemv_phase = [&](const Mat& A, const Mat* B) {
+        MegaPhase P;
+        memset(&P, 0, sizeof P);
+        P.kind = PH_GEMV;
+        P.g = gemv_base(A, B);
+        P.g.step = m->d_step;
+        return P;
+    };
     for (size_t l = 0; l < L; l++) {
         const Layer& Y = m->layers[l];
         float* kc = m->d_kcache + l * (size_t)a.seq_len * m->l_kv_dim;
         float* vc = m->d_vcache + l * (size_t)a.seq_len * m->l_kv_dim;
         {   // x(+delta) -> rmsnorm(w_rms_att) -> quantize -> [Wq;Wk;Wv]   (:409-431)
-            GemvParams p = gemv_base(Y.qkv, nullptr);
+            MegaPhase P = gemv_phase(Y.qkv, nullptr);
+            GemvParams& p = P.g;
             p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
             p.x_out = m->d_x[1]; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
+            if (l == 0) {
+                if (serial_prefill) { p.x_in = m->d_rows; p.x_in_stride = (int)a.dim; }
+                else {   // embedding row (:324) with Gemma's sqrt(dim) scaling (:327-332) folded into the prologue
+                    p.emb_q = m->emb.q; p.emb_s = m->emb.s; p.emb_qtype = a.q_type;
+                    p.emb_apply_mul = gemma; p.emb_mul = sqrtf((float)a.dim);
+                }
+            }
             p.epi = EPI_QKV; p.out = m->d_q; p.out_k = m->d_knew; p.out_v = vc;
-            p.att_dim = m->l_att_dim; p.kv_dim = m->l_kv_dim; p.step = m->d_step;
-            CK(launch_gemv(m, qt, p));
+            p.att_dim = m->l_att_dim; p.kv_dim = m->l_kv_dim;
+            ph.push_back(P);
         }
         {   // RoPE + attention (:443-544)
-            AttnParams p{};
+            MegaPhase P;
+            memset(&P, 0, sizeof P);
+            P.kind = PH_ATTN;
+            AttnParams& p = P.a;
             p.q = m->d_q; p.k_new = m->d_knew; p.kcache = kc; p.vcache = vc;
             p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = m->d_att; p.scores = m->d_scores;
             p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
             p.chunks = m->att_chunks; p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4);
             p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
-            CK(launch_attn(m, p, m->l_kv_heads));
+            ph.push_back(P);
         }
         {   // quantize(att) -> Wo (:546-560)
-            GemvParams p = gemv_base(Y.wo, nullptr);
-            p.pro = PRO_QUANT; p.act_in = m->d_att; p.epi = EPI_STORE; p.out = m->d_wo_out;
-            CK(launch_gemv(m, qt, p));
-            if (m->world > 1) { if (shard_allreduce(m->shard, m->d_wo_out, a.dim, m->stream)) return fail(shard_error()); m->launches++; }
+            MegaPhase P = gemv_phase(Y.wo, nullptr);
+            P.g.pro = PRO_QUANT; P.g.act_in = m->d_att; P.g.epi = EPI_STORE; P.g.out = m->d_wo_out;
+            P.pad = 1;   // multi-GPU: all-reduce the output
+            ph.push_back(P);
         }
         {   // x += wo_out (Gemma: normed) -> rmsnorm -> quantize -> gate/up -> act*up (:562-624)
-            GemvParams p = gemv_base(Y.w1, &Y.w3);
+            MegaPhase P = gemv_phase(Y.w1, &Y.w3);
+            GemvParams& p = P.g;
             p.pro = PRO_NORM; p.x_in = m->d_x[1]; p.delta = m->d_wo_out; p.w_post = gemma ? Y.rms_post_att : nullptr;
             p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_x[0]; p.eps = a.rms_norm_eps;
             p.unit_offset = gemma; p.epi = gemma ? EPI_GLU_GELU : EPI_GLU_SILU; p.out = m->d_h;
-            CK(launch_gemv(m, qt, p));
+            ph.push_back(P);
         }
         {   // quantize(hidden) -> W2 (:626-640)
-            GemvParams p = gemv_base(Y.w2, nullptr);
-            p.pro = PRO_QUANT; p.act_in = m->d_h; p.epi = EPI_STORE; p.out = m->d_down_out;
-            CK(launch_gemv(m, qt, p));
-            if (m->world > 1) { if (shard_allreduce(m->shard, m->d_down_out, a.dim, m->stream)) return fail(shard_error()); m->launches++; }
+            MegaPhase P = gemv_phase(Y.w2, nullptr);
+            P.g.pro = PRO_QUANT; P.g.act_in = m->d_h; P.g.epi = EPI_STORE; P.g.out = m->d_down_out;
+            P.pad = 1;
+            ph.push_back(P);
         }
         delta = m->d_down_out;
         w_post = gemma ? Y.rms_post_ffn : nullptr;   // (:642-656) applied by the next prologue
     }
-    if (with_classifier) {   // final rmsnorm + classifier (:343-371) + Gemma soft-cap quirk (:375-381)
-        GemvParams p = gemv_base(m->cls, nullptr);
+    if (!serial_prefill) {   // final rmsnorm + classifier (:343-371) + Gemma soft-cap quirk (:375-381)
+        MegaPhase P = gemv_phase(m->cls, nullptr);
+        GemvParams& p = P.g;
         p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = m->rms_final;
         p.x_out = nullptr; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
         p.epi = EPI_LOGITS; p.out = m->d_logits + m->vocab_off;
         int cap = gemma ? (int)a.dim - m->vocab_off : 0;
         p.softcap_rows = cap < 0 ? 0 : (cap > m->l_vocab ? m->l_vocab : cap);
-        CK(launch_gemv(m, qt, p));
-        if (m->world > 1) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
+        P.pad = 2;   // multi-GPU: all-gather logits
+        ph.push_back(P);
+    } else {                 // fill_kv_cache returns the residual stream: apply the pending add (:642-656)
+        MegaPhase P;
+        memset(&P, 0, sizeof P);
+        P.kind = PH_FINALIZE;
+        P.r.x_in = m->d_x[0]; P.r.delta = delta; P.r.w_post = w_post; P.r.n = a.dim; P.r.eps = a.rms_norm_eps;
+        P.r.rows = m->d_rows; P.r.step = m->d_step;
+        ph.push_back(P);
     }
-    if (finalize_rows) {     // fill_kv_cache returns the residual stream: apply the pending add (:642-656)
-        ResidualParams p{};
-        p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.n = a.dim; p.eps = a.rms_norm_eps;
-        p.rows = finalize_rows; p.step = m->d_step;
-        CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, p));
+    return ph;
+}
+
+// one kernel per phase (PDL-chained); the only mode with world > 1 (NCCL collectives between kernels)
+static int enqueue_phases_multi(lmrs_b200* m, const std::vector<MegaPhase>& ph) {
+    for (const MegaPhase& P : ph) {
+        if (P.kind == PH_GEMV) {
+            CK(launch_gemv(m, m->args.q_type, P.g));
+            if (m->world > 1 && P.pad == 1) { if (shard_allreduce(m->shard, P.g.out, m->args.dim, m->stream)) return fail(shard_error()); m->launches++; }
+            if (m->world > 1 && P.pad == 2) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
+        } else if (P.kind == PH_ATTN) {
+            CK(launch_attn(m, P.a, m->l_kv_heads));
+        } else {
+            CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r));
+        }
     }
     return 0;
 }
 
-static int enqueue_embed(lmrs_b200* m, const float* rows_src) {
-    const lmrs_args_t& a = m->args;
-    EmbedParams p{};
-    p.dim = a.dim; p.step = m->d_step; p.out = m->d_x[0]; p.tokens = nullptr;
-    if (rows_src) { p.q_type = 0; p.f32_table = rows_src; p.apply_scale = 0; }   // prefill: row `token` of the staged embeddings
-    else {
-        p.q_type = a.q_type; p.q = m->emb.q; p.s = m->emb.s;
-        p.apply_scale = a.model_type == 0; p.scale_mul = sqrtf((float)a.dim);      // :327-332
+template <int QT, int HS> static cudaError_t launch_mega_t(lmrs_b200* m, const MegaParams& mp) {
+    static thread_local size_t set_for = 0;
+    if (set_for < m->mega_smem) {
+        cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<QT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->mega_smem);
+        if (e != cudaSuccess) return e;
+        set_for = m->mega_smem;
     }
-    CK(launch(m, embed_kernel, dim3(1), dim3(256), 0, p));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(m->sms);
+    cfg.blockDim = dim3(MEGA_WARPS * 32);
+    cfg.dynamicSmemBytes = m->mega_smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: required by the in-kernel grid barriers
+    attr[0].val.cooperative = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    m->launches++;
+    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<QT, HS>, mp);
+}
+template <int QT> static cudaError_t launch_mega_q(lmrs_b200* m, const MegaParams& mp) {
+    switch (m->args.head_size) {
+        case 64: return launch_mega_t<QT, 64>(m, mp);
+        case 96: return launch_mega_t<QT, 96>(m, mp);
+        case 128: return launch_mega_t<QT, 128>(m, mp);
+        case 256: return launch_mega_t<QT, 256>(m, mp);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <int HS> static size_t attn_smem_for() { return attn_smem_bytes<HS>(); }
+static size_t attn_smem_host(int hs) {
+    switch (hs) { case 64: return attn_smem_bytes<64>(); case 96: return attn_smem_bytes<96>(); case 128: return attn_smem_bytes<128>(); default: return attn_smem_bytes<256>(); }
+}
+
+static int enqueue_step(lmrs_b200* m, bool decode) {
+    const std::vector<MegaPhase>& ph = decode ? m->ph_decode : m->ph_prefill;
+    if (!m->use_mega || m->world > 1) return enqueue_phases_multi(m, ph);
+    MegaParams mp{};
+    mp.phases = decode ? m->d_ph_decode : m->d_ph_prefill;
+    mp.n_phases = (int)ph.size();
+    mp.depth = m->mega_depth;
+    mp.act_n = std::max<int>(m->args.dim, std::max<int>(m->l_hidden, m->l_att_dim));
+    mp.norm_n = m->args.dim;
+    mp.n_kv_heads = m->l_kv_heads; mp.att_chunks = m->att_chunks; mp.head_size = m->args.head_size;
+    mp.bar_ctr = m->d_bar + (decode ? 0 : 1);
+    mp.step = m->d_step;
+    CK(m->args.q_type == 1 ? launch_mega_q<1>(m, mp) : launch_mega_q<2>(m, mp));
     return 0;
 }
 
-// build (once) and replay the whole decode step as a CUDA graph; kernels keep their PDL edges inside it
+// build (once) and replay the step as a CUDA graph (one cooperative launch, or the PDL-chained kernel sequence)
 static int run_graph(lmrs_b200* m, cudaGraphExec_t* exec, cudaStream_t* built_on, int* n_kernels, bool decode) {
-    if (!m->use_graph) {
-        if (enqueue_embed(m, decode ? nullptr : m->d_rows)) return 1;
-        return enqueue_layers(m, decode, decode ? nullptr : m->d_rows);
-    }
+    if (!m->use_graph) return enqueue_step(m, decode);
     if (!*exec || *built_on != m->stream) {
         if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
         cudaGraph_t graph;
         uint64_t before = m->launches;
         CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_embed(m, decode ? nullptr : m->d_rows);
-        if (!rc) rc = enqueue_layers(m, decode, decode ? nullptr : m->d_rows);
+        int rc = enqueue_step(m, decode);
         cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
         if (rc) return 1;
         if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
@@ -508,10 +591,36 @@ static int run_graph(lmrs_b200* m, cudaGraphExec_t* exec, cudaStream_t* built_on
     return 0;
 }
 
-static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_base) {
+static int upload_phases(lmrs_b200* m, bool decode) {
+    std::vector<MegaPhase>& ph = decode ? m->ph_decode : m->ph_prefill;
+    MegaPhase** dptr = decode ? &m->d_ph_decode : &m->d_ph_prefill;
+    ph = make_phases(m, !decode);
+    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
+    CK(cudaMalloc(dptr, ph.size() * sizeof(MegaPhase)));
+    CK(cudaMemcpy(*dptr, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+static int setup_mega(lmrs_b200* m) {
+    const int act_n = std::max<int>(m->args.dim, std::max<int>(m->l_hidden, m->l_att_dim));
+    const size_t uni = std::max(mega_act_bytes(act_n, m->args.dim), attn_smem_host(m->args.head_size));
+    const size_t stage = m->args.q_type == 1 ? gemv_stage_bytes<1>() : gemv_stage_bytes<2>();
+    const size_t limit = 227 * 1024;
+    int depth = env_int("LMRS_B200_MEGA_DEPTH", MEGA_MAX_DEPTH);
+    if (depth > MEGA_MAX_DEPTH) depth = MEGA_MAX_DEPTH;
+    while (depth > 1 && MEGA_WARPS * depth * stage + MEGA_WARPS * MEGA_MAX_DEPTH * 8 + uni > limit) depth--;
+    m->mega_depth = depth;
+    m->mega_smem = MEGA_WARPS * depth * stage + MEGA_WARPS * MEGA_MAX_DEPTH * 8 + uni;
+    if (m->mega_smem > limit) m->use_mega = false;   // does not fit: fall back to one kernel per phase
+    CK(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned long long)));
+    CK(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned long long)));
+    return 0;
+}
+
+static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_base, uint32_t seq) {
     if (m->step_slot == 64) { CK(cudaStreamSynchronize(m->stream)); m->step_slot = 0; }
     StepParams* s = &m->h_step_ring[m->step_slot++];
-    s->token = token; s->pos = pos; s->mask_base = mask_base; s->pad = 0;
+    s->token = token; s->pos = pos; s->mask_base = mask_base; s->seq = seq;
     CK(cudaMemcpyAsync(m->d_step, s, sizeof(StepParams), cudaMemcpyHostToDevice, m->stream));
     return 0;
 }
@@ -521,7 +630,7 @@ static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_b
 // K/V are identical in both schedules); the Gemma window quirk is reproduced through mask_base.
 static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
     for (size_t i = 0; i < n; i++) {
-        if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos)) return 1;
+        if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos, m->seq_prefill++)) return 1;
         if (run_graph(m, &m->g_prefill, &m->g_prefill_stream, &m->n_prefill_kernels, false)) return 1;
     }
     return 0;
@@ -556,6 +665,8 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
+    m->use_mega = env_int("LMRS_B200_MEGA", 1) != 0;
+    if (setup_mega(m) || upload_phases(m, true)) { lmrs_b200_destroy(m); return 1; }
     *out = m;
     return 0;
 }
@@ -584,7 +695,7 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     cudaFree(m->d_arena); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
     cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
-    cudaFree(m->d_step); cudaFree(m->d_rows);
+    cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_bar);
     if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -602,7 +713,7 @@ extern "C" int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t
     if (token >= m->args.vocab_size) return fail("token out of range");
     if (pos >= m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
     CK(cudaSetDevice(m->device));
-    if (push_step(m, token, pos, pos)) return 1;
+    if (push_step(m, token, pos, pos, m->seq_decode++)) return 1;
     return run_graph(m, &m->g_decode, &m->g_decode_stream, &m->n_decode_kernels, true);
 }
 
@@ -678,6 +789,7 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
         CK(cudaMalloc(&m->d_rows, n * dim * 4));
         m->rows_cap = n * dim;
         if (m->g_prefill) { cudaGraphExecDestroy(m->g_prefill); m->g_prefill = nullptr; }
+        if (upload_phases(m, false)) return 1;   // the phase table embeds the staging buffer's address
     }
     CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));
     if (prefill_batched(m, n, pos)) return 1;

@@ -1,0 +1,157 @@
+// mega.cuh -- the whole decode step (Transformer::forward, src/transformer.rs:316-384) as ONE persistent kernel.
+//
+// Why: a decode step is 5*n_layers+1 dependent matrix-vector products of 1-34 MB each.  As separate launches each one
+// pays a launch gap, a pipeline fill and a drain (measured ~3.5 us per kernel, 82 kernels per Llama-1B token, against
+// ~2.4 us of pure streaming time each), so HBM idles most of the time.  Here one CTA per SM stays resident for the
+// whole step and every warp walks ONE continuous stream of weight stages that runs across phase boundaries:
+//
+//   * the schedule is static (row ranges per warp per matrix are a pure function of the warp id), so after consuming
+//     a stage a warp immediately issues the bulk copy (TMA engine, cp.async.bulk + mbarrier) for the stage DEPTH
+//     positions ahead in its stream -- which may belong to the next matrix or the next layer.  Weight traffic keeps
+//     flowing while the CTA sits in a grid barrier, runs the exact-order rmsnorm chain or the attention phase;
+//   * phases are separated by grid-wide barriers (one 64-bit arrival counter in HBM, release/acquire), 5 per layer;
+//   * attention (RoPE, QK^T, softmax, AV -- attention.cuh) runs on n_kv_heads CTAs while the others wait with full
+//     rings; the activation scratch and the attention scratch alias the same shared-memory region.
+//
+// Arithmetic is exactly that of gemv.cuh / attention.cuh (shared device functions), so results stay bit-identical.
+#pragma once
+#include "attention.cuh"
+#include "common.cuh"
+#include "gemv.cuh"
+#include "misc.cuh"
+
+namespace lmrs {
+
+constexpr int MEGA_WARPS = 8;          // == ATT_THREADS / 32
+constexpr int MEGA_MAX_DEPTH = 6;
+
+enum { PH_GEMV = 0, PH_ATTN = 1, PH_FINALIZE = 2 };
+
+struct MegaPhase {
+    int kind;
+    int pad;
+    GemvParams g;
+    AttnParams a;
+    ResidualParams r;
+};
+
+struct MegaParams {
+    const MegaPhase* phases;
+    int n_phases;
+    int depth;                     // ring stages per warp
+    int act_n;                     // largest GEMV input length (bytes of quantized activation)
+    int norm_n;                    // dim (f32 staging of the normed vector)
+    int n_kv_heads, att_chunks, head_size;
+    unsigned long long* bar_ctr;   // grid barrier arrival counter (monotonic across launches)
+    const StepParams* step;        // step->seq numbers the launches of this kernel variant
+};
+
+LMRS_DEVINL unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// all CTAs of the (co-resident) grid arrive; writes before the barrier are visible to every CTA after it
+LMRS_DEVINL void grid_barrier(unsigned long long* ctr, unsigned long long target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1ULL);
+        while (ld_acquire_u64(ctr) < target) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+template <int QT> __host__ __device__ constexpr size_t mega_ring_bytes(int depth) {
+    return (size_t)MEGA_WARPS * depth * gemv_stage_bytes<QT>();
+}
+inline size_t mega_act_bytes(int act_n, int norm_n) {
+    return 64 * 4 + (size_t)norm_n * 4 + (size_t)((act_n + 127) / 128) * 128 + (size_t)((act_n / GS * 8 + 127) / 128) * 128 + 128;
+}
+
+template <int QT, int HS>
+__global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const MegaParams mp) {
+    constexpr int STAGE = gemv_stage_bytes<QT>();
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int depth = mp.depth;
+    uint8_t* ring = smem + (size_t)warp * depth * STAGE;                                  // this warp's ring
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + mega_ring_bytes<QT>(depth)) + warp * MEGA_MAX_DEPTH;
+    uint8_t* uni = smem + mega_ring_bytes<QT>(depth) + MEGA_WARPS * MEGA_MAX_DEPTH * 8;   // activation / attention union
+    float* red = reinterpret_cast<float*>(uni);
+    float* xf = red + 64;
+    uint8_t* xq = reinterpret_cast<uint8_t*>(xf + mp.norm_n);
+
+    if (lane == 0) {
+        for (int d = 0; d < depth; d++) mbar_init(&bars[d], 1);
+        fence_barrier_init();
+    }
+    __syncwarp();
+
+    const int wslot = blockIdx.x * MEGA_WARPS + warp, n_wslots = gridDim.x * MEGA_WARPS;
+    // ---- prefetch iterator: the next (phase, stage) of this warp's weight stream --------------------------------
+    int pf_phase = -1, pf_stage = 0;
+    WarpStreams<QT> pf_w;
+    pf_w.nst = 0;
+    auto pf_seek = [&]() {   // move to the next existing stage (skipping phases where this warp owns nothing)
+        while (pf_phase < mp.n_phases && (pf_phase < 0 || pf_stage >= pf_w.nst)) {
+            pf_phase++;
+            pf_stage = 0;
+            pf_w.nst = 0;
+            if (pf_phase < mp.n_phases && mp.phases[pf_phase].kind == PH_GEMV)
+                pf_w = make_streams<QT>(mp.phases[pf_phase].g, wslot, n_wslots);
+        }
+    };
+    uint32_t issued = 0, consumed = 0;
+    auto pf_issue = [&]() {
+        const uint32_t slot = issued % (uint32_t)depth;
+        if (lane == 0) issue_stage<QT>(pf_w, pf_stage, ring + (size_t)slot * STAGE, &bars[slot]);
+        issued++;
+        pf_stage++;
+        pf_seek();
+    };
+    pf_seek();
+    while (issued < (uint32_t)depth && pf_phase < mp.n_phases) pf_issue();   // weights do not depend on anything
+
+    const unsigned long long nbar = (unsigned long long)(mp.n_phases - 1);
+    const unsigned long long base = (unsigned long long)mp.step->seq * nbar * gridDim.x;
+    const uint32_t pos = mp.step->pos;
+
+    for (int ph = 0; ph < mp.n_phases; ph++) {
+        const MegaPhase& P = mp.phases[ph];
+        if (P.kind == PH_GEMV) {
+            const GemvParams& g = P.g;
+            GemvSmem sm;
+            sm.red = red; sm.xf = xf; sm.xq = xq;
+            sm.xs = reinterpret_cast<float*>(xq + ((g.n + 127) / 128) * 128);
+            sm.xsum = reinterpret_cast<int*>(sm.xs + g.n / GS);
+            gemv_prologue<QT, MEGA_WARPS>(g, sm);
+            const WarpStreams<QT> w = make_streams<QT>(g, wslot, n_wslots);
+            float acc = 0.0f;
+            for (int s = 0; s < w.nst; s++) {
+                const uint32_t slot = consumed % (uint32_t)depth;
+                mbar_wait(&bars[slot], (consumed / (uint32_t)depth) & 1u);
+                consume_stage<QT>(g, w, s, ring + (size_t)slot * STAGE, sm, acc, pos);
+                __syncwarp();
+                consumed++;
+                if (pf_phase < mp.n_phases) pf_issue();   // refill the slot just freed with the stage DEPTH ahead
+            }
+        } else if (P.kind == PH_ATTN) {
+            const int units = mp.n_kv_heads * mp.att_chunks;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int kvh = u / mp.att_chunks, chunk = u % mp.att_chunks;
+                const int h0 = kvh * P.a.kv_mul + chunk * ATT_QH;
+                const int nh = min(ATT_QH, P.a.kv_mul - chunk * ATT_QH);
+                __syncthreads();
+                attn_decode_body<HS>(P.a, reinterpret_cast<float*>(uni), kvh, h0, nh, chunk == 0);
+            }
+        } else {   // PH_FINALIZE: residual stream row back to the caller (fill_kv_cache), one CTA
+            if (blockIdx.x == 0) residual_finalize_body(P.r, red);
+        }
+        if (ph + 1 < mp.n_phases) grid_barrier(mp.bar_ctr, base + (unsigned long long)(ph + 1) * gridDim.x);
+    }
+}
+
+}  // namespace lmrs

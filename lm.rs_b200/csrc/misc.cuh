@@ -16,18 +16,21 @@ struct ResidualParams {
     float* rows;               // [n_rows][n]; row index = step->token
     const StepParams* step;
 };
+LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
+    float* out = p.rows + (size_t)p.step->token * p.n;
+    float r = 1.0f;
+    if (p.w_post) r = exact_rnorm(p.delta, p.n, p.eps, red);   // chains read global memory directly
+    for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+        float d = __ldcg(p.delta + i);
+        if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
+        out[i] = __fadd_rn(__ldcg(p.x_in + i), d);
+    }
+}
 __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualParams p) {
     __shared__ float red[32];
     pdl_launch_dependents();
     pdl_wait();
-    float* out = p.rows + (size_t)p.step->token * p.n;
-    float r = 1.0f;
-    if (p.w_post) r = exact_rnorm(p.delta, p.n, p.eps, red);   // chains read global memory directly
-    for (int i = threadIdx.x; i < p.n; i += 256) {
-        float d = p.delta[i];
-        if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
-        out[i] = __fadd_rn(p.x_in[i], d);
-    }
+    residual_finalize_body(p, red);
 }
 
 // ---- operator-level kernels (any group size; one thread walks one group serially like the reference) -------
