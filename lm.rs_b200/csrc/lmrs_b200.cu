@@ -76,6 +76,7 @@ struct lmrs_b200 {
     MegaPhase *d_ph_decode = nullptr, *d_ph_prefill = nullptr;   // device copies of the phase tables
     std::vector<MegaPhase> ph_decode, ph_prefill;
     unsigned long long* d_bar = nullptr;      // [2] grid-barrier counters (decode, prefill variants)
+    unsigned long long* d_timing = nullptr;   // LMRS_B200_TIMING=1: per-phase globaltimer stamps of the last decode step
     uint32_t seq_decode = 0, seq_prefill = 0;
     bool use_mega = true;
     int mega_depth = 4;
@@ -564,6 +565,7 @@ static int enqueue_step(lmrs_b200* m, bool decode) {
     mp.n_kv_heads = m->l_kv_heads; mp.att_chunks = m->att_chunks; mp.head_size = m->args.head_size;
     mp.bar_ctr = m->d_bar + (decode ? 0 : 1);
     mp.step = m->d_step;
+    mp.timing = decode ? m->d_timing : nullptr;
     CK(m->args.q_type == 1 ? launch_mega_q<1>(m, mp) : launch_mega_q<2>(m, mp));
     return 0;
 }
@@ -614,6 +616,11 @@ static int setup_mega(lmrs_b200* m) {
     if (m->mega_smem > limit) m->use_mega = false;   // does not fit: fall back to one kernel per phase
     CK(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned long long)));
+    if (env_int("LMRS_B200_TIMING", 0)) {
+        size_t n = (size_t)(5 * m->args.n_layers + 2) * 4 * m->sms;
+        CK(cudaMalloc(&m->d_timing, n * 8));
+        CK(cudaMemset(m->d_timing, 0, n * 8));
+    }
     return 0;
 }
 
@@ -823,6 +830,10 @@ extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* o
     else if (nm == "wo_out") { src = m->d_wo_out; cnt = m->args.dim; }
     else if (nm == "h") { src = m->d_h; cnt = m->l_hidden; }
     else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
+    else if (nm == "timing") {   // raw 64-bit stamps viewed as pairs of floats: [n_phases][4][sms] u64
+        if (!m->d_timing) return fail("timing not enabled (LMRS_B200_TIMING=1)");
+        src = (const float*)m->d_timing; cnt = (size_t)m->ph_decode.size() * 4 * m->sms * 2;
+    }
     else return fail("unknown buffer name");
     if (*n < cnt) return fail("buffer too small");
     CK(cudaSetDevice(m->device));

@@ -44,8 +44,14 @@ struct MegaParams {
     int n_kv_heads, att_chunks, head_size;
     unsigned long long* bar_ctr;   // grid barrier arrival counter (monotonic across launches)
     const StepParams* step;        // step->seq numbers the launches of this kernel variant
+    unsigned long long* timing;    // optional [n_phases][4][gridDim] globaltimer stamps (profiling aid), else nullptr
 };
 
+LMRS_DEVINL unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 LMRS_DEVINL unsigned long long ld_acquire_u64(const unsigned long long* p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -119,8 +125,12 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
     const unsigned long long base = (unsigned long long)mp.step->seq * nbar * gridDim.x;
     const uint32_t pos = mp.step->pos;
 
+    auto stamp = [&](int ph, int k) {
+        if (mp.timing && threadIdx.x == 0) mp.timing[((size_t)ph * 4 + k) * gridDim.x + blockIdx.x] = globaltimer_ns();
+    };
     for (int ph = 0; ph < mp.n_phases; ph++) {
         const MegaPhase& P = mp.phases[ph];
+        stamp(ph, 0);
         if (P.kind == PH_GEMV) {
             const GemvParams& g = P.g;
             GemvSmem sm;
@@ -128,6 +138,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             sm.xs = reinterpret_cast<float*>(xq + ((g.n + 127) / 128) * 128);
             sm.xsum = reinterpret_cast<int*>(sm.xs + g.n / GS);
             gemv_prologue<QT, MEGA_WARPS>(g, sm);
+            stamp(ph, 1);
             const WarpStreams<QT> w = make_streams<QT>(g, wslot, n_wslots);
             float acc = 0.0f;
             for (int s = 0; s < w.nst; s++) {
@@ -150,7 +161,9 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
         } else {   // PH_FINALIZE: residual stream row back to the caller (fill_kv_cache), one CTA
             if (blockIdx.x == 0) residual_finalize_body(P.r, red);
         }
+        if (mp.timing) { __syncthreads(); stamp(ph, 2); }
         if (ph + 1 < mp.n_phases) grid_barrier(mp.bar_ctr, base + (unsigned long long)(ph + 1) * gridDim.x);
+        stamp(ph, 3);
     }
 }
 

@@ -34,6 +34,13 @@ static __thread char g_err[256];
 const char* lmrs_ref_last_error(void) { return g_err; }
 static int fail(const char* msg) { snprintf(g_err, sizeof g_err, "%s", msg); return 1; }
 
+void lmrs_ref_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
 int lmrs_ref_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -71,6 +71,7 @@ void lmrs_ref_dequantize(float* x, const void* q, const float* s, int n, int gs,
 void lmrs_ref_rope_freq(int model_type, float rope_theta, int head_size, int j, float* freq, float* mscale);
 
 int lmrs_ref_num_threads(void);
+void lmrs_ref_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

@@ -13,6 +13,28 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "_build", "liblmrs_ref.so")
 
 
+def usable_cores():
+    """CPU cores this process may actually use: affinity mask, capped by the cgroup v2/v1 CPU quota."""
+    n = len(os.sched_getaffinity(0))
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(int(q) / int(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return n
+
+
+def set_threads(n):
+    lib().lmrs_ref_set_num_threads(int(n))
+
+
 def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "lmrs_ref.c")):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -37,6 +59,12 @@ def lib():
         if not os.path.exists(_SO):
             build()
         L = C.CDLL(_SO)
+        L.lmrs_ref_set_num_threads.argtypes = [C.c_int]
+        L.lmrs_ref_set_num_threads.restype = None
+        if "OMP_NUM_THREADS" not in os.environ:
+            # shared hosts: nproc may far exceed the cgroup's CPU quota, and oversubscribed OpenMP spin-waits are
+            # catastrophic (measured 11 s/token at 128 threads); default to the quota, capped at 32
+            L.lmrs_ref_set_num_threads(min(32, usable_cores()))
         L.lmrs_ref_last_error.restype = C.c_char_p
         L.lmrs_ref_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.lmrs_ref_destroy.argtypes = [C.c_void_p]
