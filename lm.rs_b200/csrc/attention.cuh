@@ -15,7 +15,8 @@ namespace lmrs {
 
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_QH = 4;        // query heads per CTA (all sharing one KV head)
-constexpr int ATT_SC_CAP = 2048; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
+constexpr int ATT_SC_CAP = 1024; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
+constexpr int ATT_NT = 4;        // K/V tiles in flight (cp.async ring)
 
 struct AttnParams {
     const float* q;        // [att_dim] un-rotated
@@ -31,28 +32,36 @@ struct AttnParams {
     const StepParams* step;
 };
 
-template <int HS> __host__ __device__ constexpr int att_tile_rows() { return HS > 128 ? 32 : 64; }
+template <int HS> __host__ __device__ constexpr int att_tile_rows() { return HS <= 64 ? 64 : (HS <= 128 ? 32 : 16); }
 template <int HS> __host__ __device__ constexpr size_t attn_smem_bytes() {
-    return (size_t)(ATT_QH * HS + HS + 2 * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 64) * 4;
+    return (size_t)(ATT_QH * HS + HS + ATT_NT * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 64) * 4;
 }
+
+LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src_gmem) : "memory");
+}
+LMRS_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> LMRS_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Bit-exact restatement of src/transformer.rs:501-544 for one token: every f32 operation happens in the
 // reference's order (serial dot over d, serial softmax sum over t, serial a*v accumulation over t, separate
 // mul and add, exp = glibc expf); only independent chains run in parallel.  One CTA per KV head (x chunks of 4
-// query heads).  K and V tiles are register-prefetched (next tile's global loads are in flight while the
-// current tile's dependent-add chains run from shared memory); the K tile is stored column-rotated so that
-// the per-position dot products read it conflict-free without breaking the ascending-d summation order.
-// Latency floor: the two T-long dependent add chains (softmax sum, a*v) -- the price of exact parity, see
-// exact_math.cuh.
+// query heads).  K and V stream through a 4-deep cp.async (LDGSTS) tile ring so that several tiles are in
+// flight while the dependent-add chains of the current tile run; K tiles are stored with their 16-byte columns
+// rotated by the row index, which makes the per-position LDS.128 dot products bank-conflict-free without
+// touching the ascending-d summation order.  Latency floor: the two T-long dependent add chains (softmax sum,
+// a*v) -- the price of exact parity, see exact_math.cuh.
 template <int HS>
 LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const int kvh, const int h0, const int nh,
                                   const bool write_k) {
     constexpr int TILE = att_tile_rows<HS>();
-    constexpr int PER = TILE * HS / ATT_THREADS;      // tile elements per thread (16 or 32)
+    constexpr int C4 = HS / 4;                         // 16-byte chunks per row
+    constexpr int CHUNKS = TILE * C4;                  // per tile
+    constexpr int PERT = (CHUNKS + ATT_THREADS - 1) / ATT_THREADS;
     float* q_s = att_smem;                             // [ATT_QH][HS]
     float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
-    float* tile = k_s + HS;                            // [2][TILE][HS]
-    float* sc_s = tile + 2 * TILE * HS;                // [ATT_QH][ATT_SC_CAP]
+    float* tile = k_s + HS;                            // [ATT_NT][TILE][HS]
+    float* sc_s = tile + ATT_NT * TILE * HS;           // [ATT_QH][ATT_SC_CAP]
     float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [64]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -62,6 +71,31 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     const bool in_smem = T <= ATT_SC_CAP;
     float* sc_base = in_smem ? sc_s : p.scores + (size_t)h0 * p.seq_len;
     const int sc_stride = in_smem ? ATT_SC_CAP : p.seq_len;
+    const int ntiles = (T + TILE - 1) / TILE;
+
+    // tile tl of K (rotated columns) or V (plain) -> ring slot tl % ATT_NT; rows >= T and the row `pos` of K
+    // (not in the cache yet) are skipped; always commits a group so the wait counts stay uniform
+    auto issue_tile = [&](const float* base, int tl, bool rotate) {
+        if (tl < ntiles) {
+            float* tb = tile + (tl % ATT_NT) * TILE * HS;
+#pragma unroll
+            for (int i = 0; i < PERT; i++) {
+                const int e = tid + i * ATT_THREADS;
+                if (e < CHUNKS) {
+                    const int r = e / C4, c = e - r * C4, t = tl * TILE + r;
+                    if (t < T && !(rotate && t == pos)) {
+                        int cc = c;
+                        if (rotate) { cc = c + r; cc = cc % C4; }
+                        cp_async16(tb + r * HS + cc * 4, base + (size_t)t * p.kv_dim + (size_t)kvh * HS + c * 4);
+                    }
+                }
+            }
+        }
+        cp_async_commit();
+    };
+    // K tiles start flowing before anything else (rows < pos are in the cache since earlier steps)
+#pragma unroll
+    for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.kcache, k, true);
 
     // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
@@ -86,38 +120,32 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     }
     __syncthreads();
 
-    const int ntiles = (T + TILE - 1) / TILE;
-    float pre[PER];
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
-    auto load_k = [&](int tl) {      // tile element e = tid + i*256 -> row e/HS, col e%HS (coalesced rows)
-#pragma unroll
-        for (int i = 0; i < PER; i++) {
-            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
-            pre[i] = (t < T && t != pos) ? __ldcg(p.kcache + (size_t)t * p.kv_dim + (size_t)kvh * HS + d) : (t == pos ? k_s[d] : 0.0f);
-        }
-    };
-    load_k(0);
     for (int tl = 0; tl < ntiles; tl++) {
-        float* tb = tile + (tl & 1) * TILE * HS;
-#pragma unroll
-        for (int i = 0; i < PER; i++) {   // column-rotated store: (r, d) -> r*HS + (d + r) % HS
-            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS;
-            int c = d + r; if (c >= HS) c -= HS;
-            tb[r * HS + c] = pre[i];
+        cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
+        float* tb = tile + (tl % ATT_NT) * TILE * HS;
+        if (pos / TILE == tl) {                        // the new K row comes from shared memory, same rotated layout
+            const int r = pos - tl * TILE;
+            for (int d = tid; d < HS; d += ATT_THREADS) {
+                const int c = d >> 2;
+                tb[r * HS + ((c + r) % C4) * 4 + (d & 3)] = k_s[d];
+            }
         }
-        __syncthreads();
-        if (tl + 1 < ntiles) load_k(tl + 1);          // next tile's loads fly during this tile's chains
+        __syncthreads();                               // tile tl visible; everyone is done with tile tl-1
+        issue_tile(p.kcache, tl + ATT_NT - 1, true);   // refill the slot tile tl-1 used
         const int rows = min(TILE, T - tl * TILE);
         for (int idx = tid; idx < rows * nh; idx += ATT_THREADS) {
             const int h = idx / rows, r = idx - h * rows, t = tl * TILE + r;
-            const float* qh = q_s + h * HS;
-            const float* kr = tb + r * HS;
+            const float4* q4 = reinterpret_cast<const float4*>(q_s + h * HS);
+            const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
             float score = 0.0f;
-            int c = r;                                  // column of d = 0
-#pragma unroll 8
-            for (int d = 0; d < HS; d++) {
-                score = __fadd_rn(score, __fmul_rn(qh[d], kr[c]));
-                c = (c + 1 == HS) ? 0 : c + 1;
+            int c = r % C4;                             // rotated position of chunk 0
+#pragma unroll 4
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 qv = q4[d4], kv = k4[c];
+                score = __fadd_rn(score, __fmul_rn(qv.x, kv.x)); score = __fadd_rn(score, __fmul_rn(qv.y, kv.y));
+                score = __fadd_rn(score, __fmul_rn(qv.z, kv.z)); score = __fadd_rn(score, __fmul_rn(qv.w, kv.w));
+                c = (c + 1 == C4) ? 0 : c + 1;
             }
             score = __fdiv_rn(score, p.sqrt_hs);
             if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
@@ -128,20 +156,12 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             }
             sc_base[(size_t)h * sc_stride + t] = score;
         }
-        // no second barrier needed: the next iteration writes the OTHER buffer, and its __syncthreads orders
-        // this tile's reads before the buffer is overwritten two iterations later
     }
+    cp_async_wait<0>();
     __syncthreads();
-
-    // prefetch the first V tile while the softmax runs
-    auto load_v = [&](int tl) {
+    // V tiles start flowing now; the softmax below runs while they land
 #pragma unroll
-        for (int i = 0; i < PER; i++) {
-            const int e = tid + i * ATT_THREADS, r = e / HS, d = e - r * HS, t = tl * TILE + r;
-            pre[i] = t < T ? __ldcg(p.vcache + (size_t)t * p.kv_dim + (size_t)kvh * HS + d) : 0.0f;
-        }
-    };
-    load_v(0);
+    for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.vcache, k, false);
 
     // ---- softmax (src/functional.rs:122-140): max, exp(x-max), serial sum, divide ---------------------------
     for (int h = 0; h < nh; h++) {
@@ -186,11 +206,10 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) acc[k] = 0.0f;
     for (int tl = 0; tl < ntiles; tl++) {
-        float* tb = tile + (tl & 1) * TILE * HS;
-#pragma unroll
-        for (int i = 0; i < PER; i++) tb[tid + i * ATT_THREADS] = pre[i];
+        cp_async_wait<ATT_NT - 2>();
         __syncthreads();
-        if (tl + 1 < ntiles) load_v(tl + 1);
+        issue_tile(p.vcache, tl + ATT_NT - 1, false);
+        const float* tb = tile + (tl % ATT_NT) * TILE * HS;
         const int rows = min(TILE, T - tl * TILE);
 #pragma unroll
         for (int k = 0; k < MAXCH; k++) {
@@ -199,17 +218,26 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 const int h = idx / HS, d = idx - h * HS;
                 const float* a = sc_base + (size_t)h * sc_stride + tl * TILE;
                 float x = acc[k];
-#pragma unroll 8
-                for (int r = 0; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
+                int r = 0;
+                for (; r + 4 <= rows; r += 4) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(a + r);
+                    x = __fadd_rn(x, __fmul_rn(a4.x, tb[r * HS + d]));
+                    x = __fadd_rn(x, __fmul_rn(a4.y, tb[(r + 1) * HS + d]));
+                    x = __fadd_rn(x, __fmul_rn(a4.z, tb[(r + 2) * HS + d]));
+                    x = __fadd_rn(x, __fmul_rn(a4.w, tb[(r + 3) * HS + d]));
+                }
+                for (; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
                 acc[k] = x;
             }
         }
     }
+    cp_async_wait<0>();
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) {
         const int idx = tid + k * ATT_THREADS;
         if (idx < nh * HS) p.out[(size_t)h0 * HS + idx] = acc[k];
     }
+    __syncthreads();   // the tile ring / score buffers may be reused by the caller
 }
 
 template <int HS>

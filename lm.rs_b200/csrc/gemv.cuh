@@ -179,8 +179,14 @@ template <int QT> struct WarpStreams {
     const float *srcs0, *srcs1;
     bool glu;
 };
+// the part of GemvParams that defines the weight streams (kept in shared memory by the megakernel)
+struct StreamDesc {
+    const uint8_t* wq_a; const float* ws_a; const uint8_t* wq_b; const float* ws_b;
+    int n, o, row_gran, epi;
+};
+LMRS_DEVINL StreamDesc stream_desc(const GemvParams& p) { return {p.wq_a, p.ws_a, p.wq_b, p.ws_b, p.n, p.o, p.row_gran, p.epi}; }
 template <int QT>
-LMRS_DEVINL WarpStreams<QT> make_streams(const GemvParams& p, int wslot, int n_wslots) {
+LMRS_DEVINL WarpStreams<QT> make_streams(const StreamDesc& p, int wslot, int n_wslots) {
     constexpr int QB = QTraits<QT>::QB;
     WarpStreams<QT> w;
     w.glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
@@ -220,7 +226,15 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     const int n = p.n, G = n / GS;
     if (p.pro == PRO_NORM) {
         const int nchunks = n / 4;
-        float4 v[NORM_MAXC];
+        float4 v[NORM_MAXC], wnv[NORM_MAXC];
+        {   // the norm weights do not depend on the previous phase: get them in flight first
+            const float4* wn = reinterpret_cast<const float4*>(p.w_norm);
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) {
+                const int c = tid + k * THREADS;
+                wnv[k] = c < nchunks ? wn[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
         if (p.emb_q) {   // embedding row dequantized on the fly: code as f32 * scale (src/quantization.rs:25-42)
             const uint32_t tok = p.step->token;
 #pragma unroll
@@ -252,11 +266,12 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
         if (p.delta) {
             const float4* din = reinterpret_cast<const float4*>(p.delta);
-            float4 dv[NORM_MAXC];
+            float4 dv[NORM_MAXC], wpv[NORM_MAXC];
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 const int c = tid + k * THREADS;
                 dv[k] = c < nchunks ? __ldcg(&din[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                wpv[k] = (p.w_post && c < nchunks) ? reinterpret_cast<const float4*>(p.w_post)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
             if (p.w_post) {  // Gemma: x += rmsnorm(delta, w_post) with unit offset (src/transformer.rs:564,645)
 #pragma unroll
@@ -266,12 +281,11 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 }
                 __syncthreads();
                 const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);
-                const float4* wp = reinterpret_cast<const float4*>(p.w_post);
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
                     const int c = tid + k * THREADS;
                     if (c < nchunks) {
-                        const float4 w = wp[c];
+                        const float4 w = wpv[k];
                         dv[k].x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, dv[k].x));
                         dv[k].y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, dv[k].y));
                         dv[k].z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, dv[k].z));
@@ -300,12 +314,11 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
         __syncthreads();
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
-        const float4* wn = reinterpret_cast<const float4*>(p.w_norm);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
             const int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
             if (c < nchunks) {
-                const float4 w = wn[c];
+                const float4 w = wnv[k];
                 float4 y;
                 if (p.unit_offset) {
                     y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
@@ -321,7 +334,19 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
     } else if (p.pro == PRO_QUANT) {
         const float4* ain = reinterpret_cast<const float4*>(p.act_in);
-        for (int g = warp; g < G; g += WARPS) quantize_group_to_smem<QT>(__ldcg(&ain[g * 32 + lane]), g, sm.xq, sm.xs, sm.xsum, n);
+        for (int g0 = warp; g0 < G; g0 += WARPS * 8) {   // 8 groups per warp in flight: one L2 round trip, not eight
+            float4 y[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int g = g0 + u * WARPS;
+                y[u] = g < G ? __ldcg(&ain[g * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int g = g0 + u * WARPS;
+                if (g < G) quantize_group_to_smem<QT>(y[u], g, sm.xq, sm.xs, sm.xsum, n);
+            }
+        }
     } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
         if (QT == 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_q);
@@ -448,7 +473,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     uint8_t* ring = smem;
     const GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm.red + 64) + warp * DEPTH;
-    const WarpStreams<QT> w = make_streams<QT>(p, blockIdx.x * WARPS + warp, gridDim.x * WARPS);
+    const WarpStreams<QT> w = make_streams<QT>(stream_desc(p), blockIdx.x * WARPS + warp, gridDim.x * WARPS);
 
     if (lane == 0) {
 #pragma unroll

@@ -74,6 +74,7 @@ struct lmrs_b200 {
     float* h_logits = nullptr;  // pinned
     cudaStream_t stream = nullptr, own_stream = nullptr;
     MegaPhase *d_ph_decode = nullptr, *d_ph_prefill = nullptr;   // device copies of the phase tables
+    StreamDesc *d_sd_decode = nullptr, *d_sd_prefill = nullptr;
     std::vector<MegaPhase> ph_decode, ph_prefill;
     unsigned long long* d_bar = nullptr;      // [2] grid-barrier counters (decode, prefill variants)
     unsigned long long* d_timing = nullptr;   // LMRS_B200_TIMING=1: per-phase globaltimer stamps of the last decode step
@@ -558,6 +559,7 @@ static int enqueue_step(lmrs_b200* m, bool decode) {
     if (!m->use_mega || m->world > 1) return enqueue_phases_multi(m, ph);
     MegaParams mp{};
     mp.phases = decode ? m->d_ph_decode : m->d_ph_prefill;
+    mp.streams = decode ? m->d_sd_decode : m->d_sd_prefill;
     mp.n_phases = (int)ph.size();
     mp.depth = m->mega_depth;
     mp.act_n = std::max<int>(m->args.dim, std::max<int>(m->l_hidden, m->l_att_dim));
@@ -600,6 +602,15 @@ static int upload_phases(lmrs_b200* m, bool decode) {
     if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
     CK(cudaMalloc(dptr, ph.size() * sizeof(MegaPhase)));
     CK(cudaMemcpy(*dptr, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    std::vector<StreamDesc> sd(ph.size());
+    for (size_t i = 0; i < ph.size(); i++) {
+        memset(&sd[i], 0, sizeof(StreamDesc));
+        if (ph[i].kind == PH_GEMV) sd[i] = {ph[i].g.wq_a, ph[i].g.ws_a, ph[i].g.wq_b, ph[i].g.ws_b, ph[i].g.n, ph[i].g.o, ph[i].g.row_gran, ph[i].g.epi};
+    }
+    StreamDesc** sptr = decode ? &m->d_sd_decode : &m->d_sd_prefill;
+    if (*sptr) { cudaFree(*sptr); *sptr = nullptr; }
+    CK(cudaMalloc(sptr, sd.size() * sizeof(StreamDesc)));
+    CK(cudaMemcpy(*sptr, sd.data(), sd.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice));
     return 0;
 }
 
@@ -610,9 +621,10 @@ static int setup_mega(lmrs_b200* m) {
     const size_t limit = 227 * 1024;
     int depth = env_int("LMRS_B200_MEGA_DEPTH", MEGA_MAX_DEPTH);
     if (depth > MEGA_MAX_DEPTH) depth = MEGA_MAX_DEPTH;
-    while (depth > 1 && MEGA_WARPS * depth * stage + MEGA_WARPS * MEGA_MAX_DEPTH * 8 + uni > limit) depth--;
+    const size_t fixed = MEGA_WARPS * MEGA_MAX_DEPTH * 8 + mega_desc_bytes(5 * m->args.n_layers + 2) + 2 * mega_phase_bytes() + uni;
+    while (depth > 1 && MEGA_WARPS * depth * stage + fixed > limit) depth--;
     m->mega_depth = depth;
-    m->mega_smem = MEGA_WARPS * depth * stage + MEGA_WARPS * MEGA_MAX_DEPTH * 8 + uni;
+    m->mega_smem = MEGA_WARPS * depth * stage + fixed;
     if (m->mega_smem > limit) m->use_mega = false;   // does not fit: fall back to one kernel per phase
     CK(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned long long)));
     CK(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned long long)));
@@ -702,7 +714,7 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     cudaFree(m->d_arena); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
     cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
-    cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_bar);
+    cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_sd_decode); cudaFree(m->d_sd_prefill); cudaFree(m->d_bar);
     if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);

@@ -37,6 +37,7 @@ struct MegaPhase {
 
 struct MegaParams {
     const MegaPhase* phases;
+    const StreamDesc* streams;     // [n_phases] compact weight-stream descriptors (o = 0 for non-GEMV phases)
     int n_phases;
     int depth;                     // ring stages per warp
     int act_n;                     // largest GEMV input length (bytes of quantized activation)
@@ -59,13 +60,11 @@ LMRS_DEVINL unsigned long long ld_acquire_u64(const unsigned long long* p) {
 }
 // all CTAs of the (co-resident) grid arrive; writes before the barrier are visible to every CTA after it
 LMRS_DEVINL void grid_barrier(unsigned long long* ctr, unsigned long long target) {
-    __syncthreads();
+    __syncthreads();   // every thread's writes happen-before thread 0's release (cumulativity)
     if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1ULL);
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ULL) : "memory");
         while (ld_acquire_u64(ctr) < target) {
         }
-        __threadfence();
     }
     __syncthreads();
 }
@@ -73,6 +72,8 @@ LMRS_DEVINL void grid_barrier(unsigned long long* ctr, unsigned long long target
 template <int QT> __host__ __device__ constexpr size_t mega_ring_bytes(int depth) {
     return (size_t)MEGA_WARPS * depth * gemv_stage_bytes<QT>();
 }
+__host__ __device__ inline size_t mega_desc_bytes(int n_phases) { return ((size_t)n_phases * sizeof(StreamDesc) + 127) / 128 * 128; }
+__host__ __device__ inline size_t mega_phase_bytes() { return (sizeof(MegaPhase) + 127) / 128 * 128; }
 inline size_t mega_act_bytes(int act_n, int norm_n) {
     return 64 * 4 + (size_t)norm_n * 4 + (size_t)((act_n + 127) / 128) * 128 + (size_t)((act_n / GS * 8 + 127) / 128) * 128 + 128;
 }
@@ -85,7 +86,9 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
     const int depth = mp.depth;
     uint8_t* ring = smem + (size_t)warp * depth * STAGE;                                  // this warp's ring
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + mega_ring_bytes<QT>(depth)) + warp * MEGA_MAX_DEPTH;
-    uint8_t* uni = smem + mega_ring_bytes<QT>(depth) + MEGA_WARPS * MEGA_MAX_DEPTH * 8;   // activation / attention union
+    StreamDesc* sd_s = reinterpret_cast<StreamDesc*>(smem + mega_ring_bytes<QT>(depth) + MEGA_WARPS * MEGA_MAX_DEPTH * 8);
+    MegaPhase* ph_s = reinterpret_cast<MegaPhase*>(reinterpret_cast<uint8_t*>(sd_s) + mega_desc_bytes(mp.n_phases));
+    uint8_t* uni = reinterpret_cast<uint8_t*>(ph_s) + 2 * mega_phase_bytes();   // activation / attention union
     float* red = reinterpret_cast<float*>(uni);
     float* xf = red + 64;
     uint8_t* xq = reinterpret_cast<uint8_t*>(xf + mp.norm_n);
@@ -94,7 +97,16 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
         for (int d = 0; d < depth; d++) mbar_init(&bars[d], 1);
         fence_barrier_init();
     }
-    __syncwarp();
+    // stream descriptors of every phase and the parameters of phase 0 -> shared memory (one round trip)
+    for (int i = threadIdx.x; i < mp.n_phases * (int)(sizeof(StreamDesc) / 4); i += blockDim.x)
+        reinterpret_cast<uint32_t*>(sd_s)[i] = reinterpret_cast<const uint32_t*>(mp.streams)[i];
+    auto load_phase = [&](int ph) {   // copy phase parameters into the double buffer (consumed after the next barrier)
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(mp.phases + ph);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(ph_s) + (ph & 1) * mega_phase_bytes());
+        for (int i = threadIdx.x; i < (int)(sizeof(MegaPhase) / 4); i += blockDim.x) dst[i] = src[i];
+    };
+    load_phase(0);
+    __syncthreads();
 
     const int wslot = blockIdx.x * MEGA_WARPS + warp, n_wslots = gridDim.x * MEGA_WARPS;
     // ---- prefetch iterator: the next (phase, stage) of this warp's weight stream --------------------------------
@@ -106,8 +118,8 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             pf_phase++;
             pf_stage = 0;
             pf_w.nst = 0;
-            if (pf_phase < mp.n_phases && mp.phases[pf_phase].kind == PH_GEMV)
-                pf_w = make_streams<QT>(mp.phases[pf_phase].g, wslot, n_wslots);
+            if (pf_phase < mp.n_phases && sd_s[pf_phase].o > 0)
+                pf_w = make_streams<QT>(sd_s[pf_phase], wslot, n_wslots);
         }
     };
     uint32_t issued = 0, consumed = 0;
@@ -129,8 +141,9 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
         if (mp.timing && threadIdx.x == 0) mp.timing[((size_t)ph * 4 + k) * gridDim.x + blockIdx.x] = globaltimer_ns();
     };
     for (int ph = 0; ph < mp.n_phases; ph++) {
-        const MegaPhase& P = mp.phases[ph];
+        const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<uint8_t*>(ph_s) + (ph & 1) * mega_phase_bytes());
         stamp(ph, 0);
+        if (ph + 1 < mp.n_phases) load_phase(ph + 1);
         if (P.kind == PH_GEMV) {
             const GemvParams& g = P.g;
             GemvSmem sm;
@@ -139,7 +152,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             sm.xsum = reinterpret_cast<int*>(sm.xs + g.n / GS);
             gemv_prologue<QT, MEGA_WARPS>(g, sm);
             stamp(ph, 1);
-            const WarpStreams<QT> w = make_streams<QT>(g, wslot, n_wslots);
+            const WarpStreams<QT> w = make_streams<QT>(sd_s[ph], wslot, n_wslots);
             float acc = 0.0f;
             for (int s = 0; s < w.nst; s++) {
                 const uint32_t slot = consumed % (uint32_t)depth;
