@@ -93,6 +93,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         }
         cp_async_commit();
     };
+    trace_event(200);
     // K tiles start flowing before anything else (rows < pos are in the cache since earlier steps)
 #pragma unroll
     for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.kcache, k, true);
@@ -120,6 +121,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     }
     __syncthreads();
 
+    trace_event(201);
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
     for (int tl = 0; tl < ntiles; tl++) {
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
@@ -159,6 +161,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     }
     cp_async_wait<0>();
     __syncthreads();
+    trace_event(202);
     // V tiles start flowing now; the softmax below runs while they land
 #pragma unroll
     for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.vcache, k, false);
@@ -180,6 +183,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         for (int t = tid; t < T; t += ATT_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
     }
     __syncthreads();
+    trace_event(203);
     if (lane == 0 && warp < nh) {   // the reference's `sum += x[i]` chain: one thread per head, in different warps
         const float* sc = sc_base + (size_t)warp * sc_stride;
         float sum = 0.0f;
@@ -193,6 +197,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         red[32 + warp] = sum;
     }
     __syncthreads();
+    trace_event(204);
     for (int h = 0; h < nh; h++) {
         float* sc = sc_base + (size_t)h * sc_stride;
         const float sum = red[32 + h];
@@ -201,6 +206,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     // (the barrier inside the first V-tile iteration orders these writes before the chains read them)
 
     // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542) --------------------------------------
+    trace_event(205);
     constexpr int MAXCH = (ATT_QH * HS + ATT_THREADS - 1) / ATT_THREADS;   // chains per thread
     float acc[MAXCH];
 #pragma unroll
@@ -232,6 +238,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         }
     }
     cp_async_wait<0>();
+    trace_event(206);
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) {
         const int idx = tid + k * ATT_THREADS;
@@ -255,7 +262,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
 // src/quantization.rs:25-42) and copies a row per token (:324, :659-669); here a row is dequantized on the fly
 // (value = code as f32 * scale: one multiply, bit-identical).  Gemma scales by sqrt(dim) (:327-332).
 struct EmbedParams {
-    const uint8_t* q; const float* s; const float* f32_table;
+    const uint8_t* q; const float* s; const float* f32_table;   // q: BP16 table (s unused)
     int dim, q_type; float scale_mul; int apply_scale;
     const uint32_t* tokens;  // device array (get_embeddings) or nullptr -> step->token
     const StepParams* step;
@@ -270,12 +277,8 @@ __global__ void embed_kernel(const EmbedParams p) {
         const size_t e = (size_t)tok * p.dim + i;
         float v;
         if (p.q_type == 0) v = p.f32_table[e];
-        else if (p.q_type == 1) v = __fmul_rn((float)reinterpret_cast<const int8_t*>(p.q)[e], p.s[e / GS]);
-        else {
-            const int b = p.q[e >> 1];
-            const int code = ((e & 1) ? (b >> 4) : (b & 15)) - 8;
-            v = __fmul_rn((float)code, p.s[e / GS]);
-        }
+        else if (p.q_type == 1) v = bp_value<1>(p.q, e);
+        else v = bp_value<2>(p.q, e);
         if (p.apply_scale) v = __fmul_rn(v, p.scale_mul);
         out[i] = v;
     }

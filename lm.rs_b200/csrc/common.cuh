@@ -93,6 +93,18 @@ LMRS_DEVINL int round_sat_u4(float v) {
     return (int)r;
 }
 
+// ---- developer trace: (tag, globaltimer) events of CTA 0 / thread 0 when enabled (LMRS_B200_TIMING=1) ----------
+__device__ unsigned long long* g_trace_buf = nullptr;   // [2 * cap] (tag, ns)
+__device__ unsigned int g_trace_n = 0;
+LMRS_DEVINL void trace_event(int tag) {
+    if (g_trace_buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        const unsigned int i = g_trace_n++;
+        if (i < 8192u) { g_trace_buf[2 * i] = (unsigned long long)tag; g_trace_buf[2 * i + 1] = t; }
+    }
+}
+
 LMRS_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -43,7 +43,7 @@ struct StepParams {
 };
 
 struct GemvParams {
-    const uint8_t* wq_a; const float* ws_a;   // matrix A: q codes, group scales
+    const uint8_t* wq_a; const float* ws_a;   // matrix A: block-packed (BP16) weights; ws_* unused (scales ride in the blocks)
     const uint8_t* wq_b; const float* ws_b;   // matrix B (GLU: w3), else unused
     int n, o, row_gran;
     int pro;
@@ -51,7 +51,7 @@ struct GemvParams {
     int x_in_stride;   // serial prefill: x_in += step->token * x_in_stride (row of the staged embeddings)
     float eps; int unit_offset;
     // PRO_NORM may take x_in from the embedding table instead (decode step, src/transformer.rs:324-332):
-    const uint8_t* emb_q; const float* emb_s; int emb_qtype; float emb_mul; int emb_apply_mul;
+    const uint8_t* emb_q; const float* emb_s; int emb_qtype; float emb_mul; int emb_apply_mul;   // emb_q: BP16 table
     const float* act_in;
     const uint8_t* raw_q; const float* raw_s;
     int epi;
@@ -65,7 +65,40 @@ template <int QT> struct QTraits;
 template <> struct QTraits<1> { static constexpr int QB = 128; };  // bytes of codes per group, Q8_0
 template <> struct QTraits<2> { static constexpr int QB = 64; };   // Q4_0
 
-template <int QT> __host__ __device__ constexpr int gemv_stage_bytes() { return 2 * SG * QTraits<QT>::QB + 2 * SG * 4; }
+// Weights live in HBM in a block-packed layout ("BP16"): the matrix's quantization groups in row-major order, 16 per
+// block, each block = 16 x QB code bytes followed by the 16 f32 group scales (2112 B for Q8_0, 1088 B for Q4_0).  A
+// half-warp stage is exactly one block, i.e. ONE bulk copy that brings codes and scales together (the file keeps
+// them in two separate arrays; lmrs_b200.cu repacks at load time).  The last block is zero-padded.
+template <int QT> __host__ __device__ constexpr int blk_bytes() { return SG * QTraits<QT>::QB + SG * 4; }
+template <int QT> __host__ __device__ constexpr int gemv_stage_bytes() { return 2 * blk_bytes<QT>(); }
+// element e of a block-packed Q8/Q4 tensor (embedding gather): value = code as f32 * scale
+template <int QT> LMRS_DEVINL float bp_value(const uint8_t* base, size_t e) {
+    constexpr int QB = QTraits<QT>::QB;
+    const size_t f = e / GS; const int k = (int)(e % GS);
+    const uint8_t* blk = base + (f / SG) * blk_bytes<QT>();
+    const int gi = (int)(f % SG);
+    const float sc = reinterpret_cast<const float*>(blk + SG * QB)[gi];
+    int code;
+    if (QT == 1) code = reinterpret_cast<const int8_t*>(blk)[gi * QB + k];
+    else { const int b = blk[gi * QB + (k >> 1)]; code = ((k & 1) ? (b >> 4) : (b & 15)) - 8; }
+    return __fmul_rn((float)code, sc);
+}
+// file layout ([o][n] codes + [o][n/128] scales) -> BP16
+template <int QT> __global__ void repack_bp16_kernel(uint8_t* dst, const uint8_t* src_q, const float* src_s, size_t n_groups) {
+    constexpr int QB = QTraits<QT>::QB;
+    const size_t b = blockIdx.x;
+    uint8_t* out = dst + b * blk_bytes<QT>();
+    for (int i = threadIdx.x; i < SG * QB / 16; i += blockDim.x) {   // 16-byte chunks of codes
+        const size_t f = b * SG + (size_t)(i * 16) / QB;
+        int4 v = make_int4(0, 0, 0, 0);
+        if (f < n_groups) v = *reinterpret_cast<const int4*>(src_q + b * SG * QB + (size_t)i * 16);
+        reinterpret_cast<int4*>(out)[i] = v;
+    }
+    if (threadIdx.x < SG) {
+        const size_t f = b * SG + threadIdx.x;
+        reinterpret_cast<float*>(out + SG * QB)[threadIdx.x] = f < n_groups ? src_s[f] : 0.0f;
+    }
+}
 
 // shared-memory footprint of one CTA (must match the carve-up in the kernel)
 template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n, bool norm) {
@@ -78,10 +111,11 @@ template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n, boo
 
 struct RowRange { int row0, nrows; };
 LMRS_DEVINL RowRange slot_rows(int slot, int nslots, int o, int gran) {
-    int units = o / gran;
+    int units = (o + gran - 1) / gran;               // the last unit may be short
     int a = (int)(((long long)slot * units) / nslots);
     int b = (int)(((long long)(slot + 1) * units) / nslots);
-    return {a * gran, (b - a) * gran};
+    int r0 = a * gran, r1 = min(b * gran, o);
+    return {r0, max(r1 - r0, 0)};
 }
 
 template <int WARPS> LMRS_DEVINL float block_sum(float v, float* red) {
@@ -103,15 +137,24 @@ LMRS_DEVINL float exact_rnorm(const float* xf, int n, float eps, float* red) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         float s = 0.0f;
-        if (lane < 8) {
+        if (lane < 8) {   // software-pipelined: the next 8 loads are in flight while this batch's dependent adds run
             const int steps = n / 8;
+            float xa[8], xb[8];
             int j = 0;
-            for (; j + 8 <= steps; j += 8) {
-                float x[8];
+            if (steps >= 8) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) x[u] = xf[8 * (j + u) + lane];
+                for (int u = 0; u < 8; u++) xa[u] = xf[8 * u + lane];
+                for (; j + 16 <= steps; j += 8) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(x[u], x[u]));
+                    for (int u = 0; u < 8; u++) xb[u] = xf[8 * (j + 8 + u) + lane];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(xa[u], xa[u]));
+#pragma unroll
+                    for (int u = 0; u < 8; u++) xa[u] = xb[u];
+                }
+#pragma unroll
+                for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(xa[u], xa[u]));
+                j += 8;
             }
             for (; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
         }
@@ -175,8 +218,7 @@ struct GemvSmem {
 template <int QT> struct WarpStreams {
     RowRange r0, r1;
     int ng0, ng1, nst, G;
-    const uint8_t *srcq0, *srcq1;
-    const float *srcs0, *srcs1;
+    const uint8_t *src0, *src1;      // first block of each half's stream
     bool glu;
 };
 // the part of GemvParams that defines the weight streams (kept in shared memory by the megakernel)
@@ -187,7 +229,6 @@ struct StreamDesc {
 LMRS_DEVINL StreamDesc stream_desc(const GemvParams& p) { return {p.wq_a, p.ws_a, p.wq_b, p.ws_b, p.n, p.o, p.row_gran, p.epi}; }
 template <int QT>
 LMRS_DEVINL WarpStreams<QT> make_streams(const StreamDesc& p, int wslot, int n_wslots) {
-    constexpr int QB = QTraits<QT>::QB;
     WarpStreams<QT> w;
     w.glu = (p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU);
     w.G = p.n / GS;
@@ -196,26 +237,19 @@ LMRS_DEVINL WarpStreams<QT> make_streams(const StreamDesc& p, int wslot, int n_w
     w.r1 = w.glu ? w.r0 : slot_rows(wslot * 2 + 1, nslots, p.o, p.row_gran);
     w.ng0 = w.r0.nrows * w.G; w.ng1 = w.r1.nrows * w.G;
     w.nst = max((w.ng0 + SG - 1) / SG, (w.ng1 + SG - 1) / SG);
-    w.srcq0 = p.wq_a + (size_t)w.r0.row0 * w.G * QB;
-    w.srcs0 = p.ws_a + (size_t)w.r0.row0 * w.G;
-    w.srcq1 = (w.glu ? p.wq_b : p.wq_a) + (size_t)w.r1.row0 * w.G * QB;
-    w.srcs1 = (w.glu ? p.ws_b : p.ws_a) + (size_t)w.r1.row0 * w.G;
+    w.src0 = p.wq_a + ((size_t)w.r0.row0 * w.G / SG) * blk_bytes<QT>();      // row0 * G is a multiple of 16 (row_gran)
+    w.src1 = (w.glu ? p.wq_b : p.wq_a) + ((size_t)w.r1.row0 * w.G / SG) * blk_bytes<QT>();
     return w;
 }
-// lane 0: stream stage s of both halves into one ring slot (4 bulk copies, one mbarrier)
+// lane 0: stream stage s of both halves into one ring slot: one block-sized bulk copy per half, one mbarrier.
+// Weights are read exactly once per token: L2 evict_first keeps the KV cache and the activations resident instead.
 template <int QT>
-LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint64_t* bar) {
-    constexpr int QB = QTraits<QT>::QB;
-    const int c0 = min(SG, max(0, w.ng0 - SG * s)), c1 = min(SG, max(0, w.ng1 - SG * s));
-    mbar_expect_tx(bar, (uint32_t)((c0 + c1) * (QB + 4)));
-    if (c0 > 0) {
-        bulk_g2s(buf, w.srcq0 + (size_t)s * SG * QB, c0 * QB, bar);
-        bulk_g2s(buf + 2 * SG * QB, w.srcs0 + (size_t)s * SG, c0 * 4, bar);
-    }
-    if (c1 > 0) {
-        bulk_g2s(buf + SG * QB, w.srcq1 + (size_t)s * SG * QB, c1 * QB, bar);
-        bulk_g2s(buf + 2 * SG * QB + SG * 4, w.srcs1 + (size_t)s * SG, c1 * 4, bar);
-    }
+LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint64_t* bar, uint64_t pol) {
+    constexpr int BLK = blk_bytes<QT>();
+    const bool h0 = w.ng0 > SG * s, h1 = w.ng1 > SG * s;
+    mbar_expect_tx(bar, (uint32_t)((h0 ? BLK : 0) + (h1 ? BLK : 0)));
+    if (h0) bulk_g2s_hint(buf, w.src0 + (size_t)s * BLK, BLK, bar, pol);
+    if (h1) bulk_g2s_hint(buf + BLK, w.src1 + (size_t)s * BLK, BLK, bar, pol);
 }
 
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
@@ -224,6 +258,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     constexpr int THREADS = WARPS * 32;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
+    trace_event(100 + p.pro);
     if (p.pro == PRO_NORM) {
         const int nchunks = n / 4;
         float4 v[NORM_MAXC], wnv[NORM_MAXC];
@@ -243,15 +278,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (c < nchunks) {
                     const size_t e = (size_t)tok * n + (size_t)c * 4;
-                    const float sc = p.emb_s[e / GS];
-                    if (p.emb_qtype == 1) {
-                        const char4 q4 = *reinterpret_cast<const char4*>(p.emb_q + e);
-                        t = make_float4(__fmul_rn((float)q4.x, sc), __fmul_rn((float)q4.y, sc), __fmul_rn((float)q4.z, sc), __fmul_rn((float)q4.w, sc));
-                    } else {
-                        const uchar2 b = *reinterpret_cast<const uchar2*>(p.emb_q + (e >> 1));
-                        t = make_float4(__fmul_rn((float)((b.x & 15) - 8), sc), __fmul_rn((float)((b.x >> 4) - 8), sc),
-                                        __fmul_rn((float)((b.y & 15) - 8), sc), __fmul_rn((float)((b.y >> 4) - 8), sc));
-                    }
+                    t = make_float4(bp_value<QT>(p.emb_q, e), bp_value<QT>(p.emb_q, e + 1), bp_value<QT>(p.emb_q, e + 2), bp_value<QT>(p.emb_q, e + 3));
                     if (p.emb_apply_mul) { t.x = __fmul_rn(t.x, p.emb_mul); t.y = __fmul_rn(t.y, p.emb_mul); t.z = __fmul_rn(t.z, p.emb_mul); t.w = __fmul_rn(t.w, p.emb_mul); }
                 }
                 v[k] = t;
@@ -313,7 +340,9 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
             if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = v[k];
         }
         __syncthreads();
+        trace_event(110);
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
+        trace_event(111);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
             const int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
@@ -368,6 +397,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
     }
     __syncthreads();
+    trace_event(119);
 }
 
 // ---- one stage of one warp: 32 group dot products, ordered f32 accumulation, epilogue -------------------------------
@@ -386,7 +416,7 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
     if (valid) {
         int iv0 = 0, iv1 = 0;
         if (QT == 1) {
-            const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+            const int4* wv = reinterpret_cast<const int4*>(buf + half * blk_bytes<QT>() + l16 * QB);
             const int4* xv = reinterpret_cast<const int4*>(sm.xq + (size_t)g * GS);
 #pragma unroll
             for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
@@ -397,7 +427,7 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
             }
             iv0 += iv1;
         } else {
-            const int4* wv = reinterpret_cast<const int4*>(buf + (half * SG + l16) * QB);
+            const int4* wv = reinterpret_cast<const int4*>(buf + half * blk_bytes<QT>() + l16 * QB);
             const int4* ev = reinterpret_cast<const int4*>(sm.xq + (size_t)g * (GS / 2));
             const int4* ov = reinterpret_cast<const int4*>(sm.xq + (size_t)(n / 2) + (size_t)g * (GS / 2));
 #pragma unroll
@@ -411,7 +441,7 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
             }
             iv0 = iv0 + iv1 - 8 * sm.xsum[g];   // sum x_s*(w_u - 8) = sum x_s*w_u - 8*sum x_s
         }
-        const float wsc = reinterpret_cast<const float*>(buf + 2 * SG * QB)[half * SG + l16];
+        const float wsc = reinterpret_cast<const float*>(buf + half * blk_bytes<QT>() + SG * QB)[l16];
         t = __fmul_rn(__fmul_rn((float)iv0, wsc), sm.xs[g]);   // (ival*ws)*xs, src/functional.rs:207,246
     }
     // ordered f32 accumulation across the 16 lanes of this half-warp (ascending group index)
@@ -481,8 +511,9 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
         fence_barrier_init();
     }
     __syncwarp();
+    const uint64_t pol = l2_policy_evict_first();
     if (lane == 0)   // weights never depend on the previous kernel: start streaming before griddepcontrol.wait
-        for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s]);
+        for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     pdl_launch_dependents();
     pdl_wait();  // upstream activations are complete and visible from here on
 
@@ -495,7 +526,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
         mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
         consume_stage<QT>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, acc, pos);
         __syncwarp();
-        if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d]);
+        if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
     }
 }
 

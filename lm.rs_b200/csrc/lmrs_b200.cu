@@ -77,6 +77,7 @@ struct lmrs_b200 {
     StreamDesc *d_sd_decode = nullptr, *d_sd_prefill = nullptr;
     std::vector<MegaPhase> ph_decode, ph_prefill;
     unsigned long long* d_bar = nullptr;      // [2] grid-barrier counters (decode, prefill variants)
+    unsigned long long* d_trace = nullptr;
     unsigned long long* d_timing = nullptr;   // LMRS_B200_TIMING=1: per-phase globaltimer stamps of the last decode step
     uint32_t seq_decode = 0, seq_prefill = 0;
     bool use_mega = true;
@@ -131,11 +132,22 @@ template <int QT> static size_t gemv_smem_for(int cfg, int n, bool norm) {
         default: return gemv_smem_bytes<QT, 4, 4>(n, norm);
     }
 }
+// stream boundaries must fall on BP16 block boundaries: row0 * G must be a multiple of 16 groups
 static int gran_for(int n) {
     int G = n / GS;
-    for (int r = 1; r <= 4; r *= 2)
-        if ((r * G) % 4 == 0) return r;
-    return 4;
+    for (int r = 1; r <= 16; r *= 2)
+        if ((r * G) % SG == 0) return r;
+    return 16;
+}
+static size_t bp16_bytes(int q_type, size_t o, size_t n) {
+    size_t groups = o * (n / GS), blocks = (groups + SG - 1) / SG;
+    return blocks * (q_type == 1 ? blk_bytes<1>() : blk_bytes<2>());
+}
+static cudaError_t repack_bp16(int q_type, uint8_t* dst, const uint8_t* src_q, const float* src_s, size_t o, size_t n, cudaStream_t st) {
+    size_t groups = o * (n / GS), blocks = (groups + SG - 1) / SG;
+    if (q_type == 1) repack_bp16_kernel<1><<<(unsigned)blocks, 128, 0, st>>>(dst, src_q, src_s, groups);
+    else repack_bp16_kernel<2><<<(unsigned)blocks, 128, 0, st>>>(dst, src_q, src_s, groups);
+    return cudaGetLastError();
 }
 
 static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
@@ -152,7 +164,7 @@ static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
     // never launch more CTAs than there are row units to hand out (tiny matrices)
     const bool glu = p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU;
     (void)glu;
-    int units = p.o / p.row_gran;
+    int units = (p.o + p.row_gran - 1) / p.row_gran;
     if (grid > units) grid = units < 1 ? 1 : units;   // at least one row unit per CTA; otherwise every SM takes part
     return launch(m, fn, dim3(grid), dim3(c.warps * 32), smem, p);
 }
@@ -343,29 +355,57 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
         p_cls.s = p_emb.s + (size_t)m->vocab_off * (dim / GS) * 4;
     }
     size_t rms_final = plan_vec(f_rms_final[0]);
-    m->arena_bytes = cur;
-
-    CK(cudaMalloc(&m->d_arena, m->arena_bytes));
+    // ---- upload in file layout to a staging buffer, then repack every matrix into the BP16 arena ------------------
+    uint8_t* d_stage = nullptr;
+    CK(cudaMalloc(&d_stage, cur));
     for (const Piece& pc : pieces) {
-        if (pc.rows <= 1) CK(cudaMemcpy(m->d_arena + pc.dst, pc.src, pc.bytes, cudaMemcpyHostToDevice));
-        else CK(cudaMemcpy2D(m->d_arena + pc.dst, pc.dst_stride, pc.src, pc.src_stride, pc.bytes, pc.rows, cudaMemcpyHostToDevice));
+        if (pc.rows <= 1) CK(cudaMemcpy(d_stage + pc.dst, pc.src, pc.bytes, cudaMemcpyHostToDevice));
+        else CK(cudaMemcpy2D(d_stage + pc.dst, pc.dst_stride, pc.src, pc.src_stride, pc.bytes, pc.rows, cudaMemcpyHostToDevice));
     }
-    auto mk = [&](const MatPlan& p) { Mat x; x.q = m->d_arena + p.q; x.s = (const float*)(m->d_arena + p.s); x.o = p.o; x.n = p.n; x.gran = gran_for(p.n); return x; };
+    size_t pcur = 0;
+    auto pplace = [&](size_t bytes) { size_t o = pcur; pcur = align_up(pcur + bytes, 256); return o; };
+    struct PackJob { size_t dst; MatPlan src; };
+    std::vector<PackJob> jobs;
+    struct VecJob { size_t dst, src; };
+    std::vector<VecJob> vjobs;
+    auto pk = [&](const MatPlan& p) { size_t d = pplace(bp16_bytes(a.q_type, p.o, p.n)); jobs.push_back({d, p}); return d; };
+    auto pv = [&](size_t src) { size_t d = pplace(dim * 4); vjobs.push_back({d, src}); return d; };
+    struct LayerPk { size_t qkv, wo, w1, w3, w2, rms_att, rms_post, rms_pre, rms_postffn; };
+    std::vector<LayerPk> lpk(L);
+    for (size_t l = 0; l < L; l++) {
+        lpk[l].qkv = pk(lp[l].qkv); lpk[l].wo = pk(lp[l].wo); lpk[l].w1 = pk(lp[l].w1); lpk[l].w3 = pk(lp[l].w3); lpk[l].w2 = pk(lp[l].w2);
+        lpk[l].rms_att = pv(lp[l].rms_att); lpk[l].rms_post = pv(lp[l].rms_post);
+        lpk[l].rms_pre = a.model_type == 0 ? pv(lp[l].rms_pre) : 0;
+        lpk[l].rms_postffn = a.model_type == 0 ? pv(lp[l].rms_postffn) : 0;
+    }
+    const size_t emb_pk = pk(p_emb);
+    size_t cls_pk = emb_pk;
+    if (a.model_type == 2) cls_pk = pk(p_cls);
+    else if (W > 1) {   // tied classifier: this rank's vocab rows are a block-aligned sub-range of the packed table
+        if (((size_t)m->vocab_off * (dim / GS)) % SG) { cudaFree(d_stage); return fail("vocab shard is not BP16 block aligned"); }
+        cls_pk = emb_pk + ((size_t)m->vocab_off * (dim / GS) / SG) * (a.q_type == 1 ? blk_bytes<1>() : blk_bytes<2>());
+    }
+    const size_t rms_final_pk = pv(rms_final);
+    m->arena_bytes = pcur;
+    CK(cudaMalloc(&m->d_arena, m->arena_bytes));
+    for (const PackJob& j : jobs)
+        CK(repack_bp16(a.q_type, m->d_arena + j.dst, d_stage + j.src.q, (const float*)(d_stage + j.src.s), j.src.o, j.src.n, 0));
+    for (const VecJob& j : vjobs) CK(cudaMemcpy(m->d_arena + j.dst, d_stage + j.src, dim * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaDeviceSynchronize());
+    cudaFree(d_stage);
+    auto mk = [&](size_t off, int o, int n) { Mat x; x.q = m->d_arena + off; x.s = nullptr; x.o = o; x.n = n; x.gran = gran_for(n); return x; };
     auto fp = [&](size_t o) { return (const float*)(m->d_arena + o); };
     m->layers.resize(L);
     for (size_t l = 0; l < L; l++) {
         Layer& Y = m->layers[l];
-        Y.qkv = mk(lp[l].qkv); Y.wo = mk(lp[l].wo); Y.w1 = mk(lp[l].w1); Y.w3 = mk(lp[l].w3); Y.w2 = mk(lp[l].w2);
-        Y.rms_att = fp(lp[l].rms_att); Y.rms_post_att = fp(lp[l].rms_post);
-        if (a.model_type == 0) { Y.rms_pre_ffn = fp(lp[l].rms_pre); Y.rms_post_ffn = fp(lp[l].rms_postffn); }
+        Y.qkv = mk(lpk[l].qkv, lp[l].qkv.o, lp[l].qkv.n); Y.wo = mk(lpk[l].wo, lp[l].wo.o, lp[l].wo.n);
+        Y.w1 = mk(lpk[l].w1, lp[l].w1.o, lp[l].w1.n); Y.w3 = mk(lpk[l].w3, lp[l].w3.o, lp[l].w3.n); Y.w2 = mk(lpk[l].w2, lp[l].w2.o, lp[l].w2.n);
+        Y.rms_att = fp(lpk[l].rms_att); Y.rms_post_att = fp(lpk[l].rms_post);
+        if (a.model_type == 0) { Y.rms_pre_ffn = fp(lpk[l].rms_pre); Y.rms_post_ffn = fp(lpk[l].rms_postffn); }
     }
-    m->emb = mk(p_emb);
-    m->cls = mk(p_cls);
-    m->rms_final = fp(rms_final);
-    for (const Layer& Y : m->layers)
-        for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
-            if (x->o % x->gran) return fail("row count not divisible by the stream granularity");
-    if (m->cls.o % m->cls.gran) return fail("vocab shard not divisible by the stream granularity");
+    m->emb = mk(emb_pk, p_emb.o, p_emb.n);
+    m->cls = mk(cls_pk, p_cls.o, p_cls.n);
+    m->rms_final = fp(rms_final_pk);
 
     // ---- state: f32 KV cache (src/transformer.rs:302-303), RoPE tables, activations ---------------------------
     const size_t kv_elems = L * (size_t)a.seq_len * lk;
@@ -632,6 +672,11 @@ static int setup_mega(lmrs_b200* m) {
         size_t n = (size_t)(5 * m->args.n_layers + 2) * 4 * m->sms;
         CK(cudaMalloc(&m->d_timing, n * 8));
         CK(cudaMemset(m->d_timing, 0, n * 8));
+        unsigned long long* tb;
+        CK(cudaMalloc(&tb, 2 * 8192 * 8));
+        CK(cudaMemset(tb, 0, 2 * 8192 * 8));
+        CK(cudaMemcpyToSymbol(g_trace_buf, &tb, sizeof(tb)));
+        m->d_trace = tb;
     }
     return 0;
 }
@@ -842,6 +887,17 @@ extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* o
     else if (nm == "wo_out") { src = m->d_wo_out; cnt = m->args.dim; }
     else if (nm == "h") { src = m->d_h; cnt = m->l_hidden; }
     else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
+    else if (nm == "trace_reset") {
+        unsigned int z = 0;
+        CK(cudaStreamSynchronize(m->stream));
+        CK(cudaMemcpyToSymbol(g_trace_n, &z, sizeof(z)));
+        *n = 0;
+        return 0;
+    }
+    else if (nm == "trace") {
+        if (!m->d_trace) return fail("trace not enabled (LMRS_B200_TIMING=1)");
+        src = (const float*)m->d_trace; cnt = 2 * 8192 * 2;
+    }
     else if (nm == "timing") {   // raw 64-bit stamps viewed as pairs of floats: [n_phases][4][sms] u64
         if (!m->d_timing) return fail("timing not enabled (LMRS_B200_TIMING=1)");
         src = (const float*)m->d_timing; cnt = (size_t)m->ph_decode.size() * 4 * m->sms * 2;

@@ -63,8 +63,7 @@ LMRS_DEVINL void grid_barrier(unsigned long long* ctr, unsigned long long target
     __syncthreads();   // every thread's writes happen-before thread 0's release (cumulativity)
     if (threadIdx.x == 0) {
         asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(ctr), "l"(1ULL) : "memory");
-        while (ld_acquire_u64(ctr) < target) {
-        }
+        while (ld_acquire_u64(ctr) < target) __nanosleep(32);   // back off: 148 pollers on one L2 line slow everyone
     }
     __syncthreads();
 }
@@ -123,9 +122,10 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
         }
     };
     uint32_t issued = 0, consumed = 0;
+    const uint64_t pol = l2_policy_evict_first();
     auto pf_issue = [&]() {
         const uint32_t slot = issued % (uint32_t)depth;
-        if (lane == 0) issue_stage<QT>(pf_w, pf_stage, ring + (size_t)slot * STAGE, &bars[slot]);
+        if (lane == 0) issue_stage<QT>(pf_w, pf_stage, ring + (size_t)slot * STAGE, &bars[slot], pol);
         issued++;
         pf_stage++;
         pf_seek();
@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
     for (int ph = 0; ph < mp.n_phases; ph++) {
         const MegaPhase& P = *reinterpret_cast<const MegaPhase*>(reinterpret_cast<uint8_t*>(ph_s) + (ph & 1) * mega_phase_bytes());
         stamp(ph, 0);
+        trace_event(1000 + ph);
         if (ph + 1 < mp.n_phases) load_phase(ph + 1);
         if (P.kind == PH_GEMV) {
             const GemvParams& g = P.g;
@@ -175,6 +176,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             if (blockIdx.x == 0) residual_finalize_body(P.r, red);
         }
         if (mp.timing) { __syncthreads(); stamp(ph, 2); }
+        trace_event(900);
         if (ph + 1 < mp.n_phases) grid_barrier(mp.bar_ctr, base + (unsigned long long)(ph + 1) * gridDim.x);
         stamp(ph, 3);
     }

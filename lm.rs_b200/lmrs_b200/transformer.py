@@ -106,7 +106,7 @@ class Transformer:
 
     def debug_buffer(self, name: str) -> np.ndarray:
         cap = max(self.args.hidden_dim, self.args.dim, self.args.n_heads * self.args.head_size,
-                  (5 * self.args.n_layers + 2) * 4 * 160 * 2 if name == "timing" else 0)
+                  (5 * self.args.n_layers + 2) * 4 * 160 * 2 if name == "timing" else 0, 2 * 8192 * 2 if name == "trace" else 0)
         out, n = np.zeros(cap, np.float32), C.c_size_t(cap)
         check(lib().lmrs_b200_debug_buffer(self._h, name.encode(), _vp(out), C.byref(n)))
         return out[: n.value].copy()

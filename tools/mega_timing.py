@@ -40,3 +40,22 @@ print("phase    n   prologue  work(mean)  work(max)  barrier-after-last  total  
 for k, v in agg.items():
     v = np.array(v, dtype=np.float64) / 1e3
     print(f"{k:7s} {len(v):3d}   {v[:,0].mean():7.2f}   {v[:,1].mean():8.2f}   {v[:,2].mean():8.2f}   {v[:,3].mean():10.2f}      {v[:,4].mean():7.2f}   sum {v[:,4].sum():8.1f}")
+
+# ---- fine trace of CTA 0 for one step ---------------------------------------------------------------------------
+m.debug_buffer("trace_reset")
+m.forward_device(11, pos0 + 4)
+m.synchronize()
+tr = m.debug_buffer("trace").view(np.uint64).reshape(-1, 2)
+tr = tr[tr[:, 1] > 0]
+print("trace events:", len(tr))
+t00 = int(tr[0, 1])
+# print layer 2 (phases 10..14) in detail
+sel = False
+prev = None
+for tag, ts in tr:
+    tag = int(tag); ts = int(ts)
+    if tag == 1010: sel = True
+    if tag == 1016: break
+    if sel:
+        print(f"  tag {tag:5d}  t={ (ts - t00)/1e3:9.2f} us  (+{0 if prev is None else (ts-prev)/1e3:6.2f})")
+        prev = ts
