@@ -13,7 +13,7 @@
 
 namespace lmrs {
 
-constexpr int ATT_THREADS = 256;
+constexpr int ATT_THREADS = 256;   // stand-alone kernel; the megakernel runs the same body with its own block size
 constexpr int ATT_QH = 4;        // query heads per CTA (all sharing one KV head)
 constexpr int ATT_SC_CAP = 1024; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
 constexpr int ATT_NT = 4;        // K/V tiles in flight (cp.async ring)
@@ -34,7 +34,7 @@ struct AttnParams {
 
 template <int HS> __host__ __device__ constexpr int att_tile_rows() { return HS <= 64 ? 64 : (HS <= 128 ? 32 : 16); }
 template <int HS> __host__ __device__ constexpr size_t attn_smem_bytes() {
-    return (size_t)(ATT_QH * HS + HS + ATT_NT * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 64) * 4;
+    return (size_t)(ATT_QH * HS + HS + ATT_NT * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 128) * 4;
 }
 
 LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
@@ -51,18 +51,19 @@ template <int N> LMRS_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_
 // rotated by the row index, which makes the per-position LDS.128 dot products bank-conflict-free without
 // touching the ascending-d summation order.  Latency floor: the two T-long dependent add chains (softmax sum,
 // a*v) -- the price of exact parity, see exact_math.cuh.
-template <int HS>
+template <int HS, int NTHR>
 LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const int kvh, const int h0, const int nh,
                                   const bool write_k) {
+    constexpr int NWARP = NTHR / 32;
     constexpr int TILE = att_tile_rows<HS>();
     constexpr int C4 = HS / 4;                         // 16-byte chunks per row
     constexpr int CHUNKS = TILE * C4;                  // per tile
-    constexpr int PERT = (CHUNKS + ATT_THREADS - 1) / ATT_THREADS;
+    constexpr int PERT = (CHUNKS + NTHR - 1) / NTHR;
     float* q_s = att_smem;                             // [ATT_QH][HS]
     float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
     float* tile = k_s + HS;                            // [ATT_NT][TILE][HS]
     float* sc_s = tile + ATT_NT * TILE * HS;           // [ATT_QH][ATT_SC_CAP]
-    float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [64]
+    float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [128]: per-head per-warp maxima, then sums at [96..]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pos = (int)p.step->pos;
@@ -80,7 +81,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             float* tb = tile + (tl % ATT_NT) * TILE * HS;
 #pragma unroll
             for (int i = 0; i < PERT; i++) {
-                const int e = tid + i * ATT_THREADS;
+                const int e = tid + i * NTHR;
                 if (e < CHUNKS) {
                     const int r = e / C4, c = e - r * C4, t = tl * TILE + r;
                     if (t < T && !(rotate && t == pos)) {
@@ -101,14 +102,14 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
     const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
-    for (int i = tid; i < nh * (HS / 2); i += ATT_THREADS) {
+    for (int i = tid; i < nh * (HS / 2); i += NTHR) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
         const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
         q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
     }
-    for (int j = tid; j < HS / 2; j += ATT_THREADS) {
+    for (int j = tid; j < HS / 2; j += NTHR) {
         const float fcr = cs[j], fci = sn[j];
         const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
         const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
@@ -128,7 +129,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         float* tb = tile + (tl % ATT_NT) * TILE * HS;
         if (pos / TILE == tl) {                        // the new K row comes from shared memory, same rotated layout
             const int r = pos - tl * TILE;
-            for (int d = tid; d < HS; d += ATT_THREADS) {
+            for (int d = tid; d < HS; d += NTHR) {
                 const int c = d >> 2;
                 tb[r * HS + ((c + r) % C4) * 4 + (d & 3)] = k_s[d];
             }
@@ -136,7 +137,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         __syncthreads();                               // tile tl visible; everyone is done with tile tl-1
         issue_tile(p.kcache, tl + ATT_NT - 1, true);   // refill the slot tile tl-1 used
         const int rows = min(TILE, T - tl * TILE);
-        for (int idx = tid; idx < rows * nh; idx += ATT_THREADS) {
+        for (int idx = tid; idx < rows * nh; idx += NTHR) {
             const int h = idx / rows, r = idx - h * rows, t = tl * TILE + r;
             const float4* q4 = reinterpret_cast<const float4*>(q_s + h * HS);
             const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
@@ -145,8 +146,8 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 #pragma unroll 4
             for (int d4 = 0; d4 < C4; d4++) {
                 const float4 qv = q4[d4], kv = k4[c];
-                score = __fadd_rn(score, __fmul_rn(qv.x, kv.x)); score = __fadd_rn(score, __fmul_rn(qv.y, kv.y));
-                score = __fadd_rn(score, __fmul_rn(qv.z, kv.z)); score = __fadd_rn(score, __fmul_rn(qv.w, kv.w));
+                const float p0 = __fmul_rn(qv.x, kv.x), p1 = __fmul_rn(qv.y, kv.y), p2 = __fmul_rn(qv.z, kv.z), p3 = __fmul_rn(qv.w, kv.w);
+                score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
                 c = (c + 1 == C4) ? 0 : c + 1;
             }
             score = __fdiv_rn(score, p.sqrt_hs);
@@ -170,17 +171,17 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     for (int h = 0; h < nh; h++) {
         float* sc = sc_base + (size_t)h * sc_stride;
         float mx = sc[0];
-        for (int t = tid; t < T; t += ATT_THREADS) mx = fmaxf(mx, sc[t]);
+        for (int t = tid; t < T; t += NTHR) mx = fmaxf(mx, sc[t]);
         mx = warp_max(mx);
-        if (lane == 0) red[h * 8 + warp] = mx;
+        if (lane == 0) red[h * NWARP + warp] = mx;
     }
     __syncthreads();
     for (int h = 0; h < nh; h++) {
         float* sc = sc_base + (size_t)h * sc_stride;
-        float mx = red[h * 8];
+        float mx = red[h * NWARP];
 #pragma unroll
-        for (int w = 1; w < ATT_THREADS / 32; w++) mx = fmaxf(mx, red[h * 8 + w]);
-        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
+        for (int w = 1; w < NWARP; w++) mx = fmaxf(mx, red[h * NWARP + w]);
+        for (int t = tid; t < T; t += NTHR) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
     }
     __syncthreads();
     trace_event(203);
@@ -188,26 +189,33 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const float* sc = sc_base + (size_t)warp * sc_stride;
         float sum = 0.0f;
         int t = 0;
-        for (; t + 8 <= T; t += 8) {
-            const float4 a = *reinterpret_cast<const float4*>(sc + t), b = *reinterpret_cast<const float4*>(sc + t + 4);
+        if (T >= 8) {   // next 8 values are loaded while the current 8 dependent adds run (4 cycles each)
+            float4 a = *reinterpret_cast<const float4*>(sc), b = *reinterpret_cast<const float4*>(sc + 4);
+            for (; t + 16 <= T; t += 8) {
+                const float4 na = *reinterpret_cast<const float4*>(sc + t + 8), nb = *reinterpret_cast<const float4*>(sc + t + 12);
+                sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
+                sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
+                a = na; b = nb;
+            }
             sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
             sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
+            t += 8;
         }
         for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
-        red[32 + warp] = sum;
+        red[96 + warp] = sum;
     }
     __syncthreads();
     trace_event(204);
     for (int h = 0; h < nh; h++) {
         float* sc = sc_base + (size_t)h * sc_stride;
-        const float sum = red[32 + h];
-        for (int t = tid; t < T; t += ATT_THREADS) sc[t] = __fdiv_rn(sc[t], sum);
+        const float sum = red[96 + h];
+        for (int t = tid; t < T; t += NTHR) sc[t] = __fdiv_rn(sc[t], sum);
     }
     // (the barrier inside the first V-tile iteration orders these writes before the chains read them)
 
     // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542) --------------------------------------
     trace_event(205);
-    constexpr int MAXCH = (ATT_QH * HS + ATT_THREADS - 1) / ATT_THREADS;   // chains per thread
+    constexpr int MAXCH = (ATT_QH * HS + NTHR - 1) / NTHR;   // chains per thread
     float acc[MAXCH];
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) acc[k] = 0.0f;
@@ -219,18 +227,20 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const int rows = min(TILE, T - tl * TILE);
 #pragma unroll
         for (int k = 0; k < MAXCH; k++) {
-            const int idx = tid + k * ATT_THREADS;
+            const int idx = tid + k * NTHR;
             if (idx < nh * HS) {
                 const int h = idx / HS, d = idx - h * HS;
                 const float* a = sc_base + (size_t)h * sc_stride + tl * TILE;
                 float x = acc[k];
                 int r = 0;
-                for (; r + 4 <= rows; r += 4) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(a + r);
-                    x = __fadd_rn(x, __fmul_rn(a4.x, tb[r * HS + d]));
-                    x = __fadd_rn(x, __fmul_rn(a4.y, tb[(r + 1) * HS + d]));
-                    x = __fadd_rn(x, __fmul_rn(a4.z, tb[(r + 2) * HS + d]));
-                    x = __fadd_rn(x, __fmul_rn(a4.w, tb[(r + 3) * HS + d]));
+                for (; r + 8 <= rows; r += 8) {
+                    const float4 a4 = *reinterpret_cast<const float4*>(a + r), b4 = *reinterpret_cast<const float4*>(a + r + 4);
+                    const float p0 = __fmul_rn(a4.x, tb[r * HS + d]), p1 = __fmul_rn(a4.y, tb[(r + 1) * HS + d]);
+                    const float p2 = __fmul_rn(a4.z, tb[(r + 2) * HS + d]), p3 = __fmul_rn(a4.w, tb[(r + 3) * HS + d]);
+                    const float p4 = __fmul_rn(b4.x, tb[(r + 4) * HS + d]), p5 = __fmul_rn(b4.y, tb[(r + 5) * HS + d]);
+                    const float p6 = __fmul_rn(b4.z, tb[(r + 6) * HS + d]), p7 = __fmul_rn(b4.w, tb[(r + 7) * HS + d]);
+                    x = __fadd_rn(x, p0); x = __fadd_rn(x, p1); x = __fadd_rn(x, p2); x = __fadd_rn(x, p3);
+                    x = __fadd_rn(x, p4); x = __fadd_rn(x, p5); x = __fadd_rn(x, p6); x = __fadd_rn(x, p7);
                 }
                 for (; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
                 acc[k] = x;
@@ -241,7 +251,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     trace_event(206);
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) {
-        const int idx = tid + k * ATT_THREADS;
+        const int idx = tid + k * NTHR;
         if (idx < nh * HS) p.out[(size_t)h0 * HS + idx] = acc[k];
     }
     __syncthreads();   // the tile ring / score buffers may be reused by the caller
@@ -255,7 +265,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
     pdl_launch_dependents();
     pdl_wait();
-    attn_decode_body<HS>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
+    attn_decode_body<HS, ATT_THREADS>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
 }
 
 // ---- embedding row gather: the reference dequantizes the whole table at load (src/transformer.rs:243-245,

@@ -101,7 +101,7 @@ LMRS_DEVINL void trace_event(int tag) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
         const unsigned int i = g_trace_n++;
-        if (i < 8192u) { g_trace_buf[2 * i] = (unsigned long long)tag; g_trace_buf[2 * i + 1] = t; }
+        if (i < 8192u) { g_trace_buf[2 * i] = ((unsigned long long)clock64() << 16) | (unsigned long long)(tag & 0xffff); g_trace_buf[2 * i + 1] = t; }
     }
 }
 

@@ -30,7 +30,7 @@ namespace lmrs {
 
 constexpr int GS = 128;          // quantization group size (elements); the exporter always writes 128 (utils/io.py:21)
 constexpr int SG = 16;           // groups per half-warp stream per stage
-constexpr int NORM_MAXC = 4;     // float4 chunks per thread kept in registers by PRO_NORM
+constexpr int NORM_MAX_DIM = 4096;  // PRO_NORM keeps the vector in registers: dim <= 4096
 
 enum { PRO_NORM = 0, PRO_QUANT = 1, PRO_RAW = 2 };
 enum { EPI_STORE = 0, EPI_QKV = 1, EPI_GLU_SILU = 2, EPI_GLU_GELU = 3, EPI_LOGITS = 4 };
@@ -137,9 +137,9 @@ LMRS_DEVINL float exact_rnorm(const float* xf, int n, float eps, float* red) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         float s = 0.0f;
-        if (lane < 8) {   // software-pipelined: the next 8 loads are in flight while this batch's dependent adds run
+        if (lane < 8) {   // products first (independent), then the dependent adds: 4 cycles per element, loads prefetched
             const int steps = n / 8;
-            float xa[8], xb[8];
+            float xa[8], xb[8], pr[8];
             int j = 0;
             if (steps >= 8) {
 #pragma unroll
@@ -148,12 +148,16 @@ LMRS_DEVINL float exact_rnorm(const float* xf, int n, float eps, float* red) {
 #pragma unroll
                     for (int u = 0; u < 8; u++) xb[u] = xf[8 * (j + 8 + u) + lane];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(xa[u], xa[u]));
+                    for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(xa[u], xa[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) s = __fadd_rn(s, pr[u]);
 #pragma unroll
                     for (int u = 0; u < 8; u++) xa[u] = xb[u];
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) s = __fadd_rn(s, __fmul_rn(xa[u], xa[u]));
+                for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(xa[u], xa[u]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) s = __fadd_rn(s, pr[u]);
                 j += 8;
             }
             for (; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
@@ -256,6 +260,7 @@ LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint
 template <int QT, int WARPS>
 LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     constexpr int THREADS = WARPS * 32;
+    constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
     trace_event(100 + p.pro);
@@ -401,9 +406,51 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
 }
 
 // ---- one stage of one warp: 32 group dot products, ordered f32 accumulation, epilogue -------------------------------
+// Per-phase consumer state.  `aligned` (G % 16 == 0, every real model): a half-warp stage lies inside one row, so the
+// row/group bookkeeping is warp-uniform and incremental (no integer division, no per-step selects in the scan).
+// `xreg` (Q8, G == 16): lane l always meets activation group l, which then lives in 32 registers for the whole phase.
+template <int QT> struct Consumer {
+    float acc;
+    int row_l, g_base;
+    bool aligned, xreg;
+    int4 xr[8];
+};
+template <int QT>
+LMRS_DEVINL void consumer_begin(Consumer<QT>& c, const WarpStreams<QT>& w, const GemvSmem& sm) {
+    const int l16 = threadIdx.x & 15;
+    c.acc = 0.0f; c.row_l = 0; c.g_base = 0;
+    c.aligned = (w.G % SG) == 0;
+    c.xreg = (QT == 1) && w.G == SG;
+    if (c.xreg) {
+        const int4* xv = reinterpret_cast<const int4*>(sm.xq + (size_t)l16 * GS);
+#pragma unroll
+        for (int i = 0; i < 8; i++) c.xr[i] = xv[(i + l16) & 7];
+    }
+}
+LMRS_DEVINL float glu_act(int epi, float val) {
+    if (epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
+        const float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
+        const float th = (float)tanh(0.7978845608028654 * (double)inner);
+        return __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
+    }
+    return __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));   // SiLU (:617), exp = glibc expf
+}
+LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos) {
+    if (p.epi == EPI_QKV) {
+        if (row < p.att_dim) p.out[row] = v;
+        else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = v;
+        else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = v;
+    } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
+        float t = __fdiv_rn(v, 30.0f);   // src/transformer.rs:375-381
+        t = (float)tanh((double)t);
+        p.out[row] = __fmul_rn(t, 30.0f);
+    } else {
+        p.out[row] = v;
+    }
+}
 template <int QT>
 LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, int s, const uint8_t* buf, const GemvSmem& sm,
-                               float& acc, uint32_t pos) {
+                               Consumer<QT>& c, uint32_t pos) {
     constexpr int QB = QTraits<QT>::QB;
     const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
     const int n = p.n, G = w.G;
@@ -411,29 +458,39 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
     const int ng = half ? w.ng1 : w.ng0;
     const int f = s * SG + l16;           // index of my group inside my stream
     const bool valid = f < ng;
-    const int row_l = f / G, g = f - row_l * G;
+    int row_l, g;
+    if (c.aligned) { row_l = c.row_l; g = c.g_base + l16; }
+    else { row_l = f / G; g = f - row_l * G; }
     float t = 0.0f;
     if (valid) {
         int iv0 = 0, iv1 = 0;
+        const int4* wv = reinterpret_cast<const int4*>(buf + half * blk_bytes<QT>() + l16 * QB);
         if (QT == 1) {
-            const int4* wv = reinterpret_cast<const int4*>(buf + half * blk_bytes<QT>() + l16 * QB);
-            const int4* xv = reinterpret_cast<const int4*>(sm.xq + (size_t)g * GS);
+            if (c.xreg) {
 #pragma unroll
-            for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
-                const int c = (i + l16) & 7;
-                const int4 w4 = wv[c], x4 = xv[c];
-                iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
-                iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
+                for (int i = 0; i < 8; i++) {
+                    const int4 w4 = wv[(i + l16) & 7], x4 = c.xr[i];
+                    iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
+                    iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
+                }
+            } else {
+                const int4* xv = reinterpret_cast<const int4*>(sm.xq + (size_t)g * GS);
+#pragma unroll
+                for (int i = 0; i < 8; i++) {   // 16-byte column rotated by lane: conflict-free LDS.128
+                    const int cc = (i + l16) & 7;
+                    const int4 w4 = wv[cc], x4 = xv[cc];
+                    iv0 = dp4a_ss(w4.x, x4.x, iv0); iv1 = dp4a_ss(w4.y, x4.y, iv1);
+                    iv0 = dp4a_ss(w4.z, x4.z, iv0); iv1 = dp4a_ss(w4.w, x4.w, iv1);
+                }
             }
             iv0 += iv1;
         } else {
-            const int4* wv = reinterpret_cast<const int4*>(buf + half * blk_bytes<QT>() + l16 * QB);
             const int4* ev = reinterpret_cast<const int4*>(sm.xq + (size_t)g * (GS / 2));
             const int4* ov = reinterpret_cast<const int4*>(sm.xq + (size_t)(n / 2) + (size_t)g * (GS / 2));
 #pragma unroll
             for (int i = 0; i < 4; i++) {
-                const int c = (i + (l16 >> 1)) & 3;
-                const int4 w4 = wv[c], e4 = ev[c], o4 = ov[c];
+                const int cc = (i + (l16 >> 1)) & 3;
+                const int4 w4 = wv[cc], e4 = ev[cc], o4 = ov[cc];
                 iv0 = dp4a_su(e4.x, (uint32_t)w4.x & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.x, ((uint32_t)w4.x >> 4) & 0x0F0F0F0Fu, iv1);
                 iv0 = dp4a_su(e4.y, (uint32_t)w4.y & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.y, ((uint32_t)w4.y >> 4) & 0x0F0F0F0Fu, iv1);
                 iv0 = dp4a_su(e4.z, (uint32_t)w4.z & 0x0F0F0F0Fu, iv0); iv1 = dp4a_su(o4.z, ((uint32_t)w4.z >> 4) & 0x0F0F0F0Fu, iv1);
@@ -444,42 +501,39 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
         const float wsc = reinterpret_cast<const float*>(buf + half * blk_bytes<QT>() + SG * QB)[l16];
         t = __fmul_rn(__fmul_rn((float)iv0, wsc), sm.xs[g]);   // (ival*ws)*xs, src/functional.rs:207,246
     }
-    // ordered f32 accumulation across the 16 lanes of this half-warp (ascending group index)
+    if (c.aligned) {
+        // the whole half-warp stage belongs to one row: plain ordered sum of its 16 terms, ascending group index
+        float a = (c.g_base == 0) ? 0.0f : c.acc;
+#pragma unroll
+        for (int j = 0; j < SG; j++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, t, j, 16));
+        c.acc = a;
+        const bool row_done = (c.g_base + SG == G);
+        if (w.glu) {
+            const float up = __shfl_sync(0xffffffffu, a, 16);
+            if (row_done && lane == 0 && valid) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, a), up);
+        } else if (row_done && l16 == 0 && valid) {
+            store_row(p, rr.row0 + row_l, a, pos);
+        }
+        c.g_base += SG;
+        if (c.g_base == G) { c.g_base = 0; c.row_l++; }
+        return;
+    }
+    // generic path (G not a multiple of 16: tiny test models): rows may start/end anywhere inside the stage
     const bool is_last = valid && (g == G - 1);
     const uint32_t first_mask = __ballot_sync(0xffffffffu, valid && g == 0) >> (half * 16);
-    float mine = 0.0f;
+    float mine = 0.0f, acc = c.acc;
 #pragma unroll
     for (int j = 0; j < SG; j++) {
         const float tj = __shfl_sync(0xffffffffu, t, j, 16);
         acc = __fadd_rn(((first_mask >> j) & 1u) ? 0.0f : acc, tj);
         if (j == l16) mine = acc;
     }
+    c.acc = acc;
     if (w.glu) {
         const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
-        if (is_last && half == 0) {
-            float val = mine;
-            if (p.epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
-                const float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
-                const float th = (float)tanh(0.7978845608028654 * (double)inner);
-                val = __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
-            } else {                       // SiLU (src/transformer.rs:617), exp = glibc expf
-                val = __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));
-            }
-            p.out[rr.row0 + row_l] = __fmul_rn(val, up);
-        }
+        if (is_last && half == 0) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, mine), up);
     } else if (is_last) {
-        const int row = rr.row0 + row_l;
-        if (p.epi == EPI_QKV) {
-            if (row < p.att_dim) p.out[row] = mine;
-            else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = mine;
-            else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = mine;
-        } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
-            float v = __fdiv_rn(mine, 30.0f);   // src/transformer.rs:375-381
-            v = (float)tanh((double)v);
-            p.out[row] = __fmul_rn(v, 30.0f);
-        } else {
-            p.out[row] = mine;
-        }
+        store_row(p, rr.row0 + row_l, mine, pos);
     }
 }
 
@@ -520,11 +574,12 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     gemv_prologue<QT, WARPS>(p, sm);
 
     const uint32_t pos = (p.epi == EPI_QKV) ? p.step->pos : 0u;
-    float acc = 0.0f;
+    Consumer<QT> cs;
+    consumer_begin<QT>(cs, w, sm);
     for (int s = 0; s < w.nst; s++) {
         const int d = s % DEPTH;
         mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
-        consume_stage<QT>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, acc, pos);
+        consume_stage<QT>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, cs, pos);
         __syncwarp();
         if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
     }

@@ -724,7 +724,7 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     if (m->gemv_cfg < 0 || m->gemv_cfg > 4) m->gemv_cfg = 0;
     m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
-    if ((int)m->args.dim > NORM_MAXC * 4 * kGemvCfgs[m->gemv_cfg].warps * 32) {
+    if ((int)m->args.dim > NORM_MAX_DIM) {
         lmrs_b200_destroy(m);
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
     }

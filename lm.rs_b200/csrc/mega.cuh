@@ -22,8 +22,8 @@
 
 namespace lmrs {
 
-constexpr int MEGA_WARPS = 8;          // == ATT_THREADS / 32
-constexpr int MEGA_MAX_DEPTH = 6;
+constexpr int MEGA_WARPS = 16;         // 4 warps per scheduler: the per-stage dependent chains need the extra TLP
+constexpr int MEGA_MAX_DEPTH = 4;
 
 enum { PH_GEMV = 0, PH_ATTN = 1, PH_FINALIZE = 2 };
 
@@ -154,11 +154,12 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             gemv_prologue<QT, MEGA_WARPS>(g, sm);
             stamp(ph, 1);
             const WarpStreams<QT> w = make_streams<QT>(sd_s[ph], wslot, n_wslots);
-            float acc = 0.0f;
+            Consumer<QT> cs;
+            consumer_begin<QT>(cs, w, sm);
             for (int s = 0; s < w.nst; s++) {
                 const uint32_t slot = consumed % (uint32_t)depth;
                 mbar_wait(&bars[slot], (consumed / (uint32_t)depth) & 1u);
-                consume_stage<QT>(g, w, s, ring + (size_t)slot * STAGE, sm, acc, pos);
+                consume_stage<QT>(g, w, s, ring + (size_t)slot * STAGE, sm, cs, pos);
                 __syncwarp();
                 consumed++;
                 if (pf_phase < mp.n_phases) pf_issue();   // refill the slot just freed with the stage DEPTH ahead
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
                 const int h0 = kvh * P.a.kv_mul + chunk * ATT_QH;
                 const int nh = min(ATT_QH, P.a.kv_mul - chunk * ATT_QH);
                 __syncthreads();
-                attn_decode_body<HS>(P.a, reinterpret_cast<float*>(uni), kvh, h0, nh, chunk == 0);
+                attn_decode_body<HS, MEGA_WARPS * 32>(P.a, reinterpret_cast<float*>(uni), kvh, h0, nh, chunk == 0);
             }
         } else {   // PH_FINALIZE: residual stream row back to the caller (fill_kv_cache), one CTA
             if (blockIdx.x == 0) residual_finalize_body(P.r, red);

@@ -47,7 +47,9 @@ m.forward_device(11, pos0 + 4)
 m.synchronize()
 tr = m.debug_buffer("trace").view(np.uint64).reshape(-1, 2)
 tr = tr[tr[:, 1] > 0]
-print("trace events:", len(tr))
+clk = (tr[:, 0] >> np.uint64(16)).astype(np.int64)
+tr = np.stack([(tr[:, 0] & np.uint64(0xffff)).astype(np.int64), tr[:, 1].astype(np.int64)], axis=1)
+print("trace events:", len(tr), " SM clock over the step: %.0f MHz" % ((clk[-1] - clk[0]) / ((tr[-1, 1] - tr[0, 1]) / 1e3)))
 t00 = int(tr[0, 1])
 # print layer 2 (phases 10..14) in detail
 sel = False
