@@ -143,13 +143,18 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
             float score = 0.0f;
             int c = r % C4;                             // rotated position of chunk 0
+            // products of chunk d4+1 are formed while chunk d4's four dependent adds run
+            float4 qv = q4[0], kv = k4[c];
+            float p0 = __fmul_rn(qv.x, kv.x), p1 = __fmul_rn(qv.y, kv.y), p2 = __fmul_rn(qv.z, kv.z), p3 = __fmul_rn(qv.w, kv.w);
 #pragma unroll 4
-            for (int d4 = 0; d4 < C4; d4++) {
-                const float4 qv = q4[d4], kv = k4[c];
-                const float p0 = __fmul_rn(qv.x, kv.x), p1 = __fmul_rn(qv.y, kv.y), p2 = __fmul_rn(qv.z, kv.z), p3 = __fmul_rn(qv.w, kv.w);
-                score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
+            for (int d4 = 1; d4 < C4; d4++) {
                 c = (c + 1 == C4) ? 0 : c + 1;
+                qv = q4[d4]; kv = k4[c];
+                const float n0 = __fmul_rn(qv.x, kv.x), n1 = __fmul_rn(qv.y, kv.y), n2 = __fmul_rn(qv.z, kv.z), n3 = __fmul_rn(qv.w, kv.w);
+                score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
+                p0 = n0; p1 = n1; p2 = n2; p3 = n3;
             }
+            score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
             score = __fdiv_rn(score, p.sqrt_hs);
             if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
                 score = __fdiv_rn(score, 50.0f);
@@ -189,17 +194,20 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const float* sc = sc_base + (size_t)warp * sc_stride;
         float sum = 0.0f;
         int t = 0;
-        if (T >= 8) {   // next 8 values are loaded while the current 8 dependent adds run (4 cycles each)
+        if (T >= 24) {   // two batches of 8 are always in flight ahead of the 8 dependent adds being executed
             float4 a = *reinterpret_cast<const float4*>(sc), b = *reinterpret_cast<const float4*>(sc + 4);
-            for (; t + 16 <= T; t += 8) {
-                const float4 na = *reinterpret_cast<const float4*>(sc + t + 8), nb = *reinterpret_cast<const float4*>(sc + t + 12);
+            float4 c = *reinterpret_cast<const float4*>(sc + 8), d = *reinterpret_cast<const float4*>(sc + 12);
+            for (; t + 24 <= T; t += 8) {
+                const float4 e = *reinterpret_cast<const float4*>(sc + t + 16), f = *reinterpret_cast<const float4*>(sc + t + 20);
                 sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
                 sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-                a = na; b = nb;
+                a = c; b = d; c = e; d = f;
             }
             sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
             sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-            t += 8;
+            sum = __fadd_rn(sum, c.x); sum = __fadd_rn(sum, c.y); sum = __fadd_rn(sum, c.z); sum = __fadd_rn(sum, c.w);
+            sum = __fadd_rn(sum, d.x); sum = __fadd_rn(sum, d.y); sum = __fadd_rn(sum, d.z); sum = __fadd_rn(sum, d.w);
+            t += 16;
         }
         for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
         red[96 + warp] = sum;
@@ -233,14 +241,26 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 const float* a = sc_base + (size_t)h * sc_stride + tl * TILE;
                 float x = acc[k];
                 int r = 0;
-                for (; r + 8 <= rows; r += 8) {
-                    const float4 a4 = *reinterpret_cast<const float4*>(a + r), b4 = *reinterpret_cast<const float4*>(a + r + 4);
-                    const float p0 = __fmul_rn(a4.x, tb[r * HS + d]), p1 = __fmul_rn(a4.y, tb[(r + 1) * HS + d]);
-                    const float p2 = __fmul_rn(a4.z, tb[(r + 2) * HS + d]), p3 = __fmul_rn(a4.w, tb[(r + 3) * HS + d]);
-                    const float p4 = __fmul_rn(b4.x, tb[(r + 4) * HS + d]), p5 = __fmul_rn(b4.y, tb[(r + 5) * HS + d]);
-                    const float p6 = __fmul_rn(b4.z, tb[(r + 6) * HS + d]), p7 = __fmul_rn(b4.w, tb[(r + 7) * HS + d]);
-                    x = __fadd_rn(x, p0); x = __fadd_rn(x, p1); x = __fadd_rn(x, p2); x = __fadd_rn(x, p3);
-                    x = __fadd_rn(x, p4); x = __fadd_rn(x, p5); x = __fadd_rn(x, p6); x = __fadd_rn(x, p7);
+                if (rows >= 16) {   // products of the next 8 rows are formed while this batch's 8 dependent adds run
+                    float pr[8], np[8];
+                    {
+                        const float4 a4 = *reinterpret_cast<const float4*>(a), b4 = *reinterpret_cast<const float4*>(a + 4);
+                        pr[0] = __fmul_rn(a4.x, tb[d]); pr[1] = __fmul_rn(a4.y, tb[HS + d]); pr[2] = __fmul_rn(a4.z, tb[2 * HS + d]); pr[3] = __fmul_rn(a4.w, tb[3 * HS + d]);
+                        pr[4] = __fmul_rn(b4.x, tb[4 * HS + d]); pr[5] = __fmul_rn(b4.y, tb[5 * HS + d]); pr[6] = __fmul_rn(b4.z, tb[6 * HS + d]); pr[7] = __fmul_rn(b4.w, tb[7 * HS + d]);
+                    }
+                    for (; r + 16 <= rows; r += 8) {
+                        const float4 a4 = *reinterpret_cast<const float4*>(a + r + 8), b4 = *reinterpret_cast<const float4*>(a + r + 12);
+                        const float* tv = tb + (r + 8) * HS + d;
+                        np[0] = __fmul_rn(a4.x, tv[0]); np[1] = __fmul_rn(a4.y, tv[HS]); np[2] = __fmul_rn(a4.z, tv[2 * HS]); np[3] = __fmul_rn(a4.w, tv[3 * HS]);
+                        np[4] = __fmul_rn(b4.x, tv[4 * HS]); np[5] = __fmul_rn(b4.y, tv[5 * HS]); np[6] = __fmul_rn(b4.z, tv[6 * HS]); np[7] = __fmul_rn(b4.w, tv[7 * HS]);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[u]);
+#pragma unroll
+                        for (int u = 0; u < 8; u++) pr[u] = np[u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[u]);
+                    r += 8;
                 }
                 for (; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
                 acc[k] = x;

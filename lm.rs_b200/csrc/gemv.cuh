@@ -137,30 +137,37 @@ LMRS_DEVINL float exact_rnorm(const float* xf, int n, float eps, float* red) {
     if (threadIdx.x < 32) {
         const int lane = threadIdx.x;
         float s = 0.0f;
-        if (lane < 8) {   // products first (independent), then the dependent adds: 4 cycles per element, loads prefetched
+        if (lane < 8) {
+            // software pipeline, two batches deep: while batch k's eight dependent adds run (the critical path,
+            // ~4 cycles each), batch k+1's products are already in registers and batch k+2's loads are in flight
             const int steps = n / 8;
-            float xa[8], xb[8], pr[8];
-            int j = 0;
-            if (steps >= 8) {
+            const int nb = steps / 8;
+            float pa[8], pb[8], xc[8];
+            if (nb >= 2) {
 #pragma unroll
-                for (int u = 0; u < 8; u++) xa[u] = xf[8 * u + lane];
-                for (; j + 16 <= steps; j += 8) {
+                for (int u = 0; u < 8; u++) { const float x = xf[8 * u + lane]; pa[u] = __fmul_rn(x, x); }
 #pragma unroll
-                    for (int u = 0; u < 8; u++) xb[u] = xf[8 * (j + 8 + u) + lane];
+                for (int u = 0; u < 8; u++) xc[u] = xf[8 * (8 + u) + lane];
+                for (int b = 0; b + 2 < nb; b++) {
 #pragma unroll
-                    for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(xa[u], xa[u]);
+                    for (int u = 0; u < 8; u++) pb[u] = __fmul_rn(xc[u], xc[u]);
 #pragma unroll
-                    for (int u = 0; u < 8; u++) s = __fadd_rn(s, pr[u]);
+                    for (int u = 0; u < 8; u++) xc[u] = xf[8 * ((b + 2) * 8 + u) + lane];
 #pragma unroll
-                    for (int u = 0; u < 8; u++) xa[u] = xb[u];
+                    for (int u = 0; u < 8; u++) s = __fadd_rn(s, pa[u]);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) pa[u] = pb[u];
                 }
 #pragma unroll
-                for (int u = 0; u < 8; u++) pr[u] = __fmul_rn(xa[u], xa[u]);
+                for (int u = 0; u < 8; u++) pb[u] = __fmul_rn(xc[u], xc[u]);
 #pragma unroll
-                for (int u = 0; u < 8; u++) s = __fadd_rn(s, pr[u]);
-                j += 8;
+                for (int u = 0; u < 8; u++) s = __fadd_rn(s, pa[u]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) s = __fadd_rn(s, pb[u]);
+                for (int j = nb * 8; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
+            } else {
+                for (int j = 0; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
             }
-            for (; j < steps; j++) { const float x = xf[8 * j + lane]; s = __fadd_rn(s, __fmul_rn(x, x)); }
         }
         const float t = __fadd_rn(s, __shfl_sync(0xffffffffu, s, (lane + 4) & 31));   // lanes 0..3: a_l + a_{l+4}
         const float u = __fadd_rn(t, __shfl_sync(0xffffffffu, t, (lane + 2) & 31));   // lane 0: s0+s2, lane 1: s1+s3
