@@ -124,7 +124,9 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 
     trace_event(201);
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
+    long long a_wait = 0, a_comp = 0;
     for (int tl = 0; tl < ntiles; tl++) {
+        const long long ca = clock64();
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
         float* tb = tile + (tl % ATT_NT) * TILE * HS;
         if (pos / TILE == tl) {                        // the new K row comes from shared memory, same rotated layout
@@ -135,36 +137,53 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             }
         }
         __syncthreads();                               // tile tl visible; everyone is done with tile tl-1
+        const long long cb = clock64();
+        a_wait += cb - ca;
         issue_tile(p.kcache, tl + ATT_NT - 1, true);   // refill the slot tile tl-1 used
         const int rows = min(TILE, T - tl * TILE);
-        for (int idx = tid; idx < rows * nh; idx += NTHR) {
-            const int h = idx / rows, r = idx - h * rows, t = tl * TILE + r;
-            const float4* q4 = reinterpret_cast<const float4*>(q_s + h * HS);
+        // thread = (row r, pair of heads): one LDS.128 of K feeds two independent dot-product chains (ILP 2),
+        // products of chunk d4+1 are formed while chunk d4's dependent adds run
+        const int npair = (nh + 1) / 2;
+        for (int idx = tid; idx < rows * npair; idx += NTHR) {
+            const int hp = idx / rows, r = idx - hp * rows, t = tl * TILE + r;
+            const int ha = hp * 2, hb = min(hp * 2 + 1, nh - 1);
+            const float4* qa = reinterpret_cast<const float4*>(q_s + ha * HS);
+            const float4* qb = reinterpret_cast<const float4*>(q_s + hb * HS);
             const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
-            float score = 0.0f;
+            float sa = 0.0f, sb = 0.0f;
             int c = r % C4;                             // rotated position of chunk 0
-            // products of chunk d4+1 are formed while chunk d4's four dependent adds run
-            float4 qv = q4[0], kv = k4[c];
-            float p0 = __fmul_rn(qv.x, kv.x), p1 = __fmul_rn(qv.y, kv.y), p2 = __fmul_rn(qv.z, kv.z), p3 = __fmul_rn(qv.w, kv.w);
+            float4 kv = k4[c], q0 = qa[0], q1 = qb[0];
+            float a0 = __fmul_rn(q0.x, kv.x), a1 = __fmul_rn(q0.y, kv.y), a2 = __fmul_rn(q0.z, kv.z), a3 = __fmul_rn(q0.w, kv.w);
+            float b0 = __fmul_rn(q1.x, kv.x), b1 = __fmul_rn(q1.y, kv.y), b2 = __fmul_rn(q1.z, kv.z), b3 = __fmul_rn(q1.w, kv.w);
 #pragma unroll 4
             for (int d4 = 1; d4 < C4; d4++) {
                 c = (c + 1 == C4) ? 0 : c + 1;
-                qv = q4[d4]; kv = k4[c];
-                const float n0 = __fmul_rn(qv.x, kv.x), n1 = __fmul_rn(qv.y, kv.y), n2 = __fmul_rn(qv.z, kv.z), n3 = __fmul_rn(qv.w, kv.w);
-                score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
-                p0 = n0; p1 = n1; p2 = n2; p3 = n3;
+                kv = k4[c]; q0 = qa[d4]; q1 = qb[d4];
+                const float n0 = __fmul_rn(q0.x, kv.x), n1 = __fmul_rn(q0.y, kv.y), n2 = __fmul_rn(q0.z, kv.z), n3 = __fmul_rn(q0.w, kv.w);
+                const float m0 = __fmul_rn(q1.x, kv.x), m1 = __fmul_rn(q1.y, kv.y), m2 = __fmul_rn(q1.z, kv.z), m3 = __fmul_rn(q1.w, kv.w);
+                sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
+                sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
+                a0 = n0; a1 = n1; a2 = n2; a3 = n3; b0 = m0; b1 = m1; b2 = m2; b3 = m3;
             }
-            score = __fadd_rn(score, p0); score = __fadd_rn(score, p1); score = __fadd_rn(score, p2); score = __fadd_rn(score, p3);
-            score = __fdiv_rn(score, p.sqrt_hs);
-            if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
-                score = __fdiv_rn(score, 50.0f);
-                score = (float)tanh((double)score);
-                score = __fmul_rn(score, 50.0f);
-                score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
+            sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
+            sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const int h = w ? hb : ha;
+                if (w == 1 && hb == ha) break;
+                float score = __fdiv_rn(w ? sb : sa, p.sqrt_hs);
+                if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
+                    score = __fdiv_rn(score, 50.0f);
+                    score = (float)tanh((double)score);
+                    score = __fmul_rn(score, 50.0f);
+                    score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
+                }
+                sc_base[(size_t)h * sc_stride + t] = score;
             }
-            sc_base[(size_t)h * sc_stride + t] = score;
         }
+        a_comp += clock64() - cb;
     }
+    trace_value(310, (unsigned long long)a_wait); trace_value(311, (unsigned long long)a_comp);
     cp_async_wait<0>();
     __syncthreads();
     trace_event(202);
@@ -223,10 +242,14 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 
     // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542) --------------------------------------
     trace_event(205);
-    constexpr int MAXCH = (ATT_QH * HS + NTHR - 1) / NTHR;   // chains per thread
-    float acc[MAXCH];
+    // thread = (dim d, pair of heads): one V element feeds two independent accumulation chains (ILP 2); the
+    // products of the next four rows are formed while the current four dependent adds run
+    constexpr int NPMAX = ATT_QH / 2;
+    constexpr int MAXCH = (NPMAX * HS + NTHR - 1) / NTHR;   // (d, head-pair) items per thread
+    const int npair = (nh + 1) / 2;
+    float acca[MAXCH], accb[MAXCH];
 #pragma unroll
-    for (int k = 0; k < MAXCH; k++) acc[k] = 0.0f;
+    for (int k = 0; k < MAXCH; k++) { acca[k] = 0.0f; accb[k] = 0.0f; }
     for (int tl = 0; tl < ntiles; tl++) {
         cp_async_wait<ATT_NT - 2>();
         __syncthreads();
@@ -236,34 +259,39 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 #pragma unroll
         for (int k = 0; k < MAXCH; k++) {
             const int idx = tid + k * NTHR;
-            if (idx < nh * HS) {
-                const int h = idx / HS, d = idx - h * HS;
-                const float* a = sc_base + (size_t)h * sc_stride + tl * TILE;
-                float x = acc[k];
+            if (idx < npair * HS) {
+                const int hp = idx / HS, d = idx - hp * HS;
+                const int ha = hp * 2, hb = min(hp * 2 + 1, nh - 1);
+                const float* pa = sc_base + (size_t)ha * sc_stride + tl * TILE;
+                const float* pb = sc_base + (size_t)hb * sc_stride + tl * TILE;
+                const float* tv = tb + d;
+                float xa = acca[k], xb = accb[k];
                 int r = 0;
-                if (rows >= 16) {   // products of the next 8 rows are formed while this batch's 8 dependent adds run
-                    float pr[8], np[8];
-                    {
-                        const float4 a4 = *reinterpret_cast<const float4*>(a), b4 = *reinterpret_cast<const float4*>(a + 4);
-                        pr[0] = __fmul_rn(a4.x, tb[d]); pr[1] = __fmul_rn(a4.y, tb[HS + d]); pr[2] = __fmul_rn(a4.z, tb[2 * HS + d]); pr[3] = __fmul_rn(a4.w, tb[3 * HS + d]);
-                        pr[4] = __fmul_rn(b4.x, tb[4 * HS + d]); pr[5] = __fmul_rn(b4.y, tb[5 * HS + d]); pr[6] = __fmul_rn(b4.z, tb[6 * HS + d]); pr[7] = __fmul_rn(b4.w, tb[7 * HS + d]);
+                if (rows >= 8) {
+                    float4 a4 = *reinterpret_cast<const float4*>(pa), b4 = *reinterpret_cast<const float4*>(pb);
+                    float v0 = tv[0], v1 = tv[HS], v2 = tv[2 * HS], v3 = tv[3 * HS];
+                    float p0 = __fmul_rn(a4.x, v0), p1 = __fmul_rn(a4.y, v1), p2 = __fmul_rn(a4.z, v2), p3 = __fmul_rn(a4.w, v3);
+                    float q0 = __fmul_rn(b4.x, v0), q1 = __fmul_rn(b4.y, v1), q2 = __fmul_rn(b4.z, v2), q3 = __fmul_rn(b4.w, v3);
+                    for (; r + 8 <= rows; r += 4) {
+                        a4 = *reinterpret_cast<const float4*>(pa + r + 4); b4 = *reinterpret_cast<const float4*>(pb + r + 4);
+                        const float* tn = tv + (r + 4) * HS;
+                        v0 = tn[0]; v1 = tn[HS]; v2 = tn[2 * HS]; v3 = tn[3 * HS];
+                        const float n0 = __fmul_rn(a4.x, v0), n1 = __fmul_rn(a4.y, v1), n2 = __fmul_rn(a4.z, v2), n3 = __fmul_rn(a4.w, v3);
+                        const float m0 = __fmul_rn(b4.x, v0), m1 = __fmul_rn(b4.y, v1), m2 = __fmul_rn(b4.z, v2), m3 = __fmul_rn(b4.w, v3);
+                        xa = __fadd_rn(xa, p0); xb = __fadd_rn(xb, q0); xa = __fadd_rn(xa, p1); xb = __fadd_rn(xb, q1);
+                        xa = __fadd_rn(xa, p2); xb = __fadd_rn(xb, q2); xa = __fadd_rn(xa, p3); xb = __fadd_rn(xb, q3);
+                        p0 = n0; p1 = n1; p2 = n2; p3 = n3; q0 = m0; q1 = m1; q2 = m2; q3 = m3;
                     }
-                    for (; r + 16 <= rows; r += 8) {
-                        const float4 a4 = *reinterpret_cast<const float4*>(a + r + 8), b4 = *reinterpret_cast<const float4*>(a + r + 12);
-                        const float* tv = tb + (r + 8) * HS + d;
-                        np[0] = __fmul_rn(a4.x, tv[0]); np[1] = __fmul_rn(a4.y, tv[HS]); np[2] = __fmul_rn(a4.z, tv[2 * HS]); np[3] = __fmul_rn(a4.w, tv[3 * HS]);
-                        np[4] = __fmul_rn(b4.x, tv[4 * HS]); np[5] = __fmul_rn(b4.y, tv[5 * HS]); np[6] = __fmul_rn(b4.z, tv[6 * HS]); np[7] = __fmul_rn(b4.w, tv[7 * HS]);
-#pragma unroll
-                        for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[u]);
-#pragma unroll
-                        for (int u = 0; u < 8; u++) pr[u] = np[u];
-                    }
-#pragma unroll
-                    for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[u]);
-                    r += 8;
+                    xa = __fadd_rn(xa, p0); xb = __fadd_rn(xb, q0); xa = __fadd_rn(xa, p1); xb = __fadd_rn(xb, q1);
+                    xa = __fadd_rn(xa, p2); xb = __fadd_rn(xb, q2); xa = __fadd_rn(xa, p3); xb = __fadd_rn(xb, q3);
+                    r += 4;
                 }
-                for (; r < rows; r++) x = __fadd_rn(x, __fmul_rn(a[r], tb[r * HS + d]));
-                acc[k] = x;
+                for (; r < rows; r++) {
+                    const float v = tv[r * HS];
+                    xa = __fadd_rn(xa, __fmul_rn(pa[r], v));
+                    xb = __fadd_rn(xb, __fmul_rn(pb[r], v));
+                }
+                acca[k] = xa; accb[k] = xb;
             }
         }
     }
@@ -272,7 +300,11 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 #pragma unroll
     for (int k = 0; k < MAXCH; k++) {
         const int idx = tid + k * NTHR;
-        if (idx < nh * HS) p.out[(size_t)h0 * HS + idx] = acc[k];
+        if (idx < npair * HS) {
+            const int hp = idx / HS, d = idx - hp * HS;
+            p.out[(size_t)(h0 + hp * 2) * HS + d] = acca[k];
+            if (hp * 2 + 1 < nh) p.out[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
+        }
     }
     __syncthreads();   // the tile ring / score buffers may be reused by the caller
 }

@@ -887,10 +887,9 @@ extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* o
     else if (nm == "wo_out") { src = m->d_wo_out; cnt = m->args.dim; }
     else if (nm == "h") { src = m->d_h; cnt = m->l_hidden; }
     else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
-    else if (nm == "trace_reset") {
-        unsigned int z = 0;
+    else if (nm == "trace_reset") {   // the device-side counter restarts with every launch
         CK(cudaStreamSynchronize(m->stream));
-        CK(cudaMemcpyToSymbol(g_trace_n, &z, sizeof(z)));
+        if (m->d_trace) CK(cudaMemset(m->d_trace, 0, 2 * 8192 * 8));
         *n = 0;
         return 0;
     }

@@ -51,7 +51,7 @@ clk = (tr[:, 0] >> np.uint64(16)).astype(np.int64)
 tr = np.stack([(tr[:, 0] & np.uint64(0xffff)).astype(np.int64), tr[:, 1].astype(np.int64)], axis=1)
 print("trace events:", len(tr), " SM clock over the step: %.0f MHz" % ((clk[-1] - clk[0]) / ((tr[-1, 1] - tr[0, 1]) / 1e3)))
 t00 = int(tr[0, 1])
-# print layer 2 (phases 10..14) in detail
+# print layer 2 (phases 10..14) in detail; tags 300-311 carry cycle counters, not timestamps
 sel = False
 prev = None
 for tag, ts in tr:
@@ -59,5 +59,8 @@ for tag, ts in tr:
     if tag == 1010: sel = True
     if tag == 1016: break
     if sel:
-        print(f"  tag {tag:5d}  t={ (ts - t00)/1e3:9.2f} us  (+{0 if prev is None else (ts-prev)/1e3:6.2f})")
-        prev = ts
+        if 300 <= tag < 400:
+            print(f"  tag {tag:5d}  value {ts}")
+        else:
+            print(f"  tag {tag:5d}  t={ (ts - t00)/1e3:9.2f} us  (+{0 if prev is None else (ts-prev)/1e3:6.2f})")
+            prev = ts
