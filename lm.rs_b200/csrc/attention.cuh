@@ -28,6 +28,7 @@ struct AttnParams {
     float* out;            // [att_dim]
     float* scores;         // scratch [n_heads][seq_len] used when pos+1 > ATT_SC_CAP
     int kv_dim, kv_mul, chunks, gemma, seq_len;
+    int batch, q_stride;   // batched prefill: grid.y = token index; pos = step->pos + blockIdx.y, q/out rows strided
     float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
     const StepParams* step;
 };
@@ -66,8 +67,12 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [128]: per-head per-warp maxima, then sums at [96..]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int pos = (int)p.step->pos;
+    const int brow = p.batch ? (int)blockIdx.y : 0;
+    const int pos = (int)p.step->pos + brow;
     const uint32_t mask_base = p.step->mask_base;
+    const float* q_in = p.q + (size_t)brow * p.q_stride;
+    float* out_row = p.out + (size_t)brow * p.q_stride;
+    const bool have_knew = p.k_new != nullptr;   // decode: K row of this step arrives un-rotated in a staging row
     const int T = pos + 1;
     const bool in_smem = T <= ATT_SC_CAP;
     float* sc_base = in_smem ? sc_s : p.scores + (size_t)h0 * p.seq_len;
@@ -84,7 +89,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 const int e = tid + i * NTHR;
                 if (e < CHUNKS) {
                     const int r = e / C4, c = e - r * C4, t = tl * TILE + r;
-                    if (t < T && !(rotate && t == pos)) {
+                    if (t < T && !(rotate && have_knew && t == pos)) {
                         int cc = c;
                         if (rotate) { cc = c + r; cc = cc % C4; }
                         cp_async16(tb + r * HS + cc * 4, base + (size_t)t * p.kv_dim + (size_t)kvh * HS + c * 4);
@@ -105,10 +110,11 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     for (int i = tid; i < nh * (HS / 2); i += NTHR) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
-        const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
-        q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-        q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+        const float v0 = __ldcg(q_in + (size_t)(h0 + h) * HS + j), v1 = __ldcg(q_in + (size_t)(h0 + h) * HS + j + HS / 2);
+        q_s[h * HS + j] = p.batch ? v0 : __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));       // batched prefill: q rows
+        q_s[h * HS + j + HS / 2] = p.batch ? v1 : __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));   // were rotated by rope_rows_kernel
     }
+    if (have_knew)
     for (int j = tid; j < HS / 2; j += NTHR) {
         const float fcr = cs[j], fci = sn[j];
         const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
@@ -124,12 +130,12 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 
     trace_event(201);
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
-    long long a_wait = 0, a_comp = 0;
+    long long a_wait = 0, a_comp = 0, a_iss = 0, a_chain = 0;
     for (int tl = 0; tl < ntiles; tl++) {
         const long long ca = clock64();
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
         float* tb = tile + (tl % ATT_NT) * TILE * HS;
-        if (pos / TILE == tl) {                        // the new K row comes from shared memory, same rotated layout
+        if (have_knew && pos / TILE == tl) {           // the new K row comes from shared memory, same rotated layout
             const int r = pos - tl * TILE;
             for (int d = tid; d < HS; d += NTHR) {
                 const int c = d >> 2;
@@ -140,6 +146,8 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const long long cb = clock64();
         a_wait += cb - ca;
         issue_tile(p.kcache, tl + ATT_NT - 1, true);   // refill the slot tile tl-1 used
+        const long long cc_ = clock64();
+        a_iss += cc_ - cb;
         const int rows = min(TILE, T - tl * TILE);
         // thread = (row r, pair of heads): one LDS.128 of K feeds two independent dot-product chains (ILP 2),
         // products of chunk d4+1 are formed while chunk d4's dependent adds run
@@ -150,23 +158,26 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             const float4* qa = reinterpret_cast<const float4*>(q_s + ha * HS);
             const float4* qb = reinterpret_cast<const float4*>(q_s + hb * HS);
             const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
+            const long long cd = clock64();
             float sa = 0.0f, sb = 0.0f;
-            int c = r % C4;                             // rotated position of chunk 0
-            float4 kv = k4[c], q0 = qa[0], q1 = qb[0];
-            float a0 = __fmul_rn(q0.x, kv.x), a1 = __fmul_rn(q0.y, kv.y), a2 = __fmul_rn(q0.z, kv.z), a3 = __fmul_rn(q0.w, kv.w);
-            float b0 = __fmul_rn(q1.x, kv.x), b1 = __fmul_rn(q1.y, kv.y), b2 = __fmul_rn(q1.z, kv.z), b3 = __fmul_rn(q1.w, kv.w);
-#pragma unroll 4
-            for (int d4 = 1; d4 < C4; d4++) {
-                c = (c + 1 == C4) ? 0 : c + 1;
-                kv = k4[c]; q0 = qa[d4]; q1 = qb[d4];
-                const float n0 = __fmul_rn(q0.x, kv.x), n1 = __fmul_rn(q0.y, kv.y), n2 = __fmul_rn(q0.z, kv.z), n3 = __fmul_rn(q0.w, kv.w);
-                const float m0 = __fmul_rn(q1.x, kv.x), m1 = __fmul_rn(q1.y, kv.y), m2 = __fmul_rn(q1.z, kv.z), m3 = __fmul_rn(q1.w, kv.w);
+            // the whole K row first (C4 independent LDS.128: their latency overlaps), un-rotating on the fly
+            float4 kr[C4];
+            {
+                int c = r % C4;
+#pragma unroll
+                for (int d4 = 0; d4 < C4; d4++) { kr[d4] = k4[c]; c = (c + 1 == C4) ? 0 : c + 1; }
+            }
+            float4 q0 = qa[0], q1 = qb[0];
+#pragma unroll
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 kv = kr[d4];
+                const float a0 = __fmul_rn(q0.x, kv.x), a1 = __fmul_rn(q0.y, kv.y), a2 = __fmul_rn(q0.z, kv.z), a3 = __fmul_rn(q0.w, kv.w);
+                const float b0 = __fmul_rn(q1.x, kv.x), b1 = __fmul_rn(q1.y, kv.y), b2 = __fmul_rn(q1.z, kv.z), b3 = __fmul_rn(q1.w, kv.w);
+                if (d4 + 1 < C4) { q0 = qa[d4 + 1]; q1 = qb[d4 + 1]; }
                 sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
                 sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
-                a0 = n0; a1 = n1; a2 = n2; a3 = n3; b0 = m0; b1 = m1; b2 = m2; b3 = m3;
             }
-            sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
-            sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
+            a_chain += clock64() - cd;
 #pragma unroll
             for (int w = 0; w < 2; w++) {
                 const int h = w ? hb : ha;
@@ -184,6 +195,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         a_comp += clock64() - cb;
     }
     trace_value(310, (unsigned long long)a_wait); trace_value(311, (unsigned long long)a_comp);
+    trace_value(312, (unsigned long long)a_iss); trace_value(313, (unsigned long long)a_chain);
     cp_async_wait<0>();
     __syncthreads();
     trace_event(202);
@@ -302,8 +314,8 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const int idx = tid + k * NTHR;
         if (idx < npair * HS) {
             const int hp = idx / HS, d = idx - hp * HS;
-            p.out[(size_t)(h0 + hp * 2) * HS + d] = acca[k];
-            if (hp * 2 + 1 < nh) p.out[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
+            out_row[(size_t)(h0 + hp * 2) * HS + d] = acca[k];
+            if (hp * 2 + 1 < nh) out_row[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
         }
     }
     __syncthreads();   // the tile ring / score buffers may be reused by the caller

@@ -49,6 +49,7 @@ struct GemvParams {
     int pro;
     const float* x_in; const float* delta; const float* w_post; const float* w_norm; float* x_out;
     int x_in_stride;   // serial prefill: x_in += step->token * x_in_stride (row of the staged embeddings)
+    int xout_all;      // batched prefill (one CTA per row): every CTA writes its x_out
     float eps; int unit_offset;
     // PRO_NORM may take x_in from the embedding table instead (decode step, src/transformer.rs:324-332):
     const uint8_t* emb_q; const float* emb_s; int emb_qtype; float emb_mul; int emb_apply_mul;   // emb_q: BP16 table
@@ -338,7 +339,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 v[k].z = __fadd_rn(v[k].z, dv[k].z); v[k].w = __fadd_rn(v[k].w, dv[k].w);
             }
         }
-        if (p.x_out && blockIdx.x == 0) {  // exactly one CTA publishes the updated residual stream
+        if (p.x_out && (blockIdx.x == 0 || p.xout_all)) {  // decode: exactly one CTA publishes the updated residual stream
             float4* xo = reinterpret_cast<float4*>(p.x_out);
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {

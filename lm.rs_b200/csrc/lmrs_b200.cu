@@ -17,6 +17,7 @@
 
 #include "attention.cuh"
 #include "common.cuh"
+#include "gemm.cuh"
 #include "gemv.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
@@ -44,9 +45,13 @@ static int env_int(const char* name, int dflt) {
 
 // ---- device matrix views ---------------------------------------------------------------------------------
 struct Mat {
-    const uint8_t* q = nullptr;
+    const uint8_t* q = nullptr;     // BP16 block-packed weights (decode GEMV)
     const float* s = nullptr;
     int o = 0, n = 0, gran = 1;
+    const uint8_t* dq = nullptr;    // dense file-layout copy [o][n] int8 + [o][n/128] f32 (prefill GEMM operand; Q8 only)
+    const float* ds = nullptr;
+    CUtensorMap tmap;               // TMA descriptor of dq as a [o][n] byte matrix, 128x128 box, 128B swizzle
+    bool has_tmap = false;
 };
 struct Layer {
     Mat qkv, wo, w1, w3, w2;
@@ -67,6 +72,12 @@ struct lmrs_b200 {
     float *d_kcache = nullptr, *d_vcache = nullptr, *d_rope_cos = nullptr, *d_rope_sin = nullptr;
     float *d_x[2] = {nullptr, nullptr}, *d_q = nullptr, *d_knew = nullptr, *d_att = nullptr, *d_wo_out = nullptr;
     float *d_h = nullptr, *d_down_out = nullptr, *d_logits = nullptr, *d_scores = nullptr, *d_rows = nullptr;
+    uint8_t* d_dense = nullptr;           // file-layout weights kept for the tcgen05 prefill GEMM (Q8 models)
+    // batched prefill activations, capacity pf_cap rows
+    size_t pf_cap = 0;
+    uint8_t* pf_xq = nullptr;
+    float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr;
+    bool use_gemm = true;
     size_t rows_cap = 0;
     StepParams* d_step = nullptr;
     StepParams* h_step_ring = nullptr;  // pinned
@@ -186,6 +197,24 @@ template <int HS> static cudaError_t launch_attn_hs(lmrs_b200* m, const AttnPara
     }
     return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
 }
+template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
+    static thread_local bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
+}
+static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
+    switch (m->args.head_size) {
+        case 64: return launch_attn_grid_hs<64>(m, p, n_kv_heads, rows);
+        case 96: return launch_attn_grid_hs<96>(m, p, n_kv_heads, rows);
+        case 128: return launch_attn_grid_hs<128>(m, p, n_kv_heads, rows);
+        case 256: return launch_attn_grid_hs<256>(m, p, n_kv_heads, rows);
+        default: return cudaErrorInvalidValue;
+    }
+}
 static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
     switch (m->args.head_size) {
         case 64: return launch_attn_hs<64>(m, p, n_kv_heads);
@@ -194,6 +223,54 @@ static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads
         case 256: return launch_attn_hs<256>(m, p, n_kv_heads);
         default: return cudaErrorInvalidValue;
     }
+}
+
+// ---- TMA descriptors (driver entry point resolved at run time: no link-time dependency on libcuda) ---------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+// [rows][row_bytes] byte matrix, box 128 bytes x 128 rows, 128B swizzle (the K-major UMMA operand layout)
+static int make_tmap_2d(CUtensorMap* map, const void* base, size_t row_bytes, size_t rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
+    cuuint32_t box[2] = {128, 128};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return 0;
+}
+static bool gemm_shape_ok(int n, int o) { return n % 128 == 0 && o % 128 == 0; }
+// out[t][i] for t < T: tcgen05 int8 GEMM of xq [T][n] (with xs [T][n/128]) against the dense copy of w
+static int launch_gemm(lmrs_b200* m, const Mat& w, const uint8_t* xq, const float* xs, int T, GemmParams gp) {
+    CUtensorMap ta;
+    if (make_tmap_2d(&ta, xq, (size_t)w.n, (size_t)T)) return 1;
+    static thread_local bool attr = false;
+    if (!attr) { CK(cudaFuncSetAttribute(gemm_q8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM)); attr = true; }
+    gp.T = T; gp.n = w.n; gp.o = w.o; gp.ws = w.ds; gp.xs = xs;
+    dim3 grid(w.o / GEMM_N, (T + GEMM_M - 1) / GEMM_M);
+    gemm_q8_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, m->stream>>>(ta, w.tmap, gp);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static GemmParams gemm_out1(float* out, int ld, int o) {
+    GemmParams g{};
+    g.out0 = out; g.ld0 = ld; g.c1 = o; g.out1 = out; g.ld1 = ld; g.c2 = o; g.out2 = out; g.ld2 = ld;
+    return g;
 }
 
 // ---- RoPE frequency (src/transformer.rs:445-478), evaluated on the host with libm like the reference -------
@@ -392,7 +469,15 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
         CK(repack_bp16(a.q_type, m->d_arena + j.dst, d_stage + j.src.q, (const float*)(d_stage + j.src.s), j.src.o, j.src.n, 0));
     for (const VecJob& j : vjobs) CK(cudaMemcpy(m->d_arena + j.dst, d_stage + j.src, dim * 4, cudaMemcpyDeviceToDevice));
     CK(cudaDeviceSynchronize());
-    cudaFree(d_stage);
+    m->use_gemm = a.q_type == 1 && env_int("LMRS_B200_GEMM", 1) != 0 && W == 1;
+    if (m->use_gemm) m->d_dense = d_stage;   // the file-layout copy doubles as the GEMM's B operand
+    else cudaFree(d_stage);
+    int tmap_err = 0;
+    auto mkd = [&](Mat& x, const MatPlan& pl) {   // dense views + TMA descriptor
+        if (!m->use_gemm) return;
+        x.dq = m->d_dense + pl.q; x.ds = (const float*)(m->d_dense + pl.s);
+        if (gemm_shape_ok(pl.n, pl.o)) { if (make_tmap_2d(&x.tmap, x.dq, (size_t)pl.n, (size_t)pl.o)) tmap_err = 1; else x.has_tmap = true; }
+    };
     auto mk = [&](size_t off, int o, int n) { Mat x; x.q = m->d_arena + off; x.s = nullptr; x.o = o; x.n = n; x.gran = gran_for(n); return x; };
     auto fp = [&](size_t o) { return (const float*)(m->d_arena + o); };
     m->layers.resize(L);
@@ -402,7 +487,9 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
         Y.w1 = mk(lpk[l].w1, lp[l].w1.o, lp[l].w1.n); Y.w3 = mk(lpk[l].w3, lp[l].w3.o, lp[l].w3.n); Y.w2 = mk(lpk[l].w2, lp[l].w2.o, lp[l].w2.n);
         Y.rms_att = fp(lpk[l].rms_att); Y.rms_post_att = fp(lpk[l].rms_post);
         if (a.model_type == 0) { Y.rms_pre_ffn = fp(lpk[l].rms_pre); Y.rms_post_ffn = fp(lpk[l].rms_postffn); }
+        mkd(Y.qkv, lp[l].qkv); mkd(Y.wo, lp[l].wo); mkd(Y.w1, lp[l].w1); mkd(Y.w3, lp[l].w3); mkd(Y.w2, lp[l].w2);
     }
+    if (tmap_err) m->use_gemm = false;
     m->emb = mk(emb_pk, p_emb.o, p_emb.n);
     m->cls = mk(cls_pk, p_cls.o, p_cls.n);
     m->rms_final = fp(rms_final_pk);
@@ -689,15 +776,124 @@ static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_b
     return 0;
 }
 
-// fill_kv_cache, first implementation: the decode-shaped block chain once per token.  For LLAMA/PHI this is
-// mathematically the reference's batched forward_layer (every token attends to positions <= its own, whose
-// K/V are identical in both schedules); the Gemma window quirk is reproduced through mask_base.
-static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
+// fill_kv_cache, serial form: the decode-shaped block chain once per token (Q4 models, shapes the GEMM tiles do not
+// cover, contexts beyond the attention kernel's shared-memory score capacity).  For LLAMA/PHI this is mathematically the
+// reference's batched forward_layer; the Gemma window quirk is reproduced through mask_base.
+static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
     for (size_t i = 0; i < n; i++) {
         if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos, m->seq_prefill++)) return 1;
         if (run_graph(m, &m->g_prefill, &m->g_prefill_stream, &m->n_prefill_kernels, false)) return 1;
     }
     return 0;
+}
+
+static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
+    if (!m->use_gemm || n < 8 || pos + n > (size_t)ATT_SC_CAP) return false;
+    for (const Layer& Y : m->layers)
+        for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
+            if (!x->has_tmap) return false;
+    return m->l_att_dim % 128 == 0 && m->l_kv_dim % 128 == 0;
+}
+
+static int launch_rows_prologue(lmrs_b200* m, GemvParams p, int T) {
+    const int n = p.n, G = n / GS;
+    size_t smem = (size_t)((n + 127) / 128) * 128 + (size_t)((G * 8 + 127) / 128) * 128 + 64 * 4 + (p.pro == PRO_NORM ? (size_t)n * 4 : 0) + 128;
+    static thread_local size_t set_for = 0;
+    if (smem > set_for) { CK(cudaFuncSetAttribute(rows_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_for = smem; }
+    rows_prologue_kernel<<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// fill_kv_cache, batched form (src/transformer.rs:672-684 -> forward_layer(sl = N), :388-657): per block
+//   rows prologue (residual, exact rmsnorm, quantize) -> tcgen05 GEMM [Wq;Wk;Wv] (K/V straight into the cache) -> RoPE rows
+//   -> exact attention per (token, kv head) -> quantize -> GEMM Wo -> rows prologue -> GEMM W1, W3 -> act*up -> quantize
+//   -> GEMM W2; the block-closing residual is folded into the next prologue, the last one is materialised at the end.
+static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
+    const lmrs_args_t& a = m->args;
+    const int T = (int)n, dim = a.dim, att = m->l_att_dim, kvd = m->l_kv_dim, hid = m->l_hidden;
+    const bool gemma = a.model_type == 0;
+    if (m->pf_cap < n) {
+        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
+        const size_t nmax = std::max<size_t>(std::max<size_t>(dim, att), hid);
+        CK(cudaMalloc(&m->pf_xq, n * nmax)); CK(cudaMalloc(&m->pf_xs, n * (nmax / GS) * 4));
+        CK(cudaMalloc(&m->pf_q, n * att * 4)); CK(cudaMalloc(&m->pf_att, n * att * 4)); CK(cudaMalloc(&m->pf_wo, n * dim * 4));
+        CK(cudaMalloc(&m->pf_g, n * hid * 4)); CK(cudaMalloc(&m->pf_u, n * hid * 4)); CK(cudaMalloc(&m->pf_h, n * hid * 4));
+        CK(cudaMalloc(&m->pf_down, n * dim * 4));
+        m->pf_cap = n;
+    }
+    if (push_step(m, 0, pos, pos, 0)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
+    const float* delta = nullptr;
+    const float* w_post = nullptr;
+    for (size_t l = 0; l < a.n_layers; l++) {
+        const Layer& Y = m->layers[l];
+        float* kc = m->d_kcache + l * (size_t)a.seq_len * kvd;
+        float* vc = m->d_vcache + l * (size_t)a.seq_len * kvd;
+        {
+            GemvParams p{};
+            p.n = dim; p.pro = PRO_NORM; p.x_in = m->d_rows; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
+            p.x_out = m->d_rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
+            if (launch_rows_prologue(m, p, T)) return 1;
+            GemmParams g{};
+            g.out0 = m->pf_q; g.ld0 = att; g.c1 = att;
+            g.out1 = kc + (size_t)pos * kvd; g.ld1 = kvd; g.c2 = att + kvd;
+            g.out2 = vc + (size_t)pos * kvd; g.ld2 = kvd;
+            if (launch_gemm(m, Y.qkv, m->pf_xq, m->pf_xs, T, g)) return 1;
+        }
+        rope_rows_kernel<<<T, 256, 0, m->stream>>>(m->pf_q, kc, m->d_rope_cos, m->d_rope_sin, m->l_heads, m->l_kv_heads, a.head_size, (int)pos);
+        m->launches++;
+        CK(cudaGetLastError());
+        {
+            AttnParams p{};
+            p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
+            p.out = m->pf_att; p.scores = m->d_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
+            p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4); p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
+            p.batch = 1; p.q_stride = att;
+            bool pdl = m->use_pdl; m->use_pdl = false;
+            cudaError_t e = launch_attn_grid(m, p, m->l_kv_heads, T);
+            m->use_pdl = pdl;
+            CK(e);
+        }
+        {
+            GemvParams p{};
+            p.n = att; p.pro = PRO_QUANT; p.act_in = m->pf_att; p.step = m->d_step;
+            if (launch_rows_prologue(m, p, T)) return 1;
+            if (launch_gemm(m, Y.wo, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_wo, dim, dim))) return 1;
+        }
+        {
+            GemvParams p{};
+            p.n = dim; p.pro = PRO_NORM; p.x_in = m->d_rows; p.delta = m->pf_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
+            p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
+            if (launch_rows_prologue(m, p, T)) return 1;
+            if (launch_gemm(m, Y.w1, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_g, hid, hid))) return 1;
+            if (launch_gemm(m, Y.w3, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_u, hid, hid))) return 1;
+            const size_t cnt = (size_t)T * hid;
+            glu_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(m->pf_h, m->pf_g, m->pf_u, cnt, gemma ? EPI_GLU_GELU : EPI_GLU_SILU);
+            m->launches++;
+            CK(cudaGetLastError());
+        }
+        {
+            GemvParams p{};
+            p.n = hid; p.pro = PRO_QUANT; p.act_in = m->pf_h; p.step = m->d_step;
+            if (launch_rows_prologue(m, p, T)) return 1;
+            if (launch_gemm(m, Y.w2, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_down, dim, dim))) return 1;
+        }
+        delta = m->pf_down;
+        w_post = gemma ? Y.rms_post_ffn : nullptr;
+    }
+    ResidualParams r{};
+    r.x_in = m->d_rows; r.delta = delta; r.w_post = w_post; r.n = dim; r.eps = a.rms_norm_eps; r.rows = m->d_rows; r.step = m->d_step;
+    r.row_from_block = 1;
+    residual_finalize_kernel<<<T, 256, 0, m->stream>>>(r);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
+    if (gemm_prefill_ok(m, n, pos)) return prefill_gemm(m, n, pos);
+    return prefill_serial(m, n, pos);
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------------
@@ -756,7 +952,8 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     if (m->g_decode) cudaGraphExecDestroy(m->g_decode);
     if (m->g_prefill) cudaGraphExecDestroy(m->g_prefill);
     shard_destroy(m->shard);
-    cudaFree(m->d_arena); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
+    cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
+    cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
     cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
     cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_sd_decode); cudaFree(m->d_sd_prefill); cudaFree(m->d_bar);

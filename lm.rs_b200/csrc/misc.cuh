@@ -15,15 +15,19 @@ struct ResidualParams {
     int n; float eps;
     float* rows;               // [n_rows][n]; row index = step->token
     const StepParams* step;
+    int row_from_block;        // batched prefill: row = blockIdx.x and x_in/delta are row-strided too
 };
 LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
-    float* out = p.rows + (size_t)p.step->token * p.n;
+    const size_t row = p.row_from_block ? (size_t)blockIdx.x : (size_t)p.step->token;
+    float* out = p.rows + row * p.n;
+    const float* x_in = p.x_in + (p.row_from_block ? row * p.n : 0);
+    const float* delta = p.delta + (p.row_from_block ? row * p.n : 0);
     float r = 1.0f;
-    if (p.w_post) r = exact_rnorm(p.delta, p.n, p.eps, red);   // chains read global memory directly
+    if (p.w_post) r = exact_rnorm(delta, p.n, p.eps, red);   // chains read global memory directly
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-        float d = __ldcg(p.delta + i);
+        float d = __ldcg(delta + i);
         if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
-        out[i] = __fadd_rn(__ldcg(p.x_in + i), d);
+        out[i] = __fadd_rn(__ldcg(x_in + i), d);
     }
 }
 __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualParams p) {
@@ -31,6 +35,51 @@ __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualPa
     pdl_launch_dependents();
     pdl_wait();
     residual_finalize_body(p, red);
+}
+
+// ---- batched prefill row kernels (fill_kv_cache, src/transformer.rs:672-684 -> forward_layer with sl = N) ----------
+// one CTA per token row: the GEMV prologue (residual add, exact rmsnorm, activation quantize) with its result written
+// to HBM as the int8 A operand + scales of the tcgen05 GEMM
+__global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_t* xq_out, float* xs_out) {
+    extern __shared__ __align__(128) uint8_t rsm[];
+    const size_t row = blockIdx.x;
+    const int n = p.n, G = n / GS;
+    GemvSmem sm;
+    sm.xq = rsm;
+    sm.xs = reinterpret_cast<float*>(rsm + ((n + 127) / 128) * 128);
+    sm.xsum = reinterpret_cast<int*>(sm.xs + G);
+    sm.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.xs) + ((G * 8 + 127) / 128) * 128);
+    sm.xf = sm.red + 64;
+    if (p.x_in) p.x_in += row * n;
+    if (p.delta) p.delta += row * n;
+    if (p.x_out) p.x_out += row * n;
+    if (p.act_in) p.act_in += row * n;
+    p.xout_all = 1;
+    gemv_prologue<1, 8>(p, sm);
+    for (int i = threadIdx.x; i < n / 16; i += 256) reinterpret_cast<int4*>(xq_out + row * n)[i] = reinterpret_cast<const int4*>(sm.xq)[i];
+    for (int g = threadIdx.x; g < G; g += 256) xs_out[row * G + g] = sm.xs[g];
+}
+// RoPE on the q rows and on the K rows just written into the cache (src/transformer.rs:443-495), exact (host tables)
+__global__ void __launch_bounds__(256) rope_rows_kernel(float* q, float* kcache, const float* rope_cos, const float* rope_sin,
+                                                        int n_heads, int n_kv_heads, int hs, int pos0) {
+    const int row = blockIdx.x, pos = pos0 + row;
+    const int half = hs / 2;
+    const float* cs = rope_cos + (size_t)pos * half;
+    const float* sn = rope_sin + (size_t)pos * half;
+    float* qr = q + (size_t)row * n_heads * hs;
+    float* kr = kcache + (size_t)pos * n_kv_heads * hs;
+    for (int i = threadIdx.x; i < (n_heads + n_kv_heads) * half; i += 256) {
+        const int h = i / half, j = i - h * half;
+        float* v = h < n_heads ? qr + (size_t)h * hs : kr + (size_t)(h - n_heads) * hs;
+        const float fcr = cs[j], fci = sn[j], v0 = v[j], v1 = v[j + half];
+        v[j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        v[j + half] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+    }
+}
+// h = act(gate) * up (src/transformer.rs:607-624)
+__global__ void glu_rows_kernel(float* h, const float* gate, const float* up, size_t count, int epi) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) h[i] = __fmul_rn(glu_act(epi, gate[i]), up[i]);
 }
 
 // ---- operator-level kernels (any group size; one thread walks one group serially like the reference) -------

@@ -32,6 +32,19 @@ def test_matmul_q8_bit_exact(gpu_lib, ref, n, o, rows):
     assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
 
 
+@pytest.mark.parametrize("n,o,rows", [(128, 128, 8), (256, 128, 130), (2048, 2048, 128), (2048, 3072, 512), (8192, 2048, 200),
+                                      (3584, 256, 64), (384, 1152, 17)])
+def test_matmul_q8_batched_tcgen05_gemm_bit_exact(gpu_lib, ref, n, o, rows):
+    """rows >= 8 and 128-aligned shapes run the tcgen05/TMEM int8 GEMM (the fill_kv_cache kernel): same bits as the CPU path."""
+    rng = np.random.default_rng(n * 13 + o + rows)
+    xq, xs = _rand_q8(rng, rows, n, 0.01)
+    wq, ws = _rand_q8(rng, o, n, 0.002)
+    exp = ref.matmul_q8(xq, xs, wq, ws, rows, n, o, 128)
+    got = np.full(rows * o, np.nan, np.float32)
+    gpu_lib.functional.matmul_q8(got, QT(xq, xs), QT(wq, ws), n, o, 128)
+    assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}, mismatches {(got != exp).sum()}"
+
+
 @pytest.mark.parametrize("n,o,rows", [(128, 4, 1), (256, 8, 1), (3072, 3072, 1), (8192, 3072, 1), (3072, 1024, 2),
                                       (2304, 64, 1), (2048, 2048, 1)])
 def test_matmul_q4_bit_exact(gpu_lib, ref, n, o, rows):
