@@ -177,7 +177,10 @@ def main():
         torch.cuda.synchronize()
 
     # ---- prefill: fill_kv_cache(P embeddings), end to end through the C ABI ------------------------------------
-    emb = m.get_embeddings(prompt[:args.pos])
+    emb0 = m.get_embeddings(prompt[:args.pos])
+    emb = emb0.copy()
+    m.fill_kv_cache(emb, 0)            # warm-up: first call allocates the batch buffers and loads the kernels
+    emb = emb0.copy()                  # (idempotent: the same rows are written to the same cache positions)
     barrier()
     t0 = time.perf_counter()
     newpos = m.fill_kv_cache(emb, 0)
@@ -245,7 +248,12 @@ def main():
                 "ms_per_step": e2e_s / args.steps * 1e3},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
         "prefill": {"value": args.pos / t_prefill, "unit": "tok/s", "tokens": args.pos, "ms": t_prefill * 1e3,
-                    "h2d_bytes": int(emb.nbytes), "d2h_bytes": int(emb.nbytes)},
+                    "h2d_bytes": int(emb.nbytes), "d2h_bytes": int(emb.nbytes),
+                    "path": "fill_kv_cache end to end through the C ABI (host embeddings in, residual stream out)",
+                    "roofline": {"bound": "tensor", "unit": "TOP/s", "achieved": lf.prefill_int8_ops(a, args.pos) / t_prefill / 1e12,
+                                 "peak": 4500.0, "peak_source": "nominal dense int8 (B200_PROFILING.md); MEASURED_PEAKS.json has no int8 figure",
+                                 "frac": lf.prefill_int8_ops(a, args.pos) / t_prefill / 1e12 / 4500.0,
+                                 "note": "whole fill_kv_cache time (GEMMs + exact-order attention + row kernels + PCIe copies) over the matmul ops only"}},
         "published_reference": {"value": 50, "unit": "tok/s", "hardware": "16-core AMD Epyc (README.md:38)"} if args.model == "llama-3.2-1b" and args.quant == 1 else None,
     }))
     if dist is not None:

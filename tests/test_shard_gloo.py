@@ -1,0 +1,118 @@
+"""N > 1 path on CPU: the row-sharding scheme of lmrs_b200_create_sharded (SURVEY.md section 8e / DESIGN.md section 6) restated with the
+oracle's operators, run as 2 `gloo` ranks: head-aligned row shards of Wq/Wk/Wv/W1/W3, 128-aligned input-column shards
+of Wo/W2, one sum-all-reduce of the dim-vector after Wo and after W2, vocab-row shards of the classifier + all-gather.
+Checks (a) the exchange plumbing bench.py uses (unique-id style byte broadcast, all_reduce, all_gather) and (b) that the
+scheme reproduces the unsharded logits up to f32 re-association of the partial sums."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, out_dir):
+    for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    import torch
+    import torch.distributed as dist
+    import lmrs_ref as R
+    from lmrs_b200 import lmrs_file as lf
+    os.environ["OMP_NUM_THREADS"] = "2"
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    # the id broadcast bench.py performs before create_sharded
+    idt = torch.zeros(128, dtype=torch.uint8)
+    if rank == 0:
+        idt = torch.arange(128, dtype=torch.uint8)
+    dist.broadcast(idt, 0)
+    assert idt.tolist() == list(range(128))
+
+    a = lf.model_args("tiny-llama", 1)
+    buf = lf.write_synthetic(a)
+    offs, _ = lf.tensor_offsets(a)
+    dim, hs, hd = a.dim, a.head_size, a.hidden_dim
+    lh, lkv = a.n_heads // world, a.n_kv_heads // world
+    la, lk, lhid, lv = lh * hs, lkv * hs, hd // world, a.vocab_size // world
+
+    def rows(nm, l, n, r0, nr):     # output-row shard
+        qo, so = offs[nm][l]
+        return buf[qo + r0 * n: qo + (r0 + nr) * n].view(np.int8), buf[so + r0 * (n // 128) * 4: so + (r0 + nr) * (n // 128) * 4].view(np.float32)
+
+    def cols(nm, l, n, o, c0, nc):  # input-column (K) shard, 128-aligned
+        qo, so = offs[nm][l]
+        q = buf[qo: qo + o * n].view(np.int8).reshape(o, n)[:, c0:c0 + nc]
+        s = buf[so: so + o * (n // 128) * 4].view(np.float32).reshape(o, n // 128)[:, c0 // 128:(c0 + nc) // 128]
+        return np.ascontiguousarray(q).reshape(-1), np.ascontiguousarray(s).reshape(-1)
+
+    def fv(nm, l):
+        o = offs[nm][l]; return buf[o:o + dim * 4].view(np.float32)
+
+    def qmm(x, wq, ws, n, o):
+        xq, xs = R.quantize_q8(np.ascontiguousarray(x, np.float32), 128)
+        return R.matmul_q8(xq, xs, wq, ws, 1, n, o, 128)
+
+    def allreduce(v):
+        t = torch.from_numpy(v.copy()); dist.all_reduce(t); return t.numpy()
+
+    K = np.zeros((a.n_layers, 64, lk), np.float32); V = np.zeros_like(K)
+    full = R.RefTransformer(buf) if rank == 0 else None
+    toks = [3, 77, 401, 9, 250]
+    worst = 0.0
+    for pos, tok in enumerate(toks):
+        x = R.RefTransformer(buf).get_embeddings([tok]) if False else None
+        eq, es = buf[offs["emb"][0][0] + tok * dim: offs["emb"][0][0] + (tok + 1) * dim], \
+            buf[offs["emb"][0][1] + tok * (dim // 128) * 4: offs["emb"][0][1] + (tok + 1) * (dim // 128) * 4].view(np.float32)
+        x = R.dequantize(eq.view(np.int8), es, dim, 128, 1)
+        fr = np.array([R.rope_freq(1, a.rope_theta, hs, j) for j in range(hs // 2)], np.float32)
+        ang = (np.float32(pos) * fr[:, 0]).astype(np.float32)
+        c, s_ = np.cos(ang), np.sin(ang)
+        for l in range(a.n_layers):
+            hn = R.rmsnorm(x, fv("rms_att", l), a.rms_norm_eps, False)
+            q = qmm(hn, *rows("wq", l, dim, rank * la, la), dim, la)
+            k = qmm(hn, *rows("wk", l, dim, rank * lk, lk), dim, lk)
+            v = qmm(hn, *rows("wv", l, dim, rank * lk, lk), dim, lk)
+            def rope(vec, nh):
+                vec = vec.reshape(nh, hs).copy(); v0, v1 = vec[:, :hs // 2].copy(), vec[:, hs // 2:].copy()
+                vec[:, :hs // 2] = v0 * c - v1 * s_; vec[:, hs // 2:] = v0 * s_ + v1 * c
+                return vec.reshape(-1)
+            q, k = rope(q, lh), rope(k, lkv)
+            K[l, pos], V[l, pos] = k, v
+            att = np.zeros(la, np.float32)
+            kvm = lh // lkv
+            for h in range(lh):
+                kk = K[l, :pos + 1, (h // kvm) * hs:(h // kvm + 1) * hs]
+                sc = np.array([np.float32(np.dot(q[h * hs:(h + 1) * hs], kk[t])) / np.sqrt(np.float32(hs)) for t in range(pos + 1)], np.float32)
+                p = R.softmax(sc)
+                att[h * hs:(h + 1) * hs] = (p[:, None] * V[l, :pos + 1, (h // kvm) * hs:(h // kvm + 1) * hs]).sum(0)
+            wo = allreduce(qmm(att, *cols("wo", l, a.att_dim, dim, rank * la, la), la, dim))      # all-reduce #1
+            x = x + wo
+            hin = R.rmsnorm(x, fv("rms_post_att", l), a.rms_norm_eps, False)
+            g = qmm(hin, *rows("w1", l, dim, rank * lhid, lhid), dim, lhid)
+            u = qmm(hin, *rows("w3", l, dim, rank * lhid, lhid), dim, lhid)
+            hh = (g * (np.float32(1) / (np.float32(1) + np.exp(-g))) * u).astype(np.float32)
+            x = x + allreduce(qmm(hh, *cols("w2", l, hd, dim, rank * lhid, lhid), lhid, dim))      # all-reduce #2
+        y = R.rmsnorm(x, fv("rms_final", 0), a.rms_norm_eps, False)
+        part = qmm(y, *rows("emb", 0, dim, rank * lv, lv), dim, lv)
+        gathered = [torch.zeros(lv) for _ in range(world)]
+        dist.all_gather(gathered, torch.from_numpy(part.copy()))
+        logits = torch.cat(gathered).numpy()
+        if rank == 0:
+            worst = max(worst, float(np.abs(logits - full.forward(tok, pos)).max()))
+    if rank == 0:
+        open(os.path.join(out_dir, "worst.txt"), "w").write(repr(worst))
+    dist.destroy_process_group()
+
+
+def test_two_rank_row_sharding_matches_unsharded_logits(tmp_path):
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    worst = float(open(tmp_path / "worst.txt").read())
+    assert worst <= 1e-3, worst      # partial sums re-associate the f32 group accumulation: tolerance, not bit-equality
