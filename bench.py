@@ -226,13 +226,18 @@ def main():
     e2e = args.steps / e2e_s
 
     if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            m.close()
+            dist.destroy_process_group()
         return
     peak, peak_src = load_peaks()
+    peak *= args.gpus
     mid_pos = args.pos + args.warmup + args.steps // 2
     alg_bytes = lf.decode_bytes_per_token(a, mid_pos)
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "decode step (all kernels of one forward; weight-streaming GEMV dominates)",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src + (f" x {args.gpus} GPUs" if args.gpus > 1 else ""),
                 "algorithmic_bytes_per_step": alg_bytes, "traffic": None, "launches_per_step": launches / args.steps}
     cpu = None
     if args.gpus == 1 and args.cpu_steps > 0:
@@ -257,6 +262,8 @@ def main():
         "published_reference": {"value": 50, "unit": "tok/s", "hardware": "16-core AMD Epyc (README.md:38)"} if args.model == "llama-3.2-1b" and args.quant == 1 else None,
     }))
     if dist is not None:
+        dist.barrier()
+        m.close()
         dist.destroy_process_group()
 
 
