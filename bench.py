@@ -188,7 +188,8 @@ def main():
     assert newpos == args.pos
 
     # ---- decode, HBM-resident leg ("value") --------------------------------------------------------------------
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()       # a real (non-default) stream: the library launches on it, the events time it
+    assert stream.cuda_stream != 0
     m.set_stream(stream.cuda_stream)
     toks = np.random.default_rng(2).integers(0, a.vocab_size, args.warmup + args.steps)
     pos = args.pos
