@@ -359,3 +359,208 @@ __global__ void embed_kernel(const EmbedParams p) {
 }
 
 }  // namespace lmrs
+
+// =====================================================================================================================
+// Two-kernel form of the same exact attention (used by the kernel-per-phase decode chain and by batched prefill).
+//
+// The per-position dot products are independent, so `attn_scores_kernel` spreads them over the whole GPU (grid =
+// kv heads x position splits [x token rows]): thread = cached position, four query heads per thread (ILP 4), the K row
+// read straight from L2 into registers -- no tile staging, no block barriers in the loop.  The two serial chains of the
+// reference (softmax sum over t, a*v accumulation over t) then run in `attn_softmax_av_kernel`, one CTA per kv head,
+// thread = (head, dim), V read through L1 (the four heads of a GQA group share every V row) with an 8-deep register
+// prefetch.  Arithmetic and operation order are identical to attn_decode_body: bit-identical results.
+// =====================================================================================================================
+namespace lmrs {
+
+constexpr int ATTS_THREADS = 64;    // scores kernel: positions per CTA pass
+constexpr int ATTV_THREADS = 256;   // softmax/AV kernel
+
+template <int HS>
+__global__ void __launch_bounds__(ATTS_THREADS) attn_scores_kernel(const AttnParams p, const int nsplit) {
+    constexpr int C4 = HS / 4;
+    __shared__ __align__(16) float q_s[ATT_QH][HS];
+    __shared__ __align__(16) float k_s[HS];
+    const int tid = threadIdx.x;
+    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks, split = blockIdx.y;
+    const int brow = p.batch ? (int)blockIdx.z : 0;
+    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;
+    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pos = (int)p.step->pos + brow;
+    const uint32_t mask_base = p.step->mask_base;
+    const int T = pos + 1;
+    const int per = (T + nsplit - 1) / nsplit;
+    const int t0 = split * per, t1 = min(T, t0 + per);
+    const bool have_knew = p.k_new != nullptr;
+    const bool owns_pos = have_knew && pos >= t0 && pos < t1;
+    if (t0 >= t1) return;
+    const float* q_in = p.q + (size_t)brow * p.q_stride;
+    const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
+    const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
+    for (int i = tid; i < ATT_QH * (HS / 2); i += ATTS_THREADS) {
+        const int h = i / (HS / 2), j = i - h * (HS / 2);
+        float r0 = 0.0f, r1 = 0.0f;
+        if (h < nh) {
+            const float v0 = __ldcg(q_in + (size_t)(h0 + h) * HS + j), v1 = __ldcg(q_in + (size_t)(h0 + h) * HS + j + HS / 2);
+            if (p.batch) { r0 = v0; r1 = v1; }   // rotated by rope_rows_kernel already
+            else { const float fcr = cs[j], fci = sn[j]; r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci)); r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr)); }
+        }
+        q_s[h][j] = r0; q_s[h][j + HS / 2] = r1;
+    }
+    if (owns_pos) {
+        for (int j = tid; j < HS / 2; j += ATTS_THREADS) {
+            const float fcr = cs[j], fci = sn[j];
+            const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
+            const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+            const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+            k_s[j] = r0; k_s[j + HS / 2] = r1;
+            if (chunk == 0) {   // exactly one CTA per KV head publishes the rotated row into the cache
+                p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = r0;
+                p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j + HS / 2] = r1;
+            }
+        }
+    }
+    __syncthreads();
+    float* sc_out = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;   // [row][head][stride]
+    for (int t = t0 + tid; t < t1; t += ATTS_THREADS) {
+        float4 kr[C4];
+        if (have_knew && t == pos) {
+#pragma unroll
+            for (int c = 0; c < C4; c++) kr[c] = reinterpret_cast<const float4*>(k_s)[c];
+        } else {
+            const float4* krow = reinterpret_cast<const float4*>(p.kcache + (size_t)t * p.kv_dim + (size_t)kvh * HS);
+#pragma unroll
+            for (int c = 0; c < C4; c++) kr[c] = __ldcg(krow + c);
+        }
+        float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C4; c++) {   // four independent dot-product chains, ascending d
+            const float4 kv = kr[c];
+            const float4 a = reinterpret_cast<const float4*>(q_s[0])[c], b = reinterpret_cast<const float4*>(q_s[1])[c];
+            const float4 e = reinterpret_cast<const float4*>(q_s[2])[c], f = reinterpret_cast<const float4*>(q_s[3])[c];
+            s0 = __fadd_rn(s0, __fmul_rn(a.x, kv.x)); s1 = __fadd_rn(s1, __fmul_rn(b.x, kv.x)); s2 = __fadd_rn(s2, __fmul_rn(e.x, kv.x)); s3 = __fadd_rn(s3, __fmul_rn(f.x, kv.x));
+            s0 = __fadd_rn(s0, __fmul_rn(a.y, kv.y)); s1 = __fadd_rn(s1, __fmul_rn(b.y, kv.y)); s2 = __fadd_rn(s2, __fmul_rn(e.y, kv.y)); s3 = __fadd_rn(s3, __fmul_rn(f.y, kv.y));
+            s0 = __fadd_rn(s0, __fmul_rn(a.z, kv.z)); s1 = __fadd_rn(s1, __fmul_rn(b.z, kv.z)); s2 = __fadd_rn(s2, __fmul_rn(e.z, kv.z)); s3 = __fadd_rn(s3, __fmul_rn(f.z, kv.z));
+            s0 = __fadd_rn(s0, __fmul_rn(a.w, kv.w)); s1 = __fadd_rn(s1, __fmul_rn(b.w, kv.w)); s2 = __fadd_rn(s2, __fmul_rn(e.w, kv.w)); s3 = __fadd_rn(s3, __fmul_rn(f.w, kv.w));
+        }
+        const float sv[4] = {s0, s1, s2, s3};
+#pragma unroll
+        for (int h = 0; h < ATT_QH; h++) {
+            if (h < nh) {
+                float score = __fdiv_rn(sv[h], p.sqrt_hs);
+                if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
+                    score = __fdiv_rn(score, 50.0f);
+                    score = (float)tanh((double)score);
+                    score = __fmul_rn(score, 50.0f);
+                    score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
+                }
+                sc_out[(size_t)h * p.seq_len + t] = score;
+            }
+        }
+    }
+}
+
+template <int HS>
+__global__ void __launch_bounds__(ATTV_THREADS) attn_softmax_av_kernel(const AttnParams p) {
+    extern __shared__ __align__(16) float av_smem[];      // [ATT_QH][cap] probabilities
+    __shared__ float red[ATT_QH * (ATTV_THREADS / 32) + ATT_QH];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NW = ATTV_THREADS / 32;
+    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
+    const int brow = p.batch ? (int)blockIdx.y : 0;
+    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;
+    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int pos = (int)p.step->pos + brow;
+    const int T = pos + 1;
+    const int cap = p.q_stride ? ATT_SC_CAP : ATT_SC_CAP;
+    const bool in_smem = T <= cap;
+    float* sc_g = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
+    float* sc_base = in_smem ? av_smem : sc_g;
+    const int sc_stride = in_smem ? cap : p.seq_len;
+    float* out_row = p.out + (size_t)brow * p.q_stride;
+
+    // scores -> shared memory, per-head max on the way (src/functional.rs:123-130)
+    for (int h = 0; h < nh; h++) {
+        float mx = -INFINITY;
+        for (int t = tid; t < T; t += ATTV_THREADS) {
+            const float v = __ldcg(sc_g + (size_t)h * p.seq_len + t);
+            if (in_smem) av_smem[h * cap + t] = v;
+            mx = fmaxf(mx, v);
+        }
+        mx = warp_max(mx);
+        if (lane == 0) red[h * NW + warp] = mx;
+    }
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+        float* sc = sc_base + (size_t)h * sc_stride;
+        float mx = red[h * NW];
+#pragma unroll
+        for (int w = 1; w < NW; w++) mx = fmaxf(mx, red[h * NW + w]);
+        for (int t = tid; t < T; t += ATTV_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
+    }
+    __syncthreads();
+    if (lane == 0 && warp < nh) {   // the reference's `sum += x[i]` chain: one thread per head, in different warps
+        const float* sc = sc_base + (size_t)warp * sc_stride;
+        float sum = 0.0f;
+        int t = 0;
+        if (T >= 24) {
+            float4 a = *reinterpret_cast<const float4*>(sc), b = *reinterpret_cast<const float4*>(sc + 4);
+            float4 c = *reinterpret_cast<const float4*>(sc + 8), d = *reinterpret_cast<const float4*>(sc + 12);
+            for (; t + 24 <= T; t += 8) {
+                const float4 e = *reinterpret_cast<const float4*>(sc + t + 16), f = *reinterpret_cast<const float4*>(sc + t + 20);
+                sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
+                sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
+                a = c; b = d; c = e; d = f;
+            }
+            sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
+            sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
+            sum = __fadd_rn(sum, c.x); sum = __fadd_rn(sum, c.y); sum = __fadd_rn(sum, c.z); sum = __fadd_rn(sum, c.w);
+            sum = __fadd_rn(sum, d.x); sum = __fadd_rn(sum, d.y); sum = __fadd_rn(sum, d.z); sum = __fadd_rn(sum, d.w);
+            t += 16;
+        }
+        for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
+        red[ATT_QH * NW + warp] = sum;
+    }
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+        float* sc = sc_base + (size_t)h * sc_stride;
+        const float sum = red[ATT_QH * NW + h];
+        for (int t = tid; t < T; t += ATTV_THREADS) sc[t] = __fdiv_rn(sc[t], sum);
+    }
+    __syncthreads();
+    // out[h][d] = sum_t a[h][t] * v[t][d]: thread = (h, d); V through L1, eight rows prefetched ahead of the chain
+    for (int idx = tid; idx < nh * HS; idx += ATTV_THREADS) {
+        const int h = idx / HS, d = idx - h * HS;
+        const float* a = sc_base + (size_t)h * sc_stride;
+        const float* vcol = p.vcache + (size_t)kvh * HS + d;
+        float x = 0.0f;
+        int t = 0;
+        if (T >= 16) {
+            float v[8], nv[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[u] = vcol[(size_t)u * p.kv_dim];
+            for (; t + 16 <= T; t += 8) {
+#pragma unroll
+                for (int u = 0; u < 8; u++) nv[u] = vcol[(size_t)(t + 8 + u) * p.kv_dim];
+                const float4 a4 = *reinterpret_cast<const float4*>(a + t), b4 = *reinterpret_cast<const float4*>(a + t + 4);
+                const float p0 = __fmul_rn(a4.x, v[0]), p1 = __fmul_rn(a4.y, v[1]), p2 = __fmul_rn(a4.z, v[2]), p3 = __fmul_rn(a4.w, v[3]);
+                const float p4 = __fmul_rn(b4.x, v[4]), p5 = __fmul_rn(b4.y, v[5]), p6 = __fmul_rn(b4.z, v[6]), p7 = __fmul_rn(b4.w, v[7]);
+                x = __fadd_rn(x, p0); x = __fadd_rn(x, p1); x = __fadd_rn(x, p2); x = __fadd_rn(x, p3);
+                x = __fadd_rn(x, p4); x = __fadd_rn(x, p5); x = __fadd_rn(x, p6); x = __fadd_rn(x, p7);
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[u] = nv[u];
+            }
+            const float4 a4 = *reinterpret_cast<const float4*>(a + t), b4 = *reinterpret_cast<const float4*>(a + t + 4);
+            x = __fadd_rn(x, __fmul_rn(a4.x, v[0])); x = __fadd_rn(x, __fmul_rn(a4.y, v[1])); x = __fadd_rn(x, __fmul_rn(a4.z, v[2])); x = __fadd_rn(x, __fmul_rn(a4.w, v[3]));
+            x = __fadd_rn(x, __fmul_rn(b4.x, v[4])); x = __fadd_rn(x, __fmul_rn(b4.y, v[5])); x = __fadd_rn(x, __fmul_rn(b4.z, v[6])); x = __fadd_rn(x, __fmul_rn(b4.w, v[7]));
+            t += 8;
+        }
+        for (; t < T; t++) x = __fadd_rn(x, __fmul_rn(a[t], vcol[(size_t)t * p.kv_dim]));
+        out_row[(size_t)(h0 + h) * HS + d] = x;
+    }
+}
+
+}  // namespace lmrs

@@ -76,7 +76,7 @@ struct lmrs_b200 {
     // batched prefill activations, capacity pf_cap rows
     size_t pf_cap = 0;
     uint8_t* pf_xq = nullptr;
-    float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr;
+    float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr, *pf_scores = nullptr;
     bool use_gemm = true;
     size_t rows_cap = 0;
     StepParams* d_step = nullptr;
@@ -188,23 +188,20 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
     return p;
 }
 
-template <int HS> static cudaError_t launch_attn_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
-    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
-}
 template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
     static thread_local bool attr_set = false;
+    const size_t smem = (size_t)ATT_QH * ATT_SC_CAP * 4;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
+        cudaError_t e = cudaFuncSetAttribute(attn_softmax_av_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
+    // position splits so that the independent dot products cover the whole GPU (decode); batched prefill has rows for that
+    int nsplit = 1;
+    if (rows == 1) { nsplit = m->sms / (n_kv_heads * p.chunks); if (nsplit < 1) nsplit = 1; if (nsplit > 32) nsplit = 32; }
+    cudaError_t e = launch(m, attn_scores_kernel<HS>, dim3(n_kv_heads * p.chunks, nsplit, rows), dim3(ATTS_THREADS), 0, p, nsplit);
+    if (e != cudaSuccess) return e;
+    return launch(m, attn_softmax_av_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATTV_THREADS), smem, p);
 }
 static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
     switch (m->args.head_size) {
@@ -215,15 +212,7 @@ static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_
         default: return cudaErrorInvalidValue;
     }
 }
-static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) {
-    switch (m->args.head_size) {
-        case 64: return launch_attn_hs<64>(m, p, n_kv_heads);
-        case 96: return launch_attn_hs<96>(m, p, n_kv_heads);
-        case 128: return launch_attn_hs<128>(m, p, n_kv_heads);
-        case 256: return launch_attn_hs<256>(m, p, n_kv_heads);
-        default: return cudaErrorInvalidValue;
-    }
-}
+static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) { return launch_attn_grid(m, p, n_kv_heads, 1); }
 
 // ---- TMA descriptors (driver entry point resolved at run time: no link-time dependency on libcuda) ---------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -821,6 +810,8 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
         CK(cudaMalloc(&m->pf_q, n * att * 4)); CK(cudaMalloc(&m->pf_att, n * att * 4)); CK(cudaMalloc(&m->pf_wo, n * dim * 4));
         CK(cudaMalloc(&m->pf_g, n * hid * 4)); CK(cudaMalloc(&m->pf_u, n * hid * 4)); CK(cudaMalloc(&m->pf_h, n * hid * 4));
         CK(cudaMalloc(&m->pf_down, n * dim * 4));
+        cudaFree(m->pf_scores); m->pf_scores = nullptr;
+        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * align_up(a.seq_len, 4) * 4));
         m->pf_cap = n;
     }
     if (push_step(m, 0, pos, pos, 0)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
@@ -847,7 +838,7 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
         {
             AttnParams p{};
             p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
-            p.out = m->pf_att; p.scores = m->d_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
+            p.out = m->pf_att; p.scores = m->pf_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
             p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4); p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
             p.batch = 1; p.q_stride = att;
             bool pdl = m->use_pdl; m->use_pdl = false;
@@ -953,7 +944,7 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     if (m->g_prefill) cudaGraphExecDestroy(m->g_prefill);
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
-    cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
+    cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->pf_scores); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
     cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
     cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_sd_decode); cudaFree(m->d_sd_prefill); cudaFree(m->d_bar);
