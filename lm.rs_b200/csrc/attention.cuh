@@ -29,6 +29,7 @@ struct AttnParams {
     float* scores;         // scratch [n_heads][seq_len] used when pos+1 > ATT_SC_CAP
     int kv_dim, kv_mul, chunks, gemma, seq_len;
     int batch, q_stride;   // batched prefill: grid.y = token index; pos = step->pos + blockIdx.y, q/out rows strided
+    int scores_ready;      // scores already computed by attn_scores_kernel (global scratch [row][head][seq_len])
     float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
     const StepParams* step;
 };
@@ -75,7 +76,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     const bool have_knew = p.k_new != nullptr;   // decode: K row of this step arrives un-rotated in a staging row
     const int T = pos + 1;
     const bool in_smem = T <= ATT_SC_CAP;
-    float* sc_base = in_smem ? sc_s : p.scores + (size_t)h0 * p.seq_len;
+    float* sc_base = in_smem ? sc_s : p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
     const int sc_stride = in_smem ? ATT_SC_CAP : p.seq_len;
     const int ntiles = (T + TILE - 1) / TILE;
 
@@ -101,8 +102,10 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     };
     trace_event(200);
     // K tiles start flowing before anything else (rows < pos are in the cache since earlier steps)
+    if (!p.scores_ready) {
 #pragma unroll
-    for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.kcache, k, true);
+        for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.kcache, k, true);
+    }
 
     // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
@@ -114,7 +117,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         q_s[h * HS + j] = p.batch ? v0 : __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));       // batched prefill: q rows
         q_s[h * HS + j + HS / 2] = p.batch ? v1 : __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));   // were rotated by rope_rows_kernel
     }
-    if (have_knew)
+    if (have_knew && !p.scores_ready)
     for (int j = tid; j < HS / 2; j += NTHR) {
         const float fcr = cs[j], fci = sn[j];
         const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
@@ -131,7 +134,14 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     trace_event(201);
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
     long long a_wait = 0, a_comp = 0, a_iss = 0, a_chain = 0;
-    for (int tl = 0; tl < ntiles; tl++) {
+    if (p.scores_ready) {   // dot products were spread over the whole GPU by attn_scores_kernel
+        const float* sg = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
+        if (in_smem)
+            for (int h = 0; h < nh; h++)
+                for (int t = tid; t < T; t += NTHR) sc_s[h * ATT_SC_CAP + t] = __ldcg(sg + (size_t)h * p.seq_len + t);
+        else sc_base = const_cast<float*>(sg);
+    }
+    for (int tl = 0; tl < (p.scores_ready ? 0 : ntiles); tl++) {
         const long long ca = clock64();
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
         float* tb = tile + (tl % ATT_NT) * TILE * HS;

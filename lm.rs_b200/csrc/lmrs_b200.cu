@@ -188,20 +188,24 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
     return p;
 }
 
-template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
+template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p0, int n_kv_heads, int rows) {
     static thread_local bool attr_set = false;
-    const size_t smem = (size_t)ATT_QH * ATT_SC_CAP * 4;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_softmax_av_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    // position splits so that the independent dot products cover the whole GPU (decode); batched prefill has rows for that
-    int nsplit = 1;
-    if (rows == 1) { nsplit = m->sms / (n_kv_heads * p.chunks); if (nsplit < 1) nsplit = 1; if (nsplit > 32) nsplit = 32; }
-    cudaError_t e = launch(m, attn_scores_kernel<HS>, dim3(n_kv_heads * p.chunks, nsplit, rows), dim3(ATTS_THREADS), 0, p, nsplit);
-    if (e != cudaSuccess) return e;
-    return launch(m, attn_softmax_av_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATTV_THREADS), smem, p);
+    AttnParams p = p0;
+    const bool split_scores = env_int("LMRS_B200_ATT_SPLIT", 1) != 0;
+    if (split_scores) {
+        // the independent q.k dot products cover the whole GPU (decode: position splits; prefill: token rows) ...
+        int nsplit = 1;
+        if (rows == 1) { nsplit = m->sms / (n_kv_heads * p.chunks); if (nsplit < 1) nsplit = 1; if (nsplit > 32) nsplit = 32; }
+        cudaError_t e = launch(m, attn_scores_kernel<HS>, dim3(n_kv_heads * p.chunks, nsplit, rows), dim3(ATTS_THREADS), 0, p, nsplit);
+        if (e != cudaSuccess) return e;
+        p.scores_ready = 1;   // ... and the serial softmax / a*v chains run per kv head
+    }
+    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
 }
 static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
     switch (m->args.head_size) {
