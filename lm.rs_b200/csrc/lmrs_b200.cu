@@ -196,7 +196,7 @@ template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const Att
         attr_set = true;
     }
     AttnParams p = p0;
-    const bool split_scores = env_int("LMRS_B200_ATT_SPLIT", 1) != 0;
+    const bool split_scores = env_int("LMRS_B200_ATT_SPLIT", rows > 1 ? 1 : 0) != 0;   // decode: measured no gain (extra launch)
     if (split_scores) {
         // the independent q.k dot products cover the whole GPU (decode: position splits; prefill: token rows) ...
         int nsplit = 1;
@@ -920,7 +920,9 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
-    m->use_mega = env_int("LMRS_B200_MEGA", 1) != 0;
+    // default: one kernel per phase chained with programmatic dependent launch (measured faster than the persistent
+    // megakernel, whose 80 grid barriers cost ~1.3-2 us each); LMRS_B200_MEGA=1 selects the megakernel
+    m->use_mega = env_int("LMRS_B200_MEGA", 0) != 0;
     if (setup_mega(m) || upload_phases(m, true)) { lmrs_b200_destroy(m); return 1; }
     *out = m;
     return 0;
