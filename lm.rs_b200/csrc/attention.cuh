@@ -16,7 +16,10 @@ namespace lmrs {
 constexpr int ATT_THREADS = 256;   // stand-alone kernel; the megakernel runs the same body with its own block size
 constexpr int ATT_QH = 4;        // query heads per CTA (all sharing one KV head)
 constexpr int ATT_SC_CAP = 1024; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
-constexpr int ATT_NT = 4;        // K/V tiles in flight (cp.async ring)
+// K/V tile ring geometry.  BIG (decode, one CTA per kv head): 128-row tiles x 3 in flight -- per-tile fixed costs
+// (barrier, cp.async issue, fix-ups) are a large part of the phase, measured 5.5% of the whole decode step;
+// small (batched prefill, thousands of CTAs): 64-row tiles x 4, half the shared memory so two CTAs fit per SM.
+template <bool BIG> __host__ __device__ constexpr int att_nt() { return BIG ? 3 : 4; }
 
 struct AttnParams {
     const float* q;        // [att_dim] un-rotated
@@ -34,9 +37,9 @@ struct AttnParams {
     const StepParams* step;
 };
 
-template <int HS> __host__ __device__ constexpr int att_tile_rows() { return HS <= 64 ? 64 : (HS <= 128 ? 32 : 16); }
-template <int HS> __host__ __device__ constexpr size_t attn_smem_bytes() {
-    return (size_t)(ATT_QH * HS + HS + ATT_NT * att_tile_rows<HS>() * HS + ATT_QH * ATT_SC_CAP + 128) * 4;
+template <int HS, bool BIG = false> __host__ __device__ constexpr int att_tile_rows() { return (BIG ? 128 : 64) / (HS <= 64 ? 1 : (HS <= 128 ? 2 : 4)); }
+template <int HS, bool BIG = false> __host__ __device__ constexpr size_t attn_smem_bytes() {
+    return (size_t)(ATT_QH * HS + HS + att_nt<BIG>() * att_tile_rows<HS, BIG>() * HS + ATT_QH * ATT_SC_CAP + 128) * 4;
 }
 
 LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
@@ -53,11 +56,12 @@ template <int N> LMRS_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_
 // rotated by the row index, which makes the per-position LDS.128 dot products bank-conflict-free without
 // touching the ascending-d summation order.  Latency floor: the two T-long dependent add chains (softmax sum,
 // a*v) -- the price of exact parity, see exact_math.cuh.
-template <int HS, int NTHR>
+template <int HS, int NTHR, bool BIG = false>
 LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const int kvh, const int h0, const int nh,
                                   const bool write_k) {
     constexpr int NWARP = NTHR / 32;
-    constexpr int TILE = att_tile_rows<HS>();
+    constexpr int ATT_NT = att_nt<BIG>();
+    constexpr int TILE = att_tile_rows<HS, BIG>();
     constexpr int C4 = HS / 4;                         // 16-byte chunks per row
     constexpr int CHUNKS = TILE * C4;                  // per tile
     constexpr int PERT = (CHUNKS + NTHR - 1) / NTHR;
@@ -331,7 +335,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     __syncthreads();   // the tile ring / score buffers may be reused by the caller
 }
 
-template <int HS>
+template <int HS, bool BIG>
 __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnParams p) {
     extern __shared__ __align__(16) float att_smem_dyn[];
     const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
@@ -339,7 +343,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
     pdl_launch_dependents();
     pdl_wait();
-    attn_decode_body<HS, ATT_THREADS>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
+    attn_decode_body<HS, ATT_THREADS, BIG>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
 }
 
 // ---- embedding row gather: the reference dequantizes the whole table at load (src/transformer.rs:243-245,

@@ -9,8 +9,8 @@
 //   warp 0      TMA producer   A tile [128 tok][128 B], B tile [128 rows][128 B], 128B-swizzled, 4-stage mbarrier ring
 //   warp 1      MMA issuer     4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32) per group into one of two TMEM
 //                              accumulator buffers; tcgen05.commit frees the smem stage and publishes the buffer
-//   warps 2..5  epilogue       tcgen05.ld 32x32b (thread = token row), s32 -> f32, * ws[col][g] * xs[row][g], added
-//                              into 128 f32 register accumulators in the reference's order -> results are bit-identical
+//   warps 2..9  epilogue       tcgen05.ld 32x32b (thread = token row x 64 columns), s32 -> f32, * ws[col][g] * xs[row][g], added
+//                              into 64 f32 register accumulators in the reference's order -> results are bit-identical
 //                              to the CPU path; double-buffered TMEM lets group g+1's MMAs run under group g's epilogue.
 // The CUDA-core mini-epilogue (4 instructions per element per group) is about twice the MMA time of a tile: the
 // honest int8 tensor-core roofline fraction of this formulation is bounded by it (hard part 1).
@@ -22,7 +22,7 @@
 namespace lmrs {
 
 constexpr int GEMM_M = 128, GEMM_N = 128, GEMM_K = 128, GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 192;
+constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant, 64 columns each)
 constexpr int GEMM_TILE_BYTES = GEMM_M * GEMM_K;   // 16 KB per operand tile
 constexpr size_t GEMM_SMEM = 1024 + (size_t)GEMM_STAGES * 2 * GEMM_TILE_BYTES + 2 * GEMM_N * 4 + 256;
 
@@ -102,7 +102,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 4); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
         fence_barrier_init();
     }
     if (warp == 1) {   // TMEM: 256 columns = two 128-column s32 accumulators
@@ -142,30 +142,32 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 umma_commit(&tfull[b]);                              // accumulator complete
             }
         }
-    } else {   // ---- epilogue: warps 2..5, TMEM lane quadrant = warp % 4, thread = one token row ----
+    } else {   // ---- epilogue: warps 2..9, TMEM lane quadrant = warp % 4, thread = one token row x 64 columns ----
+        constexpr int EC = GEMM_N / 2;                               // columns per epilogue thread
         const int quad = warp & 3;
+        const int chalf = (warp - 2) >> 2;                           // 0: columns 0..63, 1: columns 64..127
         const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;                             // 0..127 among the epilogue threads
+        const int et = threadIdx.x - 64;                             // 0..255 among the epilogue threads
         const bool row_ok = m0 + row < p.T;
-        float acc[GEMM_N];
+        float acc[EC];
 #pragma unroll
-        for (int j = 0; j < GEMM_N; j++) acc[j] = 0.0f;
+        for (int j = 0; j < EC; j++) acc[j] = 0.0f;
         for (int g = 0; g < G; g++) {
             const int b = g & 1;
             // stage this group's 128 column scales (file layout [o][G]) and fetch my row's activation scale
-            ws_s[b * GEMM_N + et] = (n0 + et < p.o) ? p.ws[(size_t)(n0 + et) * G + g] : 0.0f;
+            if (et < GEMM_N) ws_s[b * GEMM_N + et] = (n0 + et < p.o) ? p.ws[(size_t)(n0 + et) * G + g] : 0.0f;
             const float xsc = row_ok ? p.xs[(size_t)(m0 + row) * G + g] : 0.0f;
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            asm volatile("bar.sync 1, 256;" ::: "memory");
             mbar_wait(&tfull[b], (g >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < GEMM_N / 32; c++) {
+            for (int c = 0; c < EC / 32; c++) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * GEMM_N + c * 32), v);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * GEMM_N + chalf * EC + c * 32), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
                 for (int j = 0; j < 32; j++) {
-                    const float t = __fmul_rn(__fmul_rn((float)(int)v[j], ws_s[b * GEMM_N + c * 32 + j]), xsc);
+                    const float t = __fmul_rn(__fmul_rn((float)(int)v[j], ws_s[b * GEMM_N + chalf * EC + c * 32 + j]), xsc);
                     acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], t);
                 }
             }
@@ -178,9 +180,9 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             if (n0 < p.c1) { dst = p.out0; ld = p.ld0; cbase = 0; }
             else if (n0 < p.c2) { dst = p.out1; ld = p.ld1; cbase = p.c1; }
             else { dst = p.out2; ld = p.ld2; cbase = p.c2; }
-            float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase));
+            float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase) + chalf * EC);
 #pragma unroll
-            for (int j = 0; j < GEMM_N / 4; j++) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+            for (int j = 0; j < EC / 4; j++) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

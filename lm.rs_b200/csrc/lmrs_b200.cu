@@ -188,10 +188,10 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
     return p;
 }
 
-template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p0, int n_kv_heads, int rows) {
+template <int HS, bool BIG> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p0, int n_kv_heads, int rows) {
     static thread_local bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS>());
+        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS, BIG>());
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -205,14 +205,17 @@ template <int HS> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const Att
         if (e != cudaSuccess) return e;
         p.scores_ready = 1;   // ... and the serial softmax / a*v chains run per kv head
     }
-    return launch(m, attn_decode_kernel<HS>, dim3(n_kv_heads * p.chunks, rows), dim3(ATT_THREADS), attn_smem_bytes<HS>(), p);
+    return launch(m, attn_decode_kernel<HS, BIG>, dim3(n_kv_heads * p.chunks, rows), dim3(ATT_THREADS), attn_smem_bytes<HS, BIG>(), p);
+}
+template <int HS> static cudaError_t launch_attn_grid_t(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
+    return rows == 1 ? launch_attn_grid_hs<HS, true>(m, p, n_kv_heads, rows) : launch_attn_grid_hs<HS, false>(m, p, n_kv_heads, rows);
 }
 static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int rows) {
     switch (m->args.head_size) {
-        case 64: return launch_attn_grid_hs<64>(m, p, n_kv_heads, rows);
-        case 96: return launch_attn_grid_hs<96>(m, p, n_kv_heads, rows);
-        case 128: return launch_attn_grid_hs<128>(m, p, n_kv_heads, rows);
-        case 256: return launch_attn_grid_hs<256>(m, p, n_kv_heads, rows);
+        case 64: return launch_attn_grid_t<64>(m, p, n_kv_heads, rows);
+        case 96: return launch_attn_grid_t<96>(m, p, n_kv_heads, rows);
+        case 128: return launch_attn_grid_t<128>(m, p, n_kv_heads, rows);
+        case 256: return launch_attn_grid_t<256>(m, p, n_kv_heads, rows);
         default: return cudaErrorInvalidValue;
     }
 }

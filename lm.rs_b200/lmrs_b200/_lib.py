@@ -5,7 +5,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "liblmrs_b200.so")
+SO_PATH = os.environ.get("LMRS_B200_SO") or os.path.join(_HERE, "liblmrs_b200.so")   # LMRS_B200_SO: A/B builds
 PKG_ROOT = os.path.dirname(_HERE)
 
 # every symbol include/lmrs_b200.h declares (tests/test_abi.py checks the .so exports all of them)
