@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -109,8 +109,8 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="llama-3.2-1b")
     ap.add_argument("--quant", type=int, default=1, help="1 = Q8_0, 2 = Q4_0")
@@ -193,10 +193,10 @@ def main():
     m.set_stream(stream.cuda_stream)
     toks = np.random.default_rng(2).integers(0, a.vocab_size, args.warmup + args.steps)
     pos = args.pos
+    sampler = ClockSampler(local_rank); sampler.start()   # started before the warm-up: nvidia-smi needs ~100 ms to come up
     for i in range(args.warmup):
         m.forward_device(int(toks[i]), pos); pos += 1
     barrier()
-    sampler = ClockSampler(local_rank); sampler.start()
     l0 = m.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)

@@ -15,7 +15,7 @@ namespace lmrs {
 
 constexpr int ATT_THREADS = 256;   // stand-alone kernel; the megakernel runs the same body with its own block size
 constexpr int ATT_QH = 4;        // query heads per CTA (all sharing one KV head)
-constexpr int ATT_SC_CAP = 1024; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
+constexpr int ATT_SC_CAP = 2048; // positions whose scores are kept in shared memory (longer contexts: HBM scratch)
 // K/V tile ring geometry.  BIG (decode, one CTA per kv head): 128-row tiles x 3 in flight -- per-tile fixed costs
 // (barrier, cp.async issue, fix-ups) are a large part of the phase, measured 5.5% of the whole decode step;
 // small (batched prefill, thousands of CTAs): 64-row tiles x 4, half the shared memory so two CTAs fit per SM.
