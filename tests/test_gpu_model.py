@@ -143,3 +143,57 @@ def test_llama_1b_q8_full_shape(gpu_lib, ref, lf):
     for i, t in enumerate(toks[96:]):
         lg, le = gpu.forward(int(t), 96 + i), cpu.forward(int(t), 96 + i)
         assert np.array_equal(lg, le), f"pos {96 + i}: max abs {np.abs(lg - le).max()}"
+
+
+def test_fill_kv_cache_edge_cases(gpu_lib, ref, lf):
+    """empty batch, batch crossing the shared-memory score capacity (serial fallback + HBM score scratch), out of range."""
+    a = lf.model_args("tiny-llama", 1, seq_len=4096)
+    buf = lf.write_synthetic(a)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    assert gpu.fill_kv_cache(np.zeros(0, np.float32), 7) == 7                      # no embeddings: position unchanged
+    toks = prompt_tokens(a.vocab_size, 24, seed=9)
+    eg, ec = gpu.get_embeddings(toks), cpu.get_embeddings(toks)
+    assert gpu.fill_kv_cache(eg, 2040) == cpu.fill_kv_cache(ec, 2040) == 2064      # crosses 2048: per-token chain, scores in HBM scratch
+    assert np.array_equal(eg, ec)
+    assert np.array_equal(gpu.forward(5, 2064), cpu.forward(5, 2064))
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu.fill_kv_cache(gpu.get_embeddings(toks), 4090)                           # beyond seq_len
+
+
+def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
+    """matmul_q4 with sl > 1 is undefined in the reference (src/functional.rs:224): row-wise semantics, no GEMM path."""
+    buf = synth("tiny-llama", 2)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    toks = prompt_tokens(gpu.args.vocab_size, 20, seed=4)
+    eg, ec = gpu.get_embeddings(toks), cpu.get_embeddings(toks)
+    assert gpu.fill_kv_cache(eg, 0) == cpu.fill_kv_cache(ec, 0) == 20
+    assert np.array_equal(eg, ec)
+    assert np.array_equal(gpu.forward(3, 20), cpu.forward(3, 20))
+
+
+@pytest.mark.parametrize("env", [{"LMRS_B200_MEGA": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"}, {"LMRS_B200_GEMM": "0"},
+                                 {"LMRS_B200_ATT_SPLIT": "1"}])
+def test_alternative_execution_modes_stay_bit_exact(env):
+    """persistent megakernel / no graph, no PDL / serial prefill / GPU-wide score kernel: same bits as the default path."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, os, numpy as np
+sys.path[:0] = [os.path.join(os.getcwd(), "lm.rs_b200"), os.path.join(os.getcwd(), "oracle")]
+import lmrs_b200, lmrs_ref
+from lmrs_b200 import lmrs_file as lf
+for name, q in (("tiny-llama", 1), ("tiny-phi", 2), ("small-llama", 1)):
+    buf = lf.write_synthetic(lf.model_args(name, q))
+    g, _ = lmrs_b200.Transformer.new(buf); c = lmrs_ref.RefTransformer(buf)
+    toks = np.random.default_rng(2).integers(0, g.args.vocab_size, 30).astype(np.uint32)
+    eg, ec = g.get_embeddings(toks[:18]), c.get_embeddings(toks[:18])
+    assert g.fill_kv_cache(eg, 0) == c.fill_kv_cache(ec, 0) == 18 and np.array_equal(eg, ec)
+    for i, t in enumerate(toks[18:]):
+        assert np.array_equal(g.forward(int(t), 18 + i), c.forward(int(t), 18 + i)), (name, i)
+print("ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
