@@ -39,7 +39,7 @@ struct AttnParams {
 
 template <int HS, bool BIG = false> __host__ __device__ constexpr int att_tile_rows() { return (BIG ? 128 : 64) / (HS <= 64 ? 1 : (HS <= 128 ? 2 : 4)); }
 template <int HS, bool BIG = false> __host__ __device__ constexpr size_t attn_smem_bytes() {
-    return (size_t)(ATT_QH * HS + HS + att_nt<BIG>() * att_tile_rows<HS, BIG>() * HS + ATT_QH * ATT_SC_CAP + 128) * 4;
+    return (size_t)(ATT_QH * HS + HS + att_nt<BIG>() * att_tile_rows<HS, BIG>() * HS + ATT_QH * ATT_SC_CAP + 128 + 64) * 4;
 }
 
 LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
@@ -70,6 +70,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     float* tile = k_s + HS;                            // [ATT_NT][TILE][HS]
     float* sc_s = tile + ATT_NT * TILE * HS;           // [ATT_QH][ATT_SC_CAP]
     float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [128]: per-head per-warp maxima, then sums at [96..]
+    uint64_t* exp_tab = reinterpret_cast<uint64_t*>(red + 128);   // [32] expf table copy
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int brow = p.batch ? (int)blockIdx.y : 0;
@@ -104,6 +105,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         }
         cp_async_commit();
     };
+    if (tid < 32) exp_tab[tid] = kExp2fTab[tid];
     trace_event(200);
     // K tiles start flowing before anything else (rows < pos are in the cache since earlier steps)
     if (!p.scores_ready) {
@@ -231,7 +233,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         float mx = red[h * NWARP];
 #pragma unroll
         for (int w = 1; w < NWARP; w++) mx = fmaxf(mx, red[h * NWARP + w]);
-        for (int t = tid; t < T; t += NTHR) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
+        for (int t = tid; t < T; t += NTHR) sc[t] = expf_glibc_t(__fsub_rn(sc[t], mx), exp_tab);
     }
     __syncthreads();
     trace_event(203);

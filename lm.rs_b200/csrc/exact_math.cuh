@@ -36,7 +36,9 @@ static const uint64_t kExp2fTab[32] = {
     0x3feee89f995ad3adull, 0x3feeff76f2fb5e47ull, 0x3fef199bdd85529cull, 0x3fef3720dcef9069ull,
     0x3fef5818dcfba487ull, 0x3fef7c97337b9b5full, 0x3fefa4afa2a490daull, 0x3fefd0765b6e4540ull};
 
-LMRS_HD float expf_glibc(float x) {
+// T: the 32-entry table (kExp2fTab or a shared-memory copy of it: a kernel's first touch of the global table is an
+// L2/HBM round trip on the critical path of every launch, so device code stages it in shared memory up front)
+LMRS_HD float expf_glibc_t(float x, const uint64_t* T) {
     uint32_t ix;
 #ifdef __CUDA_ARCH__
     ix = __float_as_uint(x);
@@ -60,7 +62,7 @@ LMRS_HD float expf_glibc(float x) {
     const uint64_t ki = (uint64_t)__double_as_longlong(kd);
     kd = __dsub_rn(kd, Shift);
     const double r = __dsub_rn(z, kd);
-    const uint64_t t = kExp2fTab[ki & 31] + (ki << 47);
+    const uint64_t t = T[ki & 31] + (ki << 47);
     const double s = __longlong_as_double((long long)t);
     const double zz = __dadd_rn(__dmul_rn(C0, r), C1);
     const double r2 = __dmul_rn(r, r);
@@ -76,7 +78,7 @@ LMRS_HD float expf_glibc(float x) {
     memcpy(&ki, &kd, 8);
     kd -= Shift;
     const double r = z - kd;
-    const uint64_t t = kExp2fTab[ki & 31] + (ki << 47);
+    const uint64_t t = T[ki & 31] + (ki << 47);
     double s;
     memcpy(&s, &t, 8);
     const double zz = C0 * r + C1;
@@ -87,5 +89,7 @@ LMRS_HD float expf_glibc(float x) {
     return (float)y;
 #endif
 }
+
+LMRS_HD float expf_glibc(float x) { return expf_glibc_t(x, kExp2fTab); }
 
 }  // namespace lmrs

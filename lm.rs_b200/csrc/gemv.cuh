@@ -107,7 +107,7 @@ template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n, boo
     size_t xq = (size_t)n;                         // Q8: n codes; Q4: n/2 even + n/2 odd signed bytes
     size_t xs = (size_t)(n / GS) * 4 * 2;          // scales + per-group code sums (Q4)
     size_t xf = norm ? (size_t)n * 4 : 0;          // PRO_NORM: f32 staging of the vector being normed
-    return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128 + xf;
+    return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128 + xf + 256;
 }
 
 struct RowRange { int row0, nrows; };
@@ -224,6 +224,7 @@ struct GemvSmem {
     int* xsum;      // [G] per-group sums of the signed activation bytes (Q4)
     float* red;     // [64] reduction scratch
     float* xf;      // [n] f32 staging for the exact rmsnorm chains (PRO_NORM)
+    const uint64_t* exp_tab;   // shared-memory copy of the expf table (GLU epilogue), or the global one
 };
 
 // ---- one warp's two weight streams for one matrix -------------------------------------------------------------------
@@ -265,6 +266,47 @@ LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint
 }
 
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
+// NB groups at once (one float4 per lane per group): the NB warp-max reductions and divisions are interleaved by hand
+// so that their shuffle/divide latencies overlap (one group at a time is a ~700-cycle dependent chain)
+template <int QT, int NB>
+LMRS_DEVINL void quantize_groups_to_smem(const float4 (&y)[NB], int g0, int gstride, int G, uint8_t* xq, float* xs, int* xsum, int n) {
+    const int lane = threadIdx.x & 31;
+    float m[NB];
+#pragma unroll
+    for (int u = 0; u < NB; u++) m[u] = fmaxf(fmaxf(fabsf(y[u].x), fabsf(y[u].y)), fmaxf(fabsf(y[u].z), fabsf(y[u].w)));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int u = 0; u < NB; u++) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
+    }
+    if (QT == 1) {
+        float sc[NB];
+#pragma unroll
+        for (int u = 0; u < NB; u++) sc[u] = __fdiv_rn(m[u], 127.0f);
+        uint32_t pk[NB];
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int a = round_sat_i8(__fdiv_rn(y[u].x, sc[u])), b = round_sat_i8(__fdiv_rn(y[u].y, sc[u]));
+            const int c = round_sat_i8(__fdiv_rn(y[u].z, sc[u])), d = round_sat_i8(__fdiv_rn(y[u].w, sc[u]));
+            pk[u] = (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
+        }
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int g = g0 + u * gstride;
+            if (g < G) {
+                reinterpret_cast<uint32_t*>(xq + (size_t)g * GS)[lane] = pk[u];
+                if (lane == 0) xs[g] = sc[u];
+            }
+        }
+    } else {
+#pragma unroll
+        for (int u = 0; u < NB; u++) {
+            const int g = g0 + u * gstride;
+            if (g < G) quantize_group_to_smem<QT>(y[u], g, xq, xs, xsum, n);
+        }
+    }
+}
+
 template <int QT, int WARPS>
 LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     constexpr int THREADS = WARPS * 32;
@@ -356,24 +398,24 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         trace_event(110);
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
         trace_event(111);
+        float4 yy[NORM_MAXC];
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
-            const int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
-            if (c < nchunks) {
-                const float4 w = wnv[k];
-                float4 y;
-                if (p.unit_offset) {
-                    y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
-                    y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
-                    y.z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, v[k].z));
-                    y.w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, v[k].w));
-                } else {
-                    y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
-                    y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
-                }
-                quantize_group_to_smem<QT>(y, c >> 5, sm.xq, sm.xs, sm.xsum, n);
+            const float4 w = wnv[k];
+            float4 y;
+            if (p.unit_offset) {
+                y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
+                y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
+                y.z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, v[k].z));
+                y.w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, v[k].w));
+            } else {
+                y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
+                y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
             }
+            yy[k] = y;
         }
+        // chunk c = tid + k*THREADS holds 4 elements; 32 consecutive chunks = one warp = one group: group = warp + k*WARPS
+        quantize_groups_to_smem<QT, NORM_MAXC>(yy, warp, WARPS, G, sm.xq, sm.xs, sm.xsum, n);
     } else if (p.pro == PRO_QUANT) {
         const float4* ain = reinterpret_cast<const float4*>(p.act_in);
         for (int g0 = warp; g0 < G; g0 += WARPS * 8) {   // 8 groups per warp in flight: one L2 round trip, not eight
@@ -383,11 +425,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 const int g = g0 + u * WARPS;
                 y[u] = g < G ? __ldcg(&ain[g * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int g = g0 + u * WARPS;
-                if (g < G) quantize_group_to_smem<QT>(y[u], g, sm.xq, sm.xs, sm.xsum, n);
-            }
+            quantize_groups_to_smem<QT, 8>(y, g0, WARPS, G, sm.xq, sm.xs, sm.xsum, n);
         }
     } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
         if (QT == 1) {
@@ -435,13 +473,13 @@ LMRS_DEVINL void consumer_begin(Consumer<QT>& c, const WarpStreams<QT>& w, const
         for (int i = 0; i < 8; i++) c.xr[i] = xv[(i + l16) & 7];
     }
 }
-LMRS_DEVINL float glu_act(int epi, float val) {
+LMRS_DEVINL float glu_act(int epi, float val, const uint64_t* exp_tab = kExp2fTab) {
     if (epi == EPI_GLU_GELU) {  // tanh-GELU, tanh in f64 (src/transformer.rs:614)
         const float inner = __fadd_rn(val, __fmul_rn(__fmul_rn(__fmul_rn(0.044715f, val), val), val));
         const float th = (float)tanh(0.7978845608028654 * (double)inner);
         return __fmul_rn(val, __fmul_rn(0.5f, __fadd_rn(1.0f, th)));
     }
-    return __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc(-val))));   // SiLU (:617), exp = glibc expf
+    return __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc_t(-val, exp_tab))));   // SiLU (:617), exp = glibc expf
 }
 LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos) {
     if (p.epi == EPI_QKV) {
@@ -518,7 +556,7 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
         const bool row_done = (c.g_base + SG == G);
         if (w.glu) {
             const float up = __shfl_sync(0xffffffffu, a, 16);
-            if (row_done && lane == 0 && valid) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, a), up);
+            if (row_done && lane == 0 && valid) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, a, sm.exp_tab), up);
         } else if (row_done && l16 == 0 && valid) {
             store_row(p, rr.row0 + row_l, a, pos);
         }
@@ -539,7 +577,7 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
     c.acc = acc;
     if (w.glu) {
         const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
-        if (is_last && half == 0) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, mine), up);
+        if (is_last && half == 0) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, mine, sm.exp_tab), up);
     } else if (is_last) {
         store_row(p, rr.row0 + row_l, mine, pos);
     }
@@ -554,6 +592,7 @@ LMRS_DEVINL GemvSmem carve_gemv_smem(uint8_t* base, int n, int n_bars) {
     sm.xsum = reinterpret_cast<int*>(sm.xs + G);
     sm.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.xs) + ((G * 8 + 127) / 128) * 128);
     sm.xf = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.red + 64) + n_bars * 8 + 64);
+    sm.exp_tab = kExp2fTab;
     return sm;
 }
 
@@ -563,8 +602,13 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem;
-    const GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
+    GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm.red + 64) + warp * DEPTH;
+    {   // expf table -> shared memory (last 256 B of the allocation), long before the first GLU epilogue needs it
+        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (p.pro == PRO_NORM ? (size_t)p.n * 4 : 0));
+        if (threadIdx.x < 32) tab[threadIdx.x] = kExp2fTab[threadIdx.x];
+        sm.exp_tab = tab;
+    }
     const WarpStreams<QT> w = make_streams<QT>(stream_desc(p), blockIdx.x * WARPS + warp, gridDim.x * WARPS);
 
     if (lane == 0) {

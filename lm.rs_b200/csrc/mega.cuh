@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             sm.red = red; sm.xf = xf; sm.xq = xq;
             sm.xs = reinterpret_cast<float*>(xq + ((g.n + 127) / 128) * 128);
             sm.xsum = reinterpret_cast<int*>(sm.xs + g.n / GS);
+            sm.exp_tab = kExp2fTab;
             gemv_prologue<QT, MEGA_WARPS>(g, sm);
             stamp(ph, 1);
             const WarpStreams<QT> w = make_streams<QT>(sd_s[ph], wslot, n_wslots);

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_
     sm.xsum = reinterpret_cast<int*>(sm.xs + G);
     sm.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.xs) + ((G * 8 + 127) / 128) * 128);
     sm.xf = sm.red + 64;
+    sm.exp_tab = kExp2fTab;
     if (p.x_in) p.x_in += row * n;
     if (p.delta) p.delta += row * n;
     if (p.x_out) p.x_out += row * n;
