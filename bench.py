@@ -53,7 +53,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
             self.proc = None
@@ -109,8 +109,8 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--model", default="llama-3.2-1b")
     ap.add_argument("--quant", type=int, default=1, help="1 = Q8_0, 2 = Q4_0")
@@ -176,6 +176,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank); sampler.start()   # nvidia-smi needs ~100 ms to come up: started before the prefill,
+                                                           # samples taken before the timed decode region are dropped below
     # ---- prefill: fill_kv_cache(P embeddings), end to end through the C ABI ------------------------------------
     emb0 = m.get_embeddings(prompt[:args.pos])
     emb = emb0.copy()
@@ -193,12 +195,12 @@ def main():
     m.set_stream(stream.cuda_stream)
     toks = np.random.default_rng(2).integers(0, a.vocab_size, args.warmup + args.steps)
     pos = args.pos
-    sampler = ClockSampler(local_rank); sampler.start()   # started before the warm-up: nvidia-smi needs ~100 ms to come up
-    for i in range(args.warmup):
-        m.forward_device(int(toks[i]), pos); pos += 1
+    for i in range(args.warmup):       # warm-up and timed steps cover the SAME positions P..P+K-1 (BASELINE: "64 tokens at pos 512")
+        m.forward_device(int(toks[i]), pos + (i % args.steps))
     barrier()
     l0 = m.kernel_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.rows.clear()               # keep only samples from the timed region (+ the e2e leg)
     ev0.record(stream)
     for i in range(args.steps):
         m.forward_device(int(toks[args.warmup + i]), pos); pos += 1
@@ -206,7 +208,6 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = m.kernel_launches() - l0
-    clocks = sampler.stop()
     m.set_stream(0)
     if dist is not None:
         t = torch.tensor([dev_ms], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dev_ms = float(t.item())
@@ -215,8 +216,9 @@ def main():
 
     # ---- decode, end-to-end leg: forward() -> host logits -> greedy argmax (chat.rs generate loop, temperature 0) --
     tok = int(prompt[args.pos])
+    pos = args.pos
     for i in range(args.warmup):
-        tok = int(np.argmax(m.forward(tok, pos))) % a.vocab_size; pos += 1
+        tok = int(np.argmax(m.forward(tok, pos + (i % args.steps)))) % a.vocab_size
     barrier()
     t0 = time.perf_counter()
     for i in range(args.steps):
@@ -225,6 +227,7 @@ def main():
     if dist is not None:
         t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
     e2e = args.steps / e2e_s
+    clocks = sampler.stop()
 
     if rank != 0:
         if dist is not None:
@@ -234,7 +237,7 @@ def main():
         return
     peak, peak_src = load_peaks()
     peak *= args.gpus
-    mid_pos = args.pos + args.warmup + args.steps // 2
+    mid_pos = args.pos + args.steps // 2
     alg_bytes = lf.decode_bytes_per_token(a, mid_pos)
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": "decode step (all kernels of one forward; weight-streaming GEMV dominates)",
