@@ -105,7 +105,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         }
         cp_async_commit();
     };
-    if (tid < 32) exp_tab[tid] = kExp2fTab[tid];
+    if (warp == NWARP - 1) exp_tab[lane] = kExp2fTab[lane];   // by the last warp: warp 0 must not stall before the K prefetch
     trace_event(200);
     // K tiles start flowing before anything else (rows < pos are in the cache since earlier steps)
     if (!p.scores_ready) {
@@ -139,7 +139,6 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
 
     trace_event(201);
     // ---- scores: s[h][t] = (sum_d q[h][d]*k[t][d]) / sqrt(hs)   (:507-528) --------------------------------
-    long long a_wait = 0, a_comp = 0, a_iss = 0, a_chain = 0;
     if (p.scores_ready) {   // dot products were spread over the whole GPU by attn_scores_kernel
         const float* sg = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
         if (in_smem)
@@ -148,7 +147,6 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         else sc_base = const_cast<float*>(sg);
     }
     for (int tl = 0; tl < (p.scores_ready ? 0 : ntiles); tl++) {
-        const long long ca = clock64();
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
         float* tb = tile + (tl % ATT_NT) * TILE * HS;
         if (have_knew && pos / TILE == tl) {           // the new K row comes from shared memory, same rotated layout
@@ -159,11 +157,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             }
         }
         __syncthreads();                               // tile tl visible; everyone is done with tile tl-1
-        const long long cb = clock64();
-        a_wait += cb - ca;
         issue_tile(p.kcache, tl + ATT_NT - 1, true);   // refill the slot tile tl-1 used
-        const long long cc_ = clock64();
-        a_iss += cc_ - cb;
         const int rows = min(TILE, T - tl * TILE);
         // thread = (row r, pair of heads): one LDS.128 of K feeds two independent dot-product chains (ILP 2),
         // products of chunk d4+1 are formed while chunk d4's dependent adds run
@@ -174,7 +168,6 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             const float4* qa = reinterpret_cast<const float4*>(q_s + ha * HS);
             const float4* qb = reinterpret_cast<const float4*>(q_s + hb * HS);
             const float4* k4 = reinterpret_cast<const float4*>(tb + r * HS);
-            const long long cd = clock64();
             float sa = 0.0f, sb = 0.0f;
             // the whole K row first (C4 independent LDS.128: their latency overlaps), un-rotating on the fly
             float4 kr[C4];
@@ -193,7 +186,6 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
                 sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
             }
-            a_chain += clock64() - cd;
 #pragma unroll
             for (int w = 0; w < 2; w++) {
                 const int h = w ? hb : ha;
@@ -208,10 +200,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 sc_base[(size_t)h * sc_stride + t] = score;
             }
         }
-        a_comp += clock64() - cb;
     }
-    trace_value(310, (unsigned long long)a_wait); trace_value(311, (unsigned long long)a_comp);
-    trace_value(312, (unsigned long long)a_iss); trace_value(313, (unsigned long long)a_chain);
     cp_async_wait<0>();
     __syncthreads();
     trace_event(202);

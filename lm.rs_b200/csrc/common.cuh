@@ -104,12 +104,20 @@ LMRS_DEVINL void trace_reset() {
     if (threadIdx.x == 0) trace_counter() = 0;
 }
 LMRS_DEVINL void trace_value(int tag, unsigned long long value) {   // value in the timestamp slot
+#ifndef LMRS_TRACE
+    (void)tag; (void)value;
+    return;   // compiled out by default: even the disabled check is a global load on the critical path
+#endif
     if (g_trace_buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         const unsigned int i = trace_counter()++;
         if (i < 8192u) { g_trace_buf[2 * i] = ((unsigned long long)clock64() << 16) | (unsigned long long)(tag & 0xffff); g_trace_buf[2 * i + 1] = value; }
     }
 }
 LMRS_DEVINL void trace_event(int tag) {
+#ifndef LMRS_TRACE
+    (void)tag;
+    return;
+#endif
     if (g_trace_buf != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -398,24 +398,24 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         trace_event(110);
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
         trace_event(111);
-        float4 yy[NORM_MAXC];
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
-            const float4 w = wnv[k];
-            float4 y;
-            if (p.unit_offset) {
-                y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
-                y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
-                y.z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, v[k].z));
-                y.w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, v[k].w));
-            } else {
-                y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
-                y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
+            const int c = tid + k * THREADS;       // chunk c = 4 elements; 32 consecutive chunks = one warp = one group
+            if (c < nchunks) {
+                const float4 w = wnv[k];
+                float4 y;
+                if (p.unit_offset) {
+                    y.x = __fmul_rn(__fadd_rn(1.0f, w.x), __fmul_rn(r, v[k].x));
+                    y.y = __fmul_rn(__fadd_rn(1.0f, w.y), __fmul_rn(r, v[k].y));
+                    y.z = __fmul_rn(__fadd_rn(1.0f, w.z), __fmul_rn(r, v[k].z));
+                    y.w = __fmul_rn(__fadd_rn(1.0f, w.w), __fmul_rn(r, v[k].w));
+                } else {
+                    y.x = __fmul_rn(w.x, __fmul_rn(r, v[k].x)); y.y = __fmul_rn(w.y, __fmul_rn(r, v[k].y));
+                    y.z = __fmul_rn(w.z, __fmul_rn(r, v[k].z)); y.w = __fmul_rn(w.w, __fmul_rn(r, v[k].w));
+                }
+                quantize_group_to_smem<QT>(y, c >> 5, sm.xq, sm.xs, sm.xsum, n);
             }
-            yy[k] = y;
         }
-        // chunk c = tid + k*THREADS holds 4 elements; 32 consecutive chunks = one warp = one group: group = warp + k*WARPS
-        quantize_groups_to_smem<QT, NORM_MAXC>(yy, warp, WARPS, G, sm.xq, sm.xs, sm.xsum, n);
     } else if (p.pro == PRO_QUANT) {
         const float4* ain = reinterpret_cast<const float4*>(p.act_in);
         for (int g0 = warp; g0 < G; g0 += WARPS * 8) {   // 8 groups per warp in flight: one L2 round trip, not eight
@@ -425,7 +425,11 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 const int g = g0 + u * WARPS;
                 y[u] = g < G ? __ldcg(&ain[g * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            quantize_groups_to_smem<QT, 8>(y, g0, WARPS, G, sm.xq, sm.xs, sm.xsum, n);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const int g = g0 + u * WARPS;
+                if (g < G) quantize_group_to_smem<QT>(y[u], g, sm.xq, sm.xs, sm.xsum, n);
+            }
         }
     } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
         if (QT == 1) {
@@ -604,11 +608,6 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     uint8_t* ring = smem;
     GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm.red + 64) + warp * DEPTH;
-    {   // expf table -> shared memory (last 256 B of the allocation), long before the first GLU epilogue needs it
-        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (p.pro == PRO_NORM ? (size_t)p.n * 4 : 0));
-        if (threadIdx.x < 32) tab[threadIdx.x] = kExp2fTab[threadIdx.x];
-        sm.exp_tab = tab;
-    }
     const WarpStreams<QT> w = make_streams<QT>(stream_desc(p), blockIdx.x * WARPS + warp, gridDim.x * WARPS);
 
     if (lane == 0) {
@@ -621,6 +620,11 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     if (lane == 0)   // weights never depend on the previous kernel: start streaming before griddepcontrol.wait
         for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     pdl_launch_dependents();
+    if (p.epi == EPI_GLU_SILU) {   // expf table -> shared memory (last 256 B), by the LAST warp, after the weight prefetch was issued
+        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (p.pro == PRO_NORM ? (size_t)p.n * 4 : 0));
+        if (warp == WARPS - 1) tab[lane] = kExp2fTab[lane];
+        sm.exp_tab = tab;
+    }
     pdl_wait();  // upstream activations are complete and visible from here on
 
     gemv_prologue<QT, WARPS>(p, sm);

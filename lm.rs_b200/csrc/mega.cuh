@@ -158,21 +158,14 @@ __global__ void __launch_bounds__(MEGA_WARPS * 32, 1) decode_mega_kernel(const M
             const WarpStreams<QT> w = make_streams<QT>(sd_s[ph], wslot, n_wslots);
             Consumer<QT> cs;
             consumer_begin<QT>(cs, w, sm);
-            long long c_wait = 0, c_cons = 0, c_iss = 0;
             for (int s = 0; s < w.nst; s++) {
                 const uint32_t slot = consumed % (uint32_t)depth;
-                const long long c0 = clock64();
                 mbar_wait(&bars[slot], (consumed / (uint32_t)depth) & 1u);
-                const long long c1 = clock64();
                 consume_stage<QT>(g, w, s, ring + (size_t)slot * STAGE, sm, cs, pos);
                 __syncwarp();
-                const long long c2 = clock64();
                 consumed++;
                 if (pf_phase < mp.n_phases) pf_issue();   // refill the slot just freed with the stage DEPTH ahead
-                c_wait += c1 - c0; c_cons += c2 - c1; c_iss += clock64() - c2;
             }
-            trace_value(300, (unsigned long long)c_wait); trace_value(301, (unsigned long long)c_cons); trace_value(302, (unsigned long long)c_iss);
-            trace_value(303, (unsigned long long)w.nst);
         } else if (P.kind == PH_ATTN) {
             const int units = mp.n_kv_heads * mp.att_chunks;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
