@@ -100,7 +100,7 @@ struct lmrs_b200 {
     uint64_t launches = 0;
     int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
-    int gemv_cfg = 0, gemv_ctas_per_sm = 1;
+    int gemv_cfg = 0, gemv_cfg_long = 0, gemv_ctas_per_sm = 1;
     Shard shard;  // multi-GPU exchange (shard.h); inert when world == 1
 };
 
@@ -162,14 +162,16 @@ static cudaError_t repack_bp16(int q_type, uint8_t* dst, const uint8_t* src_q, c
 }
 
 static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
-    const GemvCfg c = kGemvCfgs[m->gemv_cfg];
-    gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(m->gemv_cfg) : gemv_kernel_for<2>(m->gemv_cfg);
-    size_t smem = q_type == 1 ? gemv_smem_for<1>(m->gemv_cfg, p.n, p.pro == PRO_NORM) : gemv_smem_for<2>(m->gemv_cfg, p.n, p.pro == PRO_NORM);
+    // long activation vectors (the down projection quantizes hidden_dim elements in its prologue) get more warps
+    const int cfg = (p.pro == PRO_QUANT && p.n >= 4096) ? m->gemv_cfg_long : m->gemv_cfg;
+    const GemvCfg c = kGemvCfgs[cfg];
+    gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(cfg) : gemv_kernel_for<2>(cfg);
+    size_t smem = q_type == 1 ? gemv_smem_for<1>(cfg, p.n, p.pro == PRO_NORM) : gemv_smem_for<2>(cfg, p.n, p.pro == PRO_NORM);
     static thread_local size_t max_set[2][8] = {};
-    if (smem > max_set[q_type - 1][m->gemv_cfg]) {
+    if (smem > max_set[q_type - 1][cfg]) {
         cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        max_set[q_type - 1][m->gemv_cfg] = smem;
+        max_set[q_type - 1][cfg] = smem;
     }
     int grid = m->sms * m->gemv_ctas_per_sm;
     // never launch more CTAs than there are row units to hand out (tiny matrices)
@@ -916,6 +918,8 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     m->use_pdl = env_int("LMRS_B200_PDL", 1) != 0;
     m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 0);
     if (m->gemv_cfg < 0 || m->gemv_cfg > 4) m->gemv_cfg = 0;
+    m->gemv_cfg_long = env_int("LMRS_B200_GEMV_CFG_LONG", m->gemv_cfg);
+    if (m->gemv_cfg_long < 0 || m->gemv_cfg_long > 4) m->gemv_cfg_long = m->gemv_cfg;
     m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
     if ((int)m->args.dim > NORM_MAX_DIM) {
