@@ -81,10 +81,12 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     const bool have_knew = p.k_new != nullptr;   // decode: K row of this step arrives un-rotated in a staging row
     const int T = pos + 1;
     const bool in_smem = T <= ATT_SC_CAP;
-    float* sc_base = in_smem ? sc_s : p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
-    const int sc_stride = in_smem ? ATT_SC_CAP : p.seq_len;
+    float* const sc_glob = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
     const int ntiles = (T + TILE - 1) / TILE;
 
+    // everything below runs once, specialised on where the scores live: a pointer the compiler can prove to be shared
+    // memory turns every access of the softmax and of the a*v chains into LDS/STS instead of generic LD/ST
+    auto run = [&](float* const sc_base, const int sc_stride) {
     // tile tl of K (rotated columns) or V (plain) -> ring slot tl % ATT_NT; rows >= T and the row `pos` of K
     // (not in the cache yet) are skipped; always commits a group so the wait counts stay uniform
     auto issue_tile = [&](const float* base, int tl, bool rotate) {
@@ -144,7 +146,6 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         if (in_smem)
             for (int h = 0; h < nh; h++)
                 for (int t = tid; t < T; t += NTHR) sc_s[h * ATT_SC_CAP + t] = __ldcg(sg + (size_t)h * p.seq_len + t);
-        else sc_base = const_cast<float*>(sg);
     }
     for (int tl = 0; tl < (p.scores_ready ? 0 : ntiles); tl++) {
         cp_async_wait<ATT_NT - 2>();                   // this thread's copies of tile tl have landed
@@ -323,6 +324,9 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             if (hp * 2 + 1 < nh) out_row[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
         }
     }
+    };
+    if (in_smem) run(sc_s, ATT_SC_CAP);
+    else run(sc_glob, p.seq_len);
     __syncthreads();   // the tile ring / score buffers may be reused by the caller
 }
 

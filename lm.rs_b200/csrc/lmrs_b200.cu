@@ -918,7 +918,7 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     m->use_pdl = env_int("LMRS_B200_PDL", 1) != 0;
     m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 0);
     if (m->gemv_cfg < 0 || m->gemv_cfg > 4) m->gemv_cfg = 0;
-    m->gemv_cfg_long = env_int("LMRS_B200_GEMV_CFG_LONG", m->gemv_cfg);
+    m->gemv_cfg_long = env_int("LMRS_B200_GEMV_CFG_LONG", m->gemv_cfg == 0 ? 2 : m->gemv_cfg);   // 16 warps: measured ~1% of the step
     if (m->gemv_cfg_long < 0 || m->gemv_cfg_long > 4) m->gemv_cfg_long = m->gemv_cfg;
     m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
