@@ -84,6 +84,10 @@ int lmrs_b200_set_stream(lmrs_b200_t* m, void* cuda_stream); /* cudaStream_t; NU
 int lmrs_b200_synchronize(lmrs_b200_t* m);
 /* number of CUDA kernels this handle has launched (graph replays count their kernel nodes) */
 int lmrs_b200_kernel_launches(const lmrs_b200_t* m, uint64_t* count);
+/* measurement aid: enqueue only the matrix-vector launches (gemv_kernel) of one decode step -- the 4 per block + the
+ * classifier, with their real prologues/epilogues, attention skipped -- so that bench.py can time the HBM-bound kernel
+ * by itself with CUDA events on the handle's stream.  *n_launches = launches enqueued.  Results are meaningless. */
+int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches);
 /* test access: copy K and V rows [pos0, pos0+n) of one layer to host (f32 [n][kv_dim] each) */
 int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out);
 /* test access: copy one activation buffer of the LAST executed block to host.  name: "x0","x1" (residual

@@ -991,6 +991,18 @@ extern "C" int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, f
     return 0;
 }
 
+extern "C" int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches) {
+    if (!m) return fail("null handle");
+    if (pos >= m->args.seq_len) return fail("position out of range");
+    CK(cudaSetDevice(m->device));
+    if (push_step(m, 0, pos, pos, m->seq_decode)) return 1;
+    int n = 0;
+    for (const MegaPhase& P : m->ph_decode)
+        if (P.kind == PH_GEMV) { CK(launch_gemv(m, m->args.q_type, P.g)); n++; }
+    if (n_launches) *n_launches = n;
+    return 0;
+}
+
 extern "C" int lmrs_b200_logits_device(lmrs_b200_t* m, float** logits_dev) {
     if (!m || !logits_dev) return fail("null argument");
     *logits_dev = m->d_logits;

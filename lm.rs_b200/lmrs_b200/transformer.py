@@ -98,6 +98,12 @@ class Transformer:
         check(lib().lmrs_b200_kernel_launches(self._h, C.byref(n)))
         return n.value
 
+    def bench_gemv_pass(self, pos: int) -> int:
+        """enqueue only the gemv_kernel launches of one decode step (measurement aid); returns the launch count"""
+        n = C.c_int()
+        check(lib().lmrs_b200_bench_gemv_pass(self._h, pos, C.byref(n)))
+        return n.value
+
     def read_kv(self, layer: int, pos0: int, n: int):
         kvd = self.args.head_size * self.args.n_kv_heads
         k, v = np.zeros((n, kvd), np.float32), np.zeros((n, kvd), np.float32)
