@@ -106,6 +106,20 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
             "cores": lmrs_ref.lib().lmrs_ref_num_threads(), "steps": steps}
 
 
+def load_gemv_traffic(model, quant):
+    """dram__bytes_read.sum + dram__bytes_write.sum per gemv_kernel launch (average over a step's launches) from the
+    committed `ncu --set full` capture of this workload (profiles/r1_gemv_traffic.json); None for workloads not captured."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemv_traffic.json")
+    try:
+        d = json.load(open(p))
+    except OSError:
+        return None, "no ncu capture committed"
+    w = d.get("workload", {})
+    if w.get("model") != model or w.get("quant") != quant:
+        return None, "no ncu --set full capture for this workload"
+    return d["traffic_bytes_per_launch_avg"], "profiles/r1_gemv_traffic.json (ncu --set full, per-launch average)"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -253,12 +267,13 @@ def main():
     w_bytes = lf.decode_bytes_per_token(a)                      # weights + scales + norm vectors: what gemv_kernel streams
     achieved = (w_bytes / n_gemv) / (gemv_ms / n_gemv * 1e-3) / 1e9
     step_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    traffic, traffic_src = load_gemv_traffic(args.model, args.quant)
     roofline = {"bound": "hbm", "kernel": f"gemv_kernel ({n_gemv} launches per step: 4 per block + classifier)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src + (f" x {args.gpus} GPUs" if args.gpus > 1 else ""),
                 "algorithmic_bytes_per_launch": w_bytes / n_gemv, "avg_launch_us": gemv_ms / n_gemv * 1e3,
                 "how": "CUDA events around the step's gemv_kernel launches alone (PDL-chained, real prologues/epilogues, attention skipped)",
-                "traffic": None,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "whole_step": {"algorithmic_bytes_per_step": alg_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                                "launches_per_step": launches / args.steps,
                                "note": "includes the latency-bound exact-order attention (not an HBM-bound kernel)"}}
