@@ -34,6 +34,7 @@ struct AttnParams {
     int batch, q_stride;   // batched prefill: grid.y = token index; pos = step->pos + blockIdx.y, q/out rows strided
     int scores_ready;      // scores already computed by attn_scores_kernel (global scratch [row][head][seq_len])
     float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
+    int dev_skip;          // -DLMRS_DEV_PROBES builds only: phases to leave out when timing (results are then wrong)
     const StepParams* step;
 };
 
@@ -47,6 +48,133 @@ LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
 }
 LMRS_DEVINL void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> LMRS_DEVINL void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// sum of sc[0..T) accumulated in ascending order with one dependent f32 add per element (src/functional.rs:131-134).
+// Blocks of 8 values rotate through three statically indexed register sets (the loop body is unrolled three times), so
+// two blocks of loads are always in flight ahead of the adds and no register moves sit behind a load.
+LMRS_DEVINL float serial_sum_f32(const float* __restrict__ sc, const int T) {
+    float sum = 0.0f;
+    int t = 0;
+    if (T >= 16) {
+        float4 r[3][2];
+        r[0][0] = *reinterpret_cast<const float4*>(sc); r[0][1] = *reinterpret_cast<const float4*>(sc + 4);
+        r[1][0] = *reinterpret_cast<const float4*>(sc + 8); r[1][1] = *reinterpret_cast<const float4*>(sc + 12);
+        for (; t + 40 <= T; t += 24) {
+#pragma unroll
+            for (int s = 0; s < 3; s++) {
+                const int nx = (s + 2) % 3;
+                r[nx][0] = *reinterpret_cast<const float4*>(sc + t + 8 * s + 16);
+                r[nx][1] = *reinterpret_cast<const float4*>(sc + t + 8 * s + 20);
+                sum = __fadd_rn(sum, r[s][0].x); sum = __fadd_rn(sum, r[s][0].y); sum = __fadd_rn(sum, r[s][0].z); sum = __fadd_rn(sum, r[s][0].w);
+                sum = __fadd_rn(sum, r[s][1].x); sum = __fadd_rn(sum, r[s][1].y); sum = __fadd_rn(sum, r[s][1].z); sum = __fadd_rn(sum, r[s][1].w);
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            sum = __fadd_rn(sum, r[s][0].x); sum = __fadd_rn(sum, r[s][0].y); sum = __fadd_rn(sum, r[s][0].z); sum = __fadd_rn(sum, r[s][0].w);
+            sum = __fadd_rn(sum, r[s][1].x); sum = __fadd_rn(sum, r[s][1].y); sum = __fadd_rn(sum, r[s][1].z); sum = __fadd_rn(sum, r[s][1].w);
+        }
+        t += 16;
+    }
+    for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
+    return sum;
+}
+
+// x = sum_t a[t] * v[t * VS], one multiply and one dependent add per position in ascending order (src/transformer.rs:
+// 533-542).  Blocks of 8 positions alternate between two statically indexed register sets: while the adds of block b
+// run, the products of block b+1 are formed from registers loaded one block earlier and the loads of block b+2 are issued.
+template <int VS>
+LMRS_DEVINL float serial_av_f32(const float* __restrict__ pa, const float* __restrict__ tv, const int T) {
+    float x = 0.0f;
+    int t = 0;
+    if (T >= 16) {
+        float pr[2][8], v[2][8];
+        float4 a[2][2];
+        a[0][0] = *reinterpret_cast<const float4*>(pa); a[0][1] = *reinterpret_cast<const float4*>(pa + 4);
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[0][u] = tv[u * VS];
+        a[1][0] = *reinterpret_cast<const float4*>(pa + 8); a[1][1] = *reinterpret_cast<const float4*>(pa + 12);
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[1][u] = tv[(8 + u) * VS];
+        pr[0][0] = __fmul_rn(a[0][0].x, v[0][0]); pr[0][1] = __fmul_rn(a[0][0].y, v[0][1]); pr[0][2] = __fmul_rn(a[0][0].z, v[0][2]); pr[0][3] = __fmul_rn(a[0][0].w, v[0][3]);
+        pr[0][4] = __fmul_rn(a[0][1].x, v[0][4]); pr[0][5] = __fmul_rn(a[0][1].y, v[0][5]); pr[0][6] = __fmul_rn(a[0][1].z, v[0][6]); pr[0][7] = __fmul_rn(a[0][1].w, v[0][7]);
+        // invariant at the top of a half-trip s: pr[s] = products of block b, (a, v)[s ^ 1] = loaded values of block b+1
+        for (; t + 32 <= T; t += 16) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int o = s ^ 1;
+                const float* pn = pa + t + 8 * s + 16;
+                const float* tn = tv + (size_t)(t + 8 * s + 16) * VS;
+                a[s][0] = *reinterpret_cast<const float4*>(pn); a[s][1] = *reinterpret_cast<const float4*>(pn + 4);
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[s][u] = tn[u * VS];
+                pr[o][0] = __fmul_rn(a[o][0].x, v[o][0]); pr[o][1] = __fmul_rn(a[o][0].y, v[o][1]); pr[o][2] = __fmul_rn(a[o][0].z, v[o][2]); pr[o][3] = __fmul_rn(a[o][0].w, v[o][3]);
+                pr[o][4] = __fmul_rn(a[o][1].x, v[o][4]); pr[o][5] = __fmul_rn(a[o][1].y, v[o][5]); pr[o][6] = __fmul_rn(a[o][1].z, v[o][6]); pr[o][7] = __fmul_rn(a[o][1].w, v[o][7]);
+#pragma unroll
+                for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[s][u]);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) x = __fadd_rn(x, pr[0][u]);
+        x = __fadd_rn(x, __fmul_rn(a[1][0].x, v[1][0])); x = __fadd_rn(x, __fmul_rn(a[1][0].y, v[1][1])); x = __fadd_rn(x, __fmul_rn(a[1][0].z, v[1][2])); x = __fadd_rn(x, __fmul_rn(a[1][0].w, v[1][3]));
+        x = __fadd_rn(x, __fmul_rn(a[1][1].x, v[1][4])); x = __fadd_rn(x, __fmul_rn(a[1][1].y, v[1][5])); x = __fadd_rn(x, __fmul_rn(a[1][1].z, v[1][6])); x = __fadd_rn(x, __fmul_rn(a[1][1].w, v[1][7]));
+        t += 16;
+    }
+    for (; t < T; t++) x = __fadd_rn(x, __fmul_rn(pa[t], tv[(size_t)t * VS]));
+    return x;
+}
+
+// two chains (two query heads sharing the V element) continued over `rows` positions of a staged tile; same rotation
+template <int VS>
+LMRS_DEVINL void serial_av2_f32(float& xa_io, float& xb_io, const float* __restrict__ pa, const float* __restrict__ pb,
+                                const float* __restrict__ tv, const int rows) {
+    float xa = xa_io, xb = xb_io;
+    int t = 0;
+    if (rows >= 16) {
+        float pra[2][8], prb[2][8], v[2][8];
+        float4 a[2][2], b[2][2];
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            a[k][0] = *reinterpret_cast<const float4*>(pa + 8 * k); a[k][1] = *reinterpret_cast<const float4*>(pa + 8 * k + 4);
+            b[k][0] = *reinterpret_cast<const float4*>(pb + 8 * k); b[k][1] = *reinterpret_cast<const float4*>(pb + 8 * k + 4);
+#pragma unroll
+            for (int u = 0; u < 8; u++) v[k][u] = tv[(8 * k + u) * VS];
+        }
+        auto products = [&](const int k) {
+            pra[k][0] = __fmul_rn(a[k][0].x, v[k][0]); pra[k][1] = __fmul_rn(a[k][0].y, v[k][1]); pra[k][2] = __fmul_rn(a[k][0].z, v[k][2]); pra[k][3] = __fmul_rn(a[k][0].w, v[k][3]);
+            pra[k][4] = __fmul_rn(a[k][1].x, v[k][4]); pra[k][5] = __fmul_rn(a[k][1].y, v[k][5]); pra[k][6] = __fmul_rn(a[k][1].z, v[k][6]); pra[k][7] = __fmul_rn(a[k][1].w, v[k][7]);
+            prb[k][0] = __fmul_rn(b[k][0].x, v[k][0]); prb[k][1] = __fmul_rn(b[k][0].y, v[k][1]); prb[k][2] = __fmul_rn(b[k][0].z, v[k][2]); prb[k][3] = __fmul_rn(b[k][0].w, v[k][3]);
+            prb[k][4] = __fmul_rn(b[k][1].x, v[k][4]); prb[k][5] = __fmul_rn(b[k][1].y, v[k][5]); prb[k][6] = __fmul_rn(b[k][1].z, v[k][6]); prb[k][7] = __fmul_rn(b[k][1].w, v[k][7]);
+        };
+        products(0);
+        for (; t + 32 <= rows; t += 16) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int o = s ^ 1;
+                const int nt = t + 8 * s + 16;
+                a[s][0] = *reinterpret_cast<const float4*>(pa + nt); a[s][1] = *reinterpret_cast<const float4*>(pa + nt + 4);
+                b[s][0] = *reinterpret_cast<const float4*>(pb + nt); b[s][1] = *reinterpret_cast<const float4*>(pb + nt + 4);
+#pragma unroll
+                for (int u = 0; u < 8; u++) v[s][u] = tv[(nt + u) * VS];
+                products(o);
+#pragma unroll
+                for (int u = 0; u < 8; u++) { xa = __fadd_rn(xa, pra[s][u]); xb = __fadd_rn(xb, prb[s][u]); }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) { xa = __fadd_rn(xa, pra[0][u]); xb = __fadd_rn(xb, prb[0][u]); }
+        products(1);
+#pragma unroll
+        for (int u = 0; u < 8; u++) { xa = __fadd_rn(xa, pra[1][u]); xb = __fadd_rn(xb, prb[1][u]); }
+        t += 16;
+    }
+    for (; t < rows; t++) {
+        const float vv = tv[t * VS];
+        xa = __fadd_rn(xa, __fmul_rn(pa[t], vv));
+        xb = __fadd_rn(xb, __fmul_rn(pb[t], vv));
+    }
+    xa_io = xa; xb_io = xb;
+}
 
 // Bit-exact restatement of src/transformer.rs:501-544 for one token: every f32 operation happens in the
 // reference's order (serial dot over d, serial softmax sum over t, serial a*v accumulation over t, separate
@@ -227,28 +355,8 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     }
     __syncthreads();
     trace_event(203);
-    if (lane == 0 && warp < nh) {   // the reference's `sum += x[i]` chain: one thread per head, in different warps
-        const float* sc = sc_base + (size_t)warp * sc_stride;
-        float sum = 0.0f;
-        int t = 0;
-        if (T >= 24) {   // two batches of 8 are always in flight ahead of the 8 dependent adds being executed
-            float4 a = *reinterpret_cast<const float4*>(sc), b = *reinterpret_cast<const float4*>(sc + 4);
-            float4 c = *reinterpret_cast<const float4*>(sc + 8), d = *reinterpret_cast<const float4*>(sc + 12);
-            for (; t + 24 <= T; t += 8) {
-                const float4 e = *reinterpret_cast<const float4*>(sc + t + 16), f = *reinterpret_cast<const float4*>(sc + t + 20);
-                sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
-                sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-                a = c; b = d; c = e; d = f;
-            }
-            sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
-            sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-            sum = __fadd_rn(sum, c.x); sum = __fadd_rn(sum, c.y); sum = __fadd_rn(sum, c.z); sum = __fadd_rn(sum, c.w);
-            sum = __fadd_rn(sum, d.x); sum = __fadd_rn(sum, d.y); sum = __fadd_rn(sum, d.z); sum = __fadd_rn(sum, d.w);
-            t += 16;
-        }
-        for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
-        red[96 + warp] = sum;
-    }
+    if (lane == 0 && warp < nh)   // the reference's `sum += x[i]` chain: one thread per head, in different warps
+        red[96 + warp] = serial_sum_f32(sc_base + (size_t)warp * sc_stride, T);
     __syncthreads();
     trace_event(204);
     for (int h = 0; h < nh; h++) {
@@ -284,31 +392,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 const float* pb = sc_base + (size_t)hb * sc_stride + tl * TILE;
                 const float* tv = tb + d;
                 float xa = acca[k], xb = accb[k];
-                int r = 0;
-                if (rows >= 8) {
-                    float4 a4 = *reinterpret_cast<const float4*>(pa), b4 = *reinterpret_cast<const float4*>(pb);
-                    float v0 = tv[0], v1 = tv[HS], v2 = tv[2 * HS], v3 = tv[3 * HS];
-                    float p0 = __fmul_rn(a4.x, v0), p1 = __fmul_rn(a4.y, v1), p2 = __fmul_rn(a4.z, v2), p3 = __fmul_rn(a4.w, v3);
-                    float q0 = __fmul_rn(b4.x, v0), q1 = __fmul_rn(b4.y, v1), q2 = __fmul_rn(b4.z, v2), q3 = __fmul_rn(b4.w, v3);
-                    for (; r + 8 <= rows; r += 4) {
-                        a4 = *reinterpret_cast<const float4*>(pa + r + 4); b4 = *reinterpret_cast<const float4*>(pb + r + 4);
-                        const float* tn = tv + (r + 4) * HS;
-                        v0 = tn[0]; v1 = tn[HS]; v2 = tn[2 * HS]; v3 = tn[3 * HS];
-                        const float n0 = __fmul_rn(a4.x, v0), n1 = __fmul_rn(a4.y, v1), n2 = __fmul_rn(a4.z, v2), n3 = __fmul_rn(a4.w, v3);
-                        const float m0 = __fmul_rn(b4.x, v0), m1 = __fmul_rn(b4.y, v1), m2 = __fmul_rn(b4.z, v2), m3 = __fmul_rn(b4.w, v3);
-                        xa = __fadd_rn(xa, p0); xb = __fadd_rn(xb, q0); xa = __fadd_rn(xa, p1); xb = __fadd_rn(xb, q1);
-                        xa = __fadd_rn(xa, p2); xb = __fadd_rn(xb, q2); xa = __fadd_rn(xa, p3); xb = __fadd_rn(xb, q3);
-                        p0 = n0; p1 = n1; p2 = n2; p3 = n3; q0 = m0; q1 = m1; q2 = m2; q3 = m3;
-                    }
-                    xa = __fadd_rn(xa, p0); xb = __fadd_rn(xb, q0); xa = __fadd_rn(xa, p1); xb = __fadd_rn(xb, q1);
-                    xa = __fadd_rn(xa, p2); xb = __fadd_rn(xb, q2); xa = __fadd_rn(xa, p3); xb = __fadd_rn(xb, q3);
-                    r += 4;
-                }
-                for (; r < rows; r++) {
-                    const float v = tv[r * HS];
-                    xa = __fadd_rn(xa, __fmul_rn(pa[r], v));
-                    xb = __fadd_rn(xb, __fmul_rn(pb[r], v));
-                }
+                serial_av2_f32<HS>(xa, xb, pa, pb, tv, rows);
                 acca[k] = xa; accb[k] = xb;
             }
         }
@@ -339,6 +423,214 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     pdl_launch_dependents();
     pdl_wait();
     attn_decode_body<HS, ATT_THREADS, BIG>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
+}
+
+// ---- cluster decode attention -------------------------------------------------------------------------------------
+// The single-CTA kernel above is bounded by what ONE SM can pull from L2 (~40 B/clk) and by running the scores and
+// the a*v products of a whole KV head on one SM.  Here a thread-block CLUSTER of CL CTAs serves one KV head:
+//   scores : CTA `rank` owns positions [rank*RP, rank*RP+RP) -- 1/CL of the K rows, staged with cp.async (LDGSTS)
+//   exchange: one barrier.cluster, then every CTA gathers its peers' score slices through distributed shared
+//             memory (mapa + ld.shared::cluster.v4) so that all CL CTAs hold the complete score rows
+//   softmax: computed redundantly by every CTA (its latency is the T-long dependent add chain either way)
+//   a*v    : CTA `rank` owns output dims [rank*HS/CL, ...) -- 1/CL of every V row, prefetched during the phases above
+// The arithmetic and its order are those of attn_decode_body (bit-exact with src/transformer.rs:501-544); only the
+// placement of independent chains changes.  Everything a CTA needs lives in shared memory sized by `cap` (the graph
+// variant's position bucket), so contexts beyond the largest bucket use the single-CTA kernel.
+LMRS_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+LMRS_DEVINL uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+LMRS_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+LMRS_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+LMRS_DEVINL float4 ld_dsmem_f4(const float* local_ptr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
+    return v;
+}
+
+constexpr int ATTC_MAX_CL = 8;     // portable cluster size
+template <int HS> __host__ __device__ constexpr int attc_cap_max() { return (131072 / HS) & ~31; }   // 64: 2048, 96: 1344, 128: 1024, 256: 512
+// floats of dynamic shared memory for positions <= cap (cap % 32 == 0) with clusters of cl CTAs
+__host__ __device__ constexpr size_t attc_smem_floats(int hs, int cap, int cl) {
+    return (size_t)ATT_QH * hs + hs + (size_t)ATT_QH * (cap + 4) + (size_t)(cap / cl) * hs + (size_t)cap * (hs / cl) + 128 + 64;
+}
+
+template <int HS, int CL>
+__global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnParams p, const int cap) {
+    constexpr int NTHR = ATT_THREADS, NWARP = NTHR / 32, C4 = HS / 4;
+    extern __shared__ __align__(16) float att_smem_dyn[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int cl = CL;
+    const int rank = (int)cluster_ctarank();
+    const int cid = blockIdx.x / cl;
+    const int kvh = cid / p.chunks, chunk = cid % p.chunks;
+    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;
+    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);
+#ifdef LMRS_DEV_PROBES
+    const int skip = p.dev_skip;
+#else
+    constexpr int skip = 0;
+#endif
+    const int SCS = cap + 4;           // score row stride: +4 floats puts the four heads' float4 reads on distinct banks
+    constexpr int DS = HS / CL, DC = DS / 4;   // output dims (and 16-byte chunks per V row) owned by this CTA
+    static_assert(HS % (4 * CL) == 0, "every CTA of the cluster owns whole 16-byte chunks of a V row");
+    float* q_s = att_smem_dyn;                         // [ATT_QH][HS]
+    float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
+    float* sc_s = k_s + HS;                            // [ATT_QH][SCS]
+    float* kt = sc_s + ATT_QH * SCS;                   // [cap/cl][HS]   this CTA's K rows, 16-byte columns rotated by the row
+    float* vt = kt + (size_t)(cap / cl) * HS;          // [cap][DS]      this CTA's slice of every V row
+    float* red = vt + (size_t)cap * DS;                // [128]
+    uint64_t* exp_tab = reinterpret_cast<uint64_t*>(red + 128);
+
+    // positions < pos were written by earlier steps (complete: a step's first kernel is never launched programmatically),
+    // so their K/V rows are requested BEFORE the dependency wait and land while the QKV GEMV is still finishing
+    const int pos = (int)p.step->pos;
+    const uint32_t mask_base = p.step->mask_base;
+    const int T = pos + 1;
+    const int RP = (((T + cl - 1) / cl) + 3) & ~3;     // positions per CTA (multiple of 4: float4 exchange)
+    const int r0 = min(T, rank * RP), r1 = min(T, r0 + RP), myrows = r1 - r0;
+    {
+        const float* kb = p.kcache + (size_t)kvh * HS;
+        for (int e = tid; e < ((skip & 64) ? 0 : myrows * C4); e += NTHR) {
+            const int r = e / C4, c = e - r * C4, t = r0 + r;
+            if (t != pos) cp_async16(kt + r * HS + ((c + r) % C4) * 4, kb + (size_t)t * p.kv_dim + c * 4);
+        }
+        cp_async_commit();
+        const float* vb = p.vcache + (size_t)kvh * HS + rank * DS;
+        for (int e = tid; e < ((skip & 64) ? 0 : pos * DC); e += NTHR) {
+            const int t = e / DC, c = e - t * DC;
+            cp_async16(vt + t * DS + c * 4, vb + (size_t)t * p.kv_dim + c * 4);
+        }
+        cp_async_commit();
+    }
+    if (warp == NWARP - 1) exp_tab[lane] = kExp2fTab[lane];
+    pdl_launch_dependents();
+    pdl_wait();
+    if (tid < DC) cp_async16(vt + pos * DS + tid * 4, p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + rank * DS + tid * 4);
+    cp_async_commit();
+
+    // RoPE on q and on the new k row (src/transformer.rs:480-492)
+    const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
+    const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
+    for (int i = tid; i < nh * (HS / 2); i += NTHR) {
+        const int h = i / (HS / 2), j = i - h * (HS / 2);
+        const float fcr = cs[j], fci = sn[j];
+        const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
+        q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+    }
+    const bool own_pos = pos >= r0 && pos < r1;        // exactly one CTA of the cluster scores (and publishes) the new row
+    if (own_pos)
+    for (int j = tid; j < HS / 2; j += NTHR) {
+        const float fcr = cs[j], fci = sn[j];
+        const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
+        const float k0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
+        const float k1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
+        const int r = pos - r0, j1 = j + HS / 2;
+        kt[r * HS + (((j >> 2) + r) % C4) * 4 + (j & 3)] = k0;
+        kt[r * HS + (((j1 >> 2) + r) % C4) * 4 + (j1 & 3)] = k1;
+        if (chunk == 0) {
+            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = k0;
+            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j1] = k1;
+        }
+    }
+    cp_async_wait<2>();                                // this thread's K copies have landed
+    __syncthreads();
+
+    // ---- scores of this CTA's positions (:507-528): thread = (row, pair of heads), two dot-product chains ------
+    {
+        const int npair = (nh + 1) / 2;
+        for (int idx = tid; idx < ((skip & 1) ? 0 : myrows * npair); idx += NTHR) {
+            const int hp = idx / myrows, r = idx - hp * myrows, t = r0 + r;
+            const int ha = hp * 2, hb = min(hp * 2 + 1, nh - 1);
+            const float4* qa = reinterpret_cast<const float4*>(q_s + ha * HS);
+            const float4* qb = reinterpret_cast<const float4*>(q_s + hb * HS);
+            const float4* k4 = reinterpret_cast<const float4*>(kt + r * HS);
+            float sa = 0.0f, sb = 0.0f;
+            float4 kr[C4];
+            {
+                int c = r % C4;
+#pragma unroll
+                for (int d4 = 0; d4 < C4; d4++) { kr[d4] = k4[c]; c = (c + 1 == C4) ? 0 : c + 1; }
+            }
+            float4 q0 = qa[0], q1 = qb[0];
+#pragma unroll
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 kv = kr[d4];
+                const float a0 = __fmul_rn(q0.x, kv.x), a1 = __fmul_rn(q0.y, kv.y), a2 = __fmul_rn(q0.z, kv.z), a3 = __fmul_rn(q0.w, kv.w);
+                const float b0 = __fmul_rn(q1.x, kv.x), b1 = __fmul_rn(q1.y, kv.y), b2 = __fmul_rn(q1.z, kv.z), b3 = __fmul_rn(q1.w, kv.w);
+                if (d4 + 1 < C4) { q0 = qa[d4 + 1]; q1 = qb[d4 + 1]; }
+                sa = __fadd_rn(sa, a0); sb = __fadd_rn(sb, b0); sa = __fadd_rn(sa, a1); sb = __fadd_rn(sb, b1);
+                sa = __fadd_rn(sa, a2); sb = __fadd_rn(sb, b2); sa = __fadd_rn(sa, a3); sb = __fadd_rn(sb, b3);
+            }
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const int h = w ? hb : ha;
+                if (w == 1 && hb == ha) break;
+                float score = __fdiv_rn(w ? sb : sa, p.sqrt_hs);
+                if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
+                    score = __fdiv_rn(score, 50.0f);
+                    score = (float)tanh((double)score);
+                    score = __fmul_rn(score, 50.0f);
+                    score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
+                }
+                sc_s[h * SCS + t] = score;
+            }
+        }
+    }
+    cluster_arrive();                                  // my slice is written ...
+    cluster_wait();                                    // ... and so is everybody else's
+    {   // gather the peers' slices (float4 granules; RP % 4 == 0, granules past T carry unused values)
+        const int RP4 = RP / 4, per = nh * RP4;
+        for (int i = tid; i < ((skip & 16) ? 0 : per * cl); i += NTHR) {
+            const int rr = i / per, rem = i - rr * per, h = rem / RP4, j = rem - h * RP4;
+            const int t = rr * RP + 4 * j;
+            if (rr != rank && t < T) {
+                float* at = sc_s + h * SCS + t;
+                *reinterpret_cast<float4*>(at) = ld_dsmem_f4(at, (uint32_t)rr);
+            }
+        }
+    }
+    cluster_arrive();                                  // done reading my peers (matched by the wait before exit)
+    __syncthreads();
+
+    // ---- softmax (src/functional.rs:122-140): max, exp(x-max), serial sum, divide ---------------------------
+    for (int h = 0; h < nh; h++) {
+        const float* sc = sc_s + h * SCS;
+        float mx = sc[0];
+        for (int t = tid; t < T; t += NTHR) mx = fmaxf(mx, sc[t]);
+        mx = warp_max(mx);
+        if (lane == 0) red[h * NWARP + warp] = mx;
+    }
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+        float* sc = sc_s + h * SCS;
+        float mx = red[h * NWARP];
+#pragma unroll
+        for (int w = 1; w < NWARP; w++) mx = fmaxf(mx, red[h * NWARP + w]);
+        for (int t = tid; t < ((skip & 2) ? 0 : T); t += NTHR) sc[t] = expf_glibc_t(__fsub_rn(sc[t], mx), exp_tab);
+    }
+    __syncthreads();
+    if (lane == 0 && warp < nh && !(skip & 4))   // the reference's `sum += x[i]` chain: one thread per head, in different warps
+        red[96 + warp] = serial_sum_f32(sc_s + warp * SCS, T);
+    cp_async_wait<0>();                                // V slice (issued long ago) -- visible after the next barrier
+    __syncthreads();
+    for (int h = 0; h < nh; h++) {
+        float* sc = sc_s + h * SCS;
+        const float sum = red[96 + h];
+        for (int t = tid; t < ((skip & 32) ? 0 : T); t += NTHR) sc[t] = __fdiv_rn(sc[t], sum);
+    }
+    __syncthreads();
+
+    // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542): thread = (head, owned dim), one chain.
+    // Three-stage software pipeline over blocks of 8 positions: the loads of block b+2 are issued, the products of block
+    // b+1 are formed from registers loaded one iteration ago, and the 8 dependent adds of block b run -- the adds never
+    // wait on shared memory, only on each other.
+    if (tid < nh * DS && !(skip & 8)) {
+        const int h = tid / DS, d = tid - h * DS;
+        p.out[(size_t)(h0 + h) * HS + rank * DS + d] = serial_av_f32<DS>(sc_s + h * SCS, vt + d, T);
+    }
+    cluster_wait();                                    // no CTA leaves while a peer may still read its scores
 }
 
 // ---- embedding row gather: the reference dequantizes the whole table at load (src/transformer.rs:243-245,

@@ -94,9 +94,13 @@ struct lmrs_b200 {
     bool use_mega = true;
     int mega_depth = 4;
     size_t mega_smem = 0;
-    cudaGraphExec_t g_decode = nullptr, g_prefill = nullptr;
-    cudaStream_t g_decode_stream = nullptr, g_prefill_stream = nullptr;
-    int n_decode_kernels = 0, n_prefill_kernels = 0;
+    // one CUDA graph per attention variant: 0..2 = cluster attention position buckets, 3 = single-CTA kernel (any length)
+    cudaGraphExec_t g_decode[4] = {nullptr, nullptr, nullptr, nullptr}, g_prefill[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t g_decode_stream[4] = {nullptr, nullptr, nullptr, nullptr}, g_prefill_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+    int n_decode_kernels[4] = {0, 0, 0, 0}, n_prefill_kernels[4] = {0, 0, 0, 0};
+    int att_cl = 0;                 // CTAs per cluster of attn_cluster_kernel (0: disabled)
+    int att_caps[3] = {0, 0, 0};    // positions covered by each bucket
+    int att_variant = 3;            // variant of the step being enqueued
     uint64_t launches = 0;
     int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
@@ -222,6 +226,73 @@ static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_
     }
 }
 static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) { return launch_attn_grid(m, p, n_kv_heads, 1); }
+
+// decode attention on thread-block clusters (attention.cuh: attn_cluster_kernel), one cluster per KV head
+template <int HS, int CL> static cudaError_t launch_attn_cluster_t(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+    constexpr int cl = CL;
+    const size_t smem = attc_smem_floats(HS, cap, cl) * 4;
+    static thread_local size_t set_for = 0;
+    if (set_for < smem) {
+        cudaError_t e = cudaFuncSetAttribute(attn_cluster_kernel<HS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set_for = smem;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_kv_heads * p.chunks * cl));
+    cfg.blockDim = dim3(ATT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = m->stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = m->use_pdl ? 2 : 1;
+    m->launches++;
+    return cudaLaunchKernelEx(&cfg, attn_cluster_kernel<HS, CL>, p, cap);
+}
+template <int HS> static cudaError_t launch_attn_cluster_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+    switch (m->att_cl) {
+        case 8: return launch_attn_cluster_t<HS, 8>(m, p, n_kv_heads, cap);
+        case 4: return launch_attn_cluster_t<HS, 4>(m, p, n_kv_heads, cap);
+        case 2: return launch_attn_cluster_t<HS, 2>(m, p, n_kv_heads, cap);
+        case 1: return launch_attn_cluster_t<HS, 1>(m, p, n_kv_heads, cap);
+        default: return cudaErrorInvalidValue;
+    }
+}
+static cudaError_t launch_attn_cluster(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+    switch (m->args.head_size) {
+        case 64: return launch_attn_cluster_hs<64>(m, p, n_kv_heads, cap);
+        case 96: return launch_attn_cluster_hs<96>(m, p, n_kv_heads, cap);
+        case 128: return launch_attn_cluster_hs<128>(m, p, n_kv_heads, cap);
+        case 256: return launch_attn_cluster_hs<256>(m, p, n_kv_heads, cap);
+        default: return cudaErrorInvalidValue;
+    }
+}
+// position buckets of the cluster kernel: the largest context whose per-CTA state fits ~200 KB of shared memory, and two
+// smaller ones (short contexts then need little shared memory, so the neighbouring GEMVs' CTAs co-reside and prefetch)
+static void setup_attn_cluster(lmrs_b200* m) {
+    const int hs = (int)m->args.head_size;
+    int cl = env_int("LMRS_B200_ATT_CLUSTER", ATTC_MAX_CL);
+    if (cl < 0) cl = 0;
+    if (cl > ATTC_MAX_CL) cl = ATTC_MAX_CL;
+    while (cl > 1 && ((cl & (cl - 1)) != 0 || hs % (4 * cl) != 0)) cl--;
+    m->att_cl = cl;
+    if (cl == 0) return;
+    int cap = 0;
+    while (cap + 32 <= ATT_SC_CAP && attc_smem_floats(hs, cap + 32, cl) * 4 <= (size_t)200 * 1024) cap += 32;
+    if (cap < 64) { m->att_cl = 0; return; }
+    m->att_caps[2] = cap;
+    m->att_caps[1] = ((cap / 2) + 31) & ~31;
+    m->att_caps[0] = ((cap * 5 / 16) + 31) & ~31;
+}
+static int attn_variant_for(const lmrs_b200* m, uint32_t pos) {
+    if (m->att_cl == 0 || (m->use_mega && m->world == 1)) return 3;
+    for (int b = 0; b < 3; b++)
+        if ((int)pos + 1 <= m->att_caps[b]) return b;
+    return 3;
+}
 
 // ---- TMA descriptors (driver entry point resolved at run time: no link-time dependency on libcuda) ---------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -631,17 +702,25 @@ static std::vector<MegaPhase> make_phases(lmrs_b200* m, bool serial_prefill) {
 
 // one kernel per phase (PDL-chained); the only mode with world > 1 (NCCL collectives between kernels)
 static int enqueue_phases_multi(lmrs_b200* m, const std::vector<MegaPhase>& ph) {
+    const bool pdl = m->use_pdl;
+    bool first = true;
     for (const MegaPhase& P : ph) {
+        // the first kernel of a step is an ordinary launch: it starts after EVERYTHING earlier in the stream has
+        // completed, which is what lets later kernels of the step touch older KV rows before their dependency wait
+        m->use_pdl = pdl && !first;
+        first = false;
         if (P.kind == PH_GEMV) {
             CK(launch_gemv(m, m->args.q_type, P.g));
             if (m->world > 1 && P.pad == 1) { if (shard_allreduce(m->shard, P.g.out, m->args.dim, m->stream)) return fail(shard_error()); m->launches++; }
             if (m->world > 1 && P.pad == 2) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
         } else if (P.kind == PH_ATTN) {
-            CK(launch_attn(m, P.a, m->l_kv_heads));
+            if (m->att_variant < 3) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_caps[m->att_variant]));
+            else CK(launch_attn(m, P.a, m->l_kv_heads));
         } else {
             CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r));
         }
     }
+    m->use_pdl = pdl;
     return 0;
 }
 
@@ -780,7 +859,8 @@ static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_b
 static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
     for (size_t i = 0; i < n; i++) {
         if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos, m->seq_prefill++)) return 1;
-        if (run_graph(m, &m->g_prefill, &m->g_prefill_stream, &m->n_prefill_kernels, false)) return 1;
+        const int v = m->att_variant = attn_variant_for(m, pos + (uint32_t)i);
+        if (run_graph(m, &m->g_prefill[v], &m->g_prefill_stream[v], &m->n_prefill_kernels[v], false)) return 1;
     }
     return 0;
 }
@@ -930,6 +1010,7 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     // default: one kernel per phase chained with programmatic dependent launch (measured faster than the persistent
     // megakernel, whose 80 grid barriers cost ~1.3-2 us each); LMRS_B200_MEGA=1 selects the megakernel
     m->use_mega = env_int("LMRS_B200_MEGA", 0) != 0;
+    setup_attn_cluster(m);
     if (setup_mega(m) || upload_phases(m, true)) { lmrs_b200_destroy(m); return 1; }
     *out = m;
     return 0;
@@ -953,8 +1034,10 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
-    if (m->g_decode) cudaGraphExecDestroy(m->g_decode);
-    if (m->g_prefill) cudaGraphExecDestroy(m->g_prefill);
+    for (int v = 0; v < 4; v++) {
+        if (m->g_decode[v]) cudaGraphExecDestroy(m->g_decode[v]);
+        if (m->g_prefill[v]) cudaGraphExecDestroy(m->g_prefill[v]);
+    }
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
     cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->pf_scores); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
@@ -979,7 +1062,8 @@ extern "C" int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t
     if (pos >= m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
     CK(cudaSetDevice(m->device));
     if (push_step(m, token, pos, pos, m->seq_decode++)) return 1;
-    return run_graph(m, &m->g_decode, &m->g_decode_stream, &m->n_decode_kernels, true);
+    const int v = m->att_variant = attn_variant_for(m, pos);
+    return run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true);
 }
 
 extern "C" int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, float** logits_host) {
@@ -999,6 +1083,26 @@ extern "C" int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_la
     int n = 0;
     for (const MegaPhase& P : m->ph_decode)
         if (P.kind == PH_GEMV) { CK(launch_gemv(m, m->args.q_type, P.g)); n++; }
+    if (n_launches) *n_launches = n;
+    return 0;
+}
+
+extern "C" int lmrs_b200_bench_attn_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches) {
+    if (!m) return fail("null handle");
+    if (pos >= m->args.seq_len) return fail("position out of range");
+    CK(cudaSetDevice(m->device));
+    if (push_step(m, 0, pos, pos, m->seq_decode)) return 1;
+    m->att_variant = attn_variant_for(m, pos);
+    const int dev_skip = env_int("LMRS_B200_DEV_SKIP", 0);   // honoured by -DLMRS_DEV_PROBES builds only
+    int n = 0;
+    for (const MegaPhase& P0 : m->ph_decode)
+        if (P0.kind == PH_ATTN) {
+            MegaPhase P = P0;
+            P.a.dev_skip = dev_skip;
+            if (m->att_variant < 3) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_caps[m->att_variant]));
+            else CK(launch_attn(m, P.a, m->l_kv_heads));
+            n++;
+        }
     if (n_launches) *n_launches = n;
     return 0;
 }
@@ -1065,7 +1169,8 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
         m->d_rows = nullptr;
         CK(cudaMalloc(&m->d_rows, n * dim * 4));
         m->rows_cap = n * dim;
-        if (m->g_prefill) { cudaGraphExecDestroy(m->g_prefill); m->g_prefill = nullptr; }
+        for (int v = 0; v < 4; v++)
+            if (m->g_prefill[v]) { cudaGraphExecDestroy(m->g_prefill[v]); m->g_prefill[v] = nullptr; }
         if (upload_phases(m, false)) return 1;   // the phase table embeds the staging buffer's address
     }
     CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));

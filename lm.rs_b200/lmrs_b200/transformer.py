@@ -104,6 +104,12 @@ class Transformer:
         check(lib().lmrs_b200_bench_gemv_pass(self._h, pos, C.byref(n)))
         return n.value
 
+    def bench_attn_pass(self, pos: int) -> int:
+        """enqueue only the attention launches of one decode step at `pos` (measurement aid); returns the launch count"""
+        n = C.c_int()
+        check(lib().lmrs_b200_bench_attn_pass(self._h, pos, C.byref(n)))
+        return n.value
+
     def read_kv(self, layer: int, pos0: int, n: int):
         kvd = self.args.head_size * self.args.n_kv_heads
         k, v = np.zeros((n, kvd), np.float32), np.zeros((n, kvd), np.float32)

@@ -161,6 +161,24 @@ def test_fill_kv_cache_edge_cases(gpu_lib, ref, lf):
         gpu.fill_kv_cache(gpu.get_embeddings(toks), 4090)                           # beyond seq_len
 
 
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-gemma", "tiny-phi"])
+def test_decode_attention_position_buckets(gpu_lib, ref, lf, name):
+    """The cluster attention kernel has one graph variant per position bucket and hands over to the single-CTA kernel
+    beyond the largest one: sweep positions around every hand-over (and the first few, where most CTAs own no rows)."""
+    a = lf.model_args(name, 1, seq_len=4096)
+    buf = lf.write_synthetic(a)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    edges = [444, 572, 636, 700, 892, 1020, 1372, 1788, 2044]
+    positions = list(range(0, 40)) + [p + d for p in edges for d in range(0, 10)]
+    for i, pos in enumerate(positions):
+        t = (7 * i + 3) % a.vocab_size
+        lg, le = gpu.forward(t, pos), cpu.forward(t, pos)
+        if a.model_type != 0:
+            assert np.array_equal(lg, le), f"{name} pos {pos}: max abs {np.abs(lg - le).max()}"
+        assert float(np.abs(lg - le).max()) <= TOL, f"{name} pos {pos}"
+
+
 def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
     """matmul_q4 with sl > 1 is undefined in the reference (src/functional.rs:224): row-wise semantics, no GEMM path."""
     buf = synth("tiny-llama", 2)
@@ -174,7 +192,7 @@ def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
 
 
 @pytest.mark.parametrize("env", [{"LMRS_B200_MEGA": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"}, {"LMRS_B200_GEMM": "0"},
-                                 {"LMRS_B200_ATT_SPLIT": "1"}])
+                                 {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "2"}])
 def test_alternative_execution_modes_stay_bit_exact(env):
     """persistent megakernel / no graph, no PDL / serial prefill / GPU-wide score kernel: same bits as the default path."""
     import subprocess

@@ -56,6 +56,8 @@ if __name__ == "__main__":
             configs.append(dict(LMRS_B200_GEMV_CFG=str(cfg), LMRS_B200_GEMV_CTAS=str(ctas)))
     for ns in (4, 8, 32):
         configs.append(dict(LMRS_B200_NSPLIT=str(ns)))
+    if os.environ.get("QUICK_CONFIGS"):   # e.g. QUICK_CONFIGS='[{}, {"LMRS_B200_ATT_CLUSTER": "0"}]'
+        configs = json.loads(os.environ["QUICK_CONFIGS"])
     for c in configs:
         env = dict(os.environ, **c)
         r = subprocess.run([sys.executable, __file__, "--child", model, q_type, pos0, steps], env=env, capture_output=True, text=True)
