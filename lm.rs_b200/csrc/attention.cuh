@@ -34,6 +34,7 @@ struct AttnParams {
     int batch, q_stride;   // batched prefill: grid.y = token index; pos = step->pos + blockIdx.y, q/out rows strided
     int scores_ready;      // scores already computed by attn_scores_kernel (global scratch [row][head][seq_len])
     float sqrt_hs;         // sqrtf(head_size): scores are DIVIDED by it (src/transformer.rs:516)
+    int trace_slot;        // LMRS_TRACE builds: timeline slot of this launch (-1: none)
     int dev_skip;          // -DLMRS_DEV_PROBES builds only: phases to leave out when timing (results are then wrong)
     const StepParams* step;
 };
@@ -426,68 +427,98 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
 }
 
 // ---- cluster decode attention -------------------------------------------------------------------------------------
-// The single-CTA kernel above is bounded by what ONE SM can pull from L2 (~40 B/clk) and by running the scores and
-// the a*v products of a whole KV head on one SM.  Here a thread-block CLUSTER of CL CTAs serves one KV head:
-//   scores : CTA `rank` owns positions [rank*RP, rank*RP+RP) -- 1/CL of the K rows, staged with cp.async (LDGSTS)
-//   exchange: one barrier.cluster, then every CTA gathers its peers' score slices through distributed shared
-//             memory (mapa + ld.shared::cluster.v4) so that all CL CTAs hold the complete score rows
-//   softmax: computed redundantly by every CTA (its latency is the T-long dependent add chain either way)
-//   a*v    : CTA `rank` owns output dims [rank*HS/CL, ...) -- 1/CL of every V row, prefetched during the phases above
+// The single-CTA kernel above is bounded by what ONE SM can pull from L2 (~40 B/clk) and by running every phase of a
+// whole KV head on one SM.  Here a thread-block CLUSTER of CL CTAs serves one KV head (nh <= 4 query heads):
+//   scores : CTA `rank` owns positions [rank*RP, rank*RP+RP) -- 1/CL of the K rows, staged with cp.async (LDGSTS) --
+//            and PUSHES every score it computes into the shared memory of the CTAs that need it with st.async
+//            (SASS STAS), which also counts the bytes on the receiver's mbarrier: a consumer simply waits until its
+//            complete score rows have arrived -- no cluster-wide barrier (ptxas lowers barrier.cluster.arrive.release
+//            to MEMBAR.ALL.GPU) and no remote reads
+//   softmax: the cluster is split into G head groups of R = CL/G CTAs; a CTA runs max / exp / serial sum / divide
+//            only for its group's nh/G heads (G = nh for Llama-style GQA: one head per CTA pair)
+//   a*v    : CTA (group, part) owns output dims [part*HS/R, ...) of its heads -- that slice of every V row is
+//            prefetched during the phases above
 // The arithmetic and its order are those of attn_decode_body (bit-exact with src/transformer.rs:501-544); only the
 // placement of independent chains changes.  Everything a CTA needs lives in shared memory sized by `cap` (the graph
 // variant's position bucket), so contexts beyond the largest bucket use the single-CTA kernel.
 LMRS_DEVINL uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-LMRS_DEVINL uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
 LMRS_DEVINL void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 LMRS_DEVINL void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
-LMRS_DEVINL float4 ld_dsmem_f4(const float* local_ptr, uint32_t rank) {
-    uint32_t remote;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
-    float4 v;
-    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(remote) : "memory");
-    return v;
+// push one f32 into CTA `rank`'s shared memory (same offsets as mine) and count its 4 bytes on that CTA's mbarrier:
+// st.async (SASS STAS) -- the receiver just waits for its expected byte count, no cluster-wide barrier or fence
+LMRS_DEVINL void st_async_f32(const float* local_ptr, const uint64_t* local_bar, uint32_t rank, float v) {
+    uint32_t ra, rb;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(smem_u32(local_ptr)), "r"(rank));
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rb) : "r"(smem_u32(local_bar)), "r"(rank));
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(ra), "r"(__float_as_uint(v)), "r"(rb)
+                 : "memory");
 }
 
 constexpr int ATTC_MAX_CL = 8;     // portable cluster size
-template <int HS> __host__ __device__ constexpr int attc_cap_max() { return (131072 / HS) & ~31; }   // 64: 2048, 96: 1344, 128: 1024, 256: 512
-// floats of dynamic shared memory for positions <= cap (cap % 32 == 0) with clusters of cl CTAs
-__host__ __device__ constexpr size_t attc_smem_floats(int hs, int cap, int cl) {
-    return (size_t)ATT_QH * hs + hs + (size_t)ATT_QH * (cap + 4) + (size_t)(cap / cl) * hs + (size_t)cap * (hs / cl) + 128 + 64;
+// floats of dynamic shared memory for positions <= cap (cap % 32 == 0), clusters of cl CTAs in g head groups serving nh heads
+__host__ __device__ constexpr size_t attc_smem_floats(int hs, int cap, int cl, int g, int nh) {
+    return (size_t)ATT_QH * hs + (size_t)(nh / g) * (cap + 4) + (size_t)(cap / cl) * hs + (size_t)cap * (hs * g / cl) + 128 + 64 + 4;
 }
 
-template <int HS, int CL>
+// flattened (head, position) loops with two independent evaluations in flight per thread (the f64 exp and the IEEE
+// divide are long dependent instruction sequences: measured 20-25% faster than one at a time, more in flight is slower)
+template <typename F>
+LMRS_DEVINL void rowwise_ilp2(float* sc_s, const int nhl, const int SCS, const int T, const int tid, const int nthr, F f) {
+    const int total = nhl * T;
+    for (int i0 = tid; i0 < total; i0 += 2 * nthr) {
+        const int i1 = i0 + nthr;
+        const int ha = i0 / T, ta = i0 - ha * T;
+        const bool two = i1 < total;
+        const int hb = two ? i1 / T : ha, tb = two ? i1 - hb * T : ta;
+        const float xa = sc_s[ha * SCS + ta], xb = sc_s[hb * SCS + tb];
+        const float ya = f(xa, ha), yb = f(xb, hb);
+        sc_s[ha * SCS + ta] = ya;
+        if (two) sc_s[hb * SCS + tb] = yb;
+    }
+}
+
+template <int HS, int CL, int G>
 __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnParams p, const int cap) {
     constexpr int NTHR = ATT_THREADS, NWARP = NTHR / 32, C4 = HS / 4;
+    constexpr int R = CL / G;                  // CTAs per head group
+    constexpr int DS = HS / R, DC = DS / 4;    // output dims (and 16-byte chunks per V row) owned by this CTA
+    static_assert(CL % G == 0 && HS % (4 * R) == 0, "every CTA owns whole 16-byte chunks of a V row");
     extern __shared__ __align__(16) float att_smem_dyn[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int cl = CL;
     const int rank = (int)cluster_ctarank();
-    const int cid = blockIdx.x / cl;
+    const int cid = blockIdx.x / CL;
     const int kvh = cid / p.chunks, chunk = cid % p.chunks;
     const int h0 = kvh * p.kv_mul + chunk * ATT_QH;
-    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);
+    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);   // the host guarantees nh % G == 0
+    const int nhl = nh / G;                    // heads of my group
+    const int grp = rank / R, part = rank - grp * R;
 #ifdef LMRS_DEV_PROBES
     const int skip = p.dev_skip;
 #else
     constexpr int skip = 0;
 #endif
-    const int SCS = cap + 4;           // score row stride: +4 floats puts the four heads' float4 reads on distinct banks
-    constexpr int DS = HS / CL, DC = DS / 4;   // output dims (and 16-byte chunks per V row) owned by this CTA
-    static_assert(HS % (4 * CL) == 0, "every CTA of the cluster owns whole 16-byte chunks of a V row");
-    float* q_s = att_smem_dyn;                         // [ATT_QH][HS]
-    float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
-    float* sc_s = k_s + HS;                            // [ATT_QH][SCS]
-    float* kt = sc_s + ATT_QH * SCS;                   // [cap/cl][HS]   this CTA's K rows, 16-byte columns rotated by the row
-    float* vt = kt + (size_t)(cap / cl) * HS;          // [cap][DS]      this CTA's slice of every V row
+    const int SCS = cap + 4;                   // score row stride: +4 floats puts the heads' float4 reads on distinct banks
+    float* q_s = att_smem_dyn;                         // [ATT_QH][HS]  all heads of the KV head (scores need them all)
+    float* sc_s = q_s + ATT_QH * HS;                   // [nhl][SCS]    complete score rows of my group's heads
+    float* kt = sc_s + nhl * SCS;                      // [cap/CL][HS]  this CTA's K rows, 16-byte columns rotated by the row
+    float* vt = kt + (size_t)(cap / CL) * HS;          // [cap][DS]     this CTA's slice of every V row
     float* red = vt + (size_t)cap * DS;                // [128]
     uint64_t* exp_tab = reinterpret_cast<uint64_t*>(red + 128);
+    uint64_t* push_bar = exp_tab + 32;                 // counts the score bytes pushed into this CTA
 
     // positions < pos were written by earlier steps (complete: a step's first kernel is never launched programmatically),
     // so their K/V rows are requested BEFORE the dependency wait and land while the QKV GEMV is still finishing
+    const long long c0 = ktrace_c0();
     const int pos = (int)p.step->pos;
     const uint32_t mask_base = p.step->mask_base;
     const int T = pos + 1;
-    const int RP = (((T + cl - 1) / cl) + 3) & ~3;     // positions per CTA (multiple of 4: float4 exchange)
+    if (tid == 0) {                                    // this CTA will receive the complete score rows of its heads
+        mbar_init(push_bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(push_bar, (uint32_t)(nhl * T * 4));
+    }
+    cluster_arrive();                                  // "my shared memory and barrier exist": peers push after their wait
+    const int RP = (((T + CL - 1) / CL) + 3) & ~3;     // positions per CTA
     const int r0 = min(T, rank * RP), r1 = min(T, r0 + RP), myrows = r1 - r0;
     {
         const float* kb = p.kcache + (size_t)kvh * HS;
@@ -496,46 +527,57 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnPar
             if (t != pos) cp_async16(kt + r * HS + ((c + r) % C4) * 4, kb + (size_t)t * p.kv_dim + c * 4);
         }
         cp_async_commit();
-        const float* vb = p.vcache + (size_t)kvh * HS + rank * DS;
+        const float* vb = p.vcache + (size_t)kvh * HS + part * DS;
         for (int e = tid; e < ((skip & 64) ? 0 : pos * DC); e += NTHR) {
             const int t = e / DC, c = e - t * DC;
             cp_async16(vt + t * DS + c * 4, vb + (size_t)t * p.kv_dim + c * 4);
         }
         cp_async_commit();
     }
+    // RoPE factors of this position (constant tables: src/transformer.rs:447-482 evaluated on the host at load time)
+    const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
+    const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
+    float fcr[(ATT_QH * (HS / 2) + NTHR - 1) / NTHR], fci[(ATT_QH * (HS / 2) + NTHR - 1) / NTHR];
+#pragma unroll
+    for (int k = 0; k < (ATT_QH * (HS / 2) + NTHR - 1) / NTHR; k++) {
+        const int j = (tid + k * NTHR) % (HS / 2);
+        fcr[k] = cs[j]; fci[k] = sn[j];
+    }
     if (warp == NWARP - 1) exp_tab[lane] = kExp2fTab[lane];
+    if (blockIdx.x == 0 && tid == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
     pdl_wait();
-    if (tid < DC) cp_async16(vt + pos * DS + tid * 4, p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + rank * DS + tid * 4);
+    if (tid == 0) { ktrace(p.trace_slot, 1); ktrace_c(p.trace_slot, 1, c0); }
+    if (tid < DC) cp_async16(vt + pos * DS + tid * 4, p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + part * DS + tid * 4);
     cp_async_commit();
 
     // RoPE on q and on the new k row (src/transformer.rs:480-492)
-    const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
-    const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
-    for (int i = tid; i < nh * (HS / 2); i += NTHR) {
-        const int h = i / (HS / 2), j = i - h * (HS / 2);
-        const float fcr = cs[j], fci = sn[j];
-        const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
-        q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-        q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
-    }
     const bool own_pos = pos >= r0 && pos < r1;        // exactly one CTA of the cluster scores (and publishes) the new row
-    if (own_pos)
-    for (int j = tid; j < HS / 2; j += NTHR) {
-        const float fcr = cs[j], fci = sn[j];
-        const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
-        const float k0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
-        const float k1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
-        const int r = pos - r0, j1 = j + HS / 2;
-        kt[r * HS + (((j >> 2) + r) % C4) * 4 + (j & 3)] = k0;
-        kt[r * HS + (((j1 >> 2) + r) % C4) * 4 + (j1 & 3)] = k1;
-        if (chunk == 0) {
-            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = k0;
-            p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j1] = k1;
+    float kn0 = 0.0f, kn1 = 0.0f;
+    if (own_pos && tid < HS / 2) { kn0 = __ldcg(p.k_new + (size_t)kvh * HS + tid); kn1 = __ldcg(p.k_new + (size_t)kvh * HS + tid + HS / 2); }
+#pragma unroll
+    for (int k = 0; k < (ATT_QH * (HS / 2) + NTHR - 1) / NTHR; k++) {
+        const int i = tid + k * NTHR;
+        if (i < nh * (HS / 2)) {
+            const int h = i / (HS / 2), j = i - h * (HS / 2);
+            const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
+            q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr[k]), __fmul_rn(v1, fci[k]));
+            q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci[k]), __fmul_rn(v1, fcr[k]));
         }
     }
+    if (own_pos && tid < HS / 2) {                      // (tid < HS/2 <= NTHR/2: these threads hold factor j = tid in slot 0)
+        const int j = tid, j1 = j + HS / 2, r = pos - r0;
+        const float k0 = __fsub_rn(__fmul_rn(kn0, fcr[0]), __fmul_rn(kn1, fci[0]));
+        const float k1 = __fadd_rn(__fmul_rn(kn0, fci[0]), __fmul_rn(kn1, fcr[0]));
+        kt[r * HS + (((j >> 2) + r) % C4) * 4 + (j & 3)] = k0;
+        kt[r * HS + (((j1 >> 2) + r) % C4) * 4 + (j1 & 3)] = k1;
+        kn0 = k0; kn1 = k1;                            // published into the cache at the end of the kernel
+    }
+    if (tid == 0) ktrace_c(p.trace_slot, 2, c0);       // rope done (thread 0)
     cp_async_wait<2>();                                // this thread's K copies have landed
     __syncthreads();
+    cluster_wait();                                    // every peer is running: its shared memory and barrier may be written
+    if (tid == 0) ktrace_c(p.trace_slot, 3, c0);       // K visible
 
     // ---- scores of this CTA's positions (:507-528): thread = (row, pair of heads), two dot-product chains ------
     {
@@ -574,63 +616,67 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnPar
                     score = __fmul_rn(score, 50.0f);
                     score = __fadd_rn(score, (mask_base - (uint32_t)t <= 4096u) ? 0.0f : -2.3819763e38f);
                 }
-                sc_s[h * SCS + t] = score;
-            }
-        }
-    }
-    cluster_arrive();                                  // my slice is written ...
-    cluster_wait();                                    // ... and so is everybody else's
-    {   // gather the peers' slices (float4 granules; RP % 4 == 0, granules past T carry unused values)
-        const int RP4 = RP / 4, per = nh * RP4;
-        for (int i = tid; i < ((skip & 16) ? 0 : per * cl); i += NTHR) {
-            const int rr = i / per, rem = i - rr * per, h = rem / RP4, j = rem - h * RP4;
-            const int t = rr * RP + 4 * j;
-            if (rr != rank && t < T) {
-                float* at = sc_s + h * SCS + t;
-                *reinterpret_cast<float4*>(at) = ld_dsmem_f4(at, (uint32_t)rr);
-            }
-        }
-    }
-    cluster_arrive();                                  // done reading my peers (matched by the wait before exit)
-    __syncthreads();
-
-    // ---- softmax (src/functional.rs:122-140): max, exp(x-max), serial sum, divide ---------------------------
-    for (int h = 0; h < nh; h++) {
-        const float* sc = sc_s + h * SCS;
-        float mx = sc[0];
-        for (int t = tid; t < T; t += NTHR) mx = fmaxf(mx, sc[t]);
-        mx = warp_max(mx);
-        if (lane == 0) red[h * NWARP + warp] = mx;
-    }
-    __syncthreads();
-    for (int h = 0; h < nh; h++) {
-        float* sc = sc_s + h * SCS;
-        float mx = red[h * NWARP];
+                const int g = h / nhl, hl = h - g * nhl;   // deliver to the R CTAs of the head's group (maybe myself)
+                const float* slot = sc_s + hl * SCS + t;
 #pragma unroll
-        for (int w = 1; w < NWARP; w++) mx = fmaxf(mx, red[h * NWARP + w]);
-        for (int t = tid; t < ((skip & 2) ? 0 : T); t += NTHR) sc[t] = expf_glibc_t(__fsub_rn(sc[t], mx), exp_tab);
+                for (int c = 0; c < R; c++) st_async_f32(slot, push_bar, (uint32_t)(g * R + c), score);
+            }
+        }
+    }
+    if (tid == 0) ktrace_c(p.trace_slot, 4, c0);       // own scores done (thread 0)
+    if (!(skip & 1)) mbar_wait(push_bar, 0);           // every score of my heads has landed: complete rows, no remote access below
+    if (tid == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 5, c0); }   // scores complete
+
+    // ---- softmax (src/functional.rs:122-140) of my group's heads: max, exp(x-max), serial sum, divide ---------
+    {
+        float mx[ATT_QH];
+#pragma unroll
+        for (int h = 0; h < ATT_QH; h++) mx[h] = h < nhl ? sc_s[h * SCS] : 0.0f;
+        for (int t = tid; t < T; t += NTHR)
+#pragma unroll
+            for (int h = 0; h < ATT_QH; h++) if (h < nhl) mx[h] = fmaxf(mx[h], sc_s[h * SCS + t]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int h = 0; h < ATT_QH; h++) mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], o));   // independent chains
+        if (lane == 0)
+#pragma unroll
+            for (int h = 0; h < ATT_QH; h++) if (h < nhl) red[h * NWARP + warp] = mx[h];
     }
     __syncthreads();
-    if (lane == 0 && warp < nh && !(skip & 4))   // the reference's `sum += x[i]` chain: one thread per head, in different warps
+    if (tid < ATT_QH) {
+        float m = red[tid * NWARP];
+#pragma unroll
+        for (int w = 1; w < NWARP; w++) m = fmaxf(m, red[tid * NWARP + w]);
+        red[64 + tid] = m;
+    }
+    __syncthreads();
+    if (!(skip & 2))
+        rowwise_ilp2(sc_s, nhl, SCS, T, tid, NTHR, [&](float x, int h) { return expf_glibc_t(__fsub_rn(x, red[64 + h]), exp_tab); });
+    __syncthreads();
+    if (tid == 0) ktrace_c(p.trace_slot, 7, c0);       // max + exp done
+    if (lane == 0 && warp < nhl && !(skip & 4))   // the reference's `sum += x[i]` chain: one thread per head, in different warps
         red[96 + warp] = serial_sum_f32(sc_s + warp * SCS, T);
+    if (tid == 0) ktrace_c(p.trace_slot, 8, c0);       // serial sum done
     cp_async_wait<0>();                                // V slice (issued long ago) -- visible after the next barrier
     __syncthreads();
-    for (int h = 0; h < nh; h++) {
-        float* sc = sc_s + h * SCS;
-        const float sum = red[96 + h];
-        for (int t = tid; t < ((skip & 32) ? 0 : T); t += NTHR) sc[t] = __fdiv_rn(sc[t], sum);
-    }
+    if (tid == 0) { ktrace(p.trace_slot, 4); ktrace_c(p.trace_slot, 9, c0); }   // V visible
+    if (!(skip & 32))
+        rowwise_ilp2(sc_s, nhl, SCS, T, tid, NTHR, [&](float x, int h) { return __fdiv_rn(x, red[96 + h]); });
     __syncthreads();
 
-    // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542): thread = (head, owned dim), one chain.
-    // Three-stage software pipeline over blocks of 8 positions: the loads of block b+2 are issued, the products of block
-    // b+1 are formed from registers loaded one iteration ago, and the 8 dependent adds of block b run -- the adds never
-    // wait on shared memory, only on each other.
-    if (tid < nh * DS && !(skip & 8)) {
-        const int h = tid / DS, d = tid - h * DS;
-        p.out[(size_t)(h0 + h) * HS + rank * DS + d] = serial_av_f32<DS>(sc_s + h * SCS, vt + d, T);
+    if (tid == 0) ktrace_c(p.trace_slot, 10, c0);      // divide done
+    // ---- out[h][d] = sum_t a[h][t] * v[t][d], serial over t (:533-542): thread = (head of my group, owned dim), one
+    // chain each (serial_av_f32: loads two blocks ahead, products one block ahead of the dependent adds)
+    if (tid < nhl * DS && !(skip & 8)) {
+        const int hl = tid / DS, d = tid - hl * DS;
+        p.out[(size_t)(h0 + grp * nhl + hl) * HS + part * DS + d] = serial_av_f32<DS>(sc_s + hl * SCS, vt + d, T);
     }
-    cluster_wait();                                    // no CTA leaves while a peer may still read its scores
+    if (own_pos && chunk == 0 && tid < HS / 2) {       // the rotated K row of this step enters the cache
+        p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + tid] = kn0;
+        p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + tid + HS / 2] = kn1;
+    }
+    if (tid == 0) { ktrace(p.trace_slot, 3); ktrace_c(p.trace_slot, 11, c0); }
 }
 
 // ---- embedding row gather: the reference dequantizes the whole table at load (src/transformer.rs:243-245,

@@ -125,6 +125,37 @@ LMRS_DEVINL void trace_event(int tag) {
     }
 }
 
+// per-launch timeline (LMRS_TRACE builds, LMRS_B200_TIMING=1): slot = launch index within the step, 8 words per slot;
+// word k keeps the LATEST globaltimer value any calling thread reported for event k (k = 0: first CTA's start)
+LMRS_DEVINL void ktrace(const int slot, const int k) {
+#ifdef LMRS_TRACE
+    if (g_trace_buf != nullptr && slot >= 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        atomicMax(&g_trace_buf[(size_t)slot * 8 + k], t);
+    }
+#else
+    (void)slot; (void)k;
+#endif
+}
+
+// cycle-resolution companion: word 1024*8 + slot*16 + k keeps the largest (clock64() - c0) any calling thread reported,
+// c0 being that CTA's own clock at kernel entry (ktrace_c0)
+LMRS_DEVINL long long ktrace_c0() {
+#ifdef LMRS_TRACE
+    return clock64();
+#else
+    return 0;
+#endif
+}
+LMRS_DEVINL void ktrace_c(const int slot, const int k, const long long c0) {
+#ifdef LMRS_TRACE
+    if (g_trace_buf != nullptr && slot >= 0) atomicMax(&g_trace_buf[8192 + (size_t)slot * 16 + k], (unsigned long long)(clock64() - c0));
+#else
+    (void)slot; (void)k; (void)c0;
+#endif
+}
+
 LMRS_DEVINL float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

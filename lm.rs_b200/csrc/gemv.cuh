@@ -60,6 +60,7 @@ struct GemvParams {
     int att_dim, kv_dim;
     const StepParams* step;
     int softcap_rows;
+    int trace_slot;    // LMRS_TRACE builds: timeline slot of this launch (-1: none)
 };
 
 template <int QT> struct QTraits;
@@ -313,6 +314,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
+    const long long cP = ktrace_c0();
     trace_event(100 + p.pro);
     if (p.pro == PRO_NORM) {
         const int nchunks = n / 4;
@@ -395,8 +397,10 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
             if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = v[k];
         }
         __syncthreads();
+        if (lane == 0) ktrace_c(p.trace_slot, 4, cP);   // inputs loaded, residual formed
         trace_event(110);
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
+        if (lane == 0) ktrace_c(p.trace_slot, 5, cP);   // 1/rms known
         trace_event(111);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
@@ -452,6 +456,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
     }
     __syncthreads();
+    if (lane == 0) ktrace_c(p.trace_slot, 6, cP);       // quantized activations in shared memory
     trace_event(119);
 }
 
@@ -619,6 +624,8 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     const uint64_t pol = l2_policy_evict_first();
     if (lane == 0)   // weights never depend on the previous kernel: start streaming before griddepcontrol.wait
         for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
+    const long long c0 = ktrace_c0();
+    if (blockIdx.x == 0 && threadIdx.x == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
     if (p.epi == EPI_GLU_SILU) {   // expf table -> shared memory (last 256 B), by the LAST warp, after the weight prefetch was issued
         uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (p.pro == PRO_NORM ? (size_t)p.n * 4 : 0));
@@ -626,8 +633,10 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
         sm.exp_tab = tab;
     }
     pdl_wait();  // upstream activations are complete and visible from here on
+    if (lane == 0) { ktrace(p.trace_slot, 1); ktrace_c(p.trace_slot, 1, c0); }
 
     gemv_prologue<QT, WARPS>(p, sm);
+    if (lane == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 2, c0); }
 
     const uint32_t pos = (p.epi == EPI_QKV) ? p.step->pos : 0u;
     Consumer<QT> cs;
@@ -639,6 +648,7 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
         __syncwarp();
         if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
     }
+    if (lane == 0) { ktrace(p.trace_slot, 3); ktrace_c(p.trace_slot, 3, c0); }
 }
 
 }  // namespace lmrs

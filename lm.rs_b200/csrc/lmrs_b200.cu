@@ -94,13 +94,14 @@ struct lmrs_b200 {
     bool use_mega = true;
     int mega_depth = 4;
     size_t mega_smem = 0;
-    // one CUDA graph per attention variant: 0..2 = cluster attention position buckets, 3 = single-CTA kernel (any length)
-    cudaGraphExec_t g_decode[4] = {nullptr, nullptr, nullptr, nullptr}, g_prefill[4] = {nullptr, nullptr, nullptr, nullptr};
-    cudaStream_t g_decode_stream[4] = {nullptr, nullptr, nullptr, nullptr}, g_prefill_stream[4] = {nullptr, nullptr, nullptr, nullptr};
-    int n_decode_kernels[4] = {0, 0, 0, 0}, n_prefill_kernels[4] = {0, 0, 0, 0};
+    // one CUDA graph per attention variant: 0..5 = cluster attention variants (setup_attn_cluster), 7 = single-CTA kernel
+    cudaGraphExec_t g_decode[8] = {}, g_prefill[8] = {};
+    cudaStream_t g_decode_stream[8] = {}, g_prefill_stream[8] = {};
+    int n_decode_kernels[8] = {}, n_prefill_kernels[8] = {};
     int att_cl = 0;                 // CTAs per cluster of attn_cluster_kernel (0: disabled)
-    int att_caps[3] = {0, 0, 0};    // positions covered by each bucket
-    int att_variant = 3;            // variant of the step being enqueued
+    struct AttVar { int cap, g; } att_var[6] = {};   // cluster-kernel variants: positions covered, head groups
+    int att_nvar = 0;
+    int att_variant = 7;            // variant of the step being enqueued (7: single-CTA kernel)
     uint64_t launches = 0;
     int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
@@ -228,70 +229,98 @@ static cudaError_t launch_attn_grid(lmrs_b200* m, const AttnParams& p, int n_kv_
 static cudaError_t launch_attn(lmrs_b200* m, const AttnParams& p, int n_kv_heads) { return launch_attn_grid(m, p, n_kv_heads, 1); }
 
 // decode attention on thread-block clusters (attention.cuh: attn_cluster_kernel), one cluster per KV head
-template <int HS, int CL> static cudaError_t launch_attn_cluster_t(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
-    constexpr int cl = CL;
-    const size_t smem = attc_smem_floats(HS, cap, cl) * 4;
-    static thread_local size_t set_for = 0;
-    if (set_for < smem) {
-        cudaError_t e = cudaFuncSetAttribute(attn_cluster_kernel<HS, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        set_for = smem;
+constexpr int ATT_LEGACY = 7;   // variant index of the single-CTA kernel (any context length)
+template <int HS, int CL, int G> static cudaError_t launch_attn_cluster_t(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+    if constexpr (CL % G != 0 || HS % (4 * (CL / G)) != 0) {
+        return cudaErrorInvalidValue;
+    } else {
+        const int nh = std::min<int>(ATT_QH, p.kv_mul);
+        const size_t smem = attc_smem_floats(HS, cap, CL, G, nh) * 4;
+        static thread_local size_t set_for = 0;
+        if (set_for < smem) {
+            cudaError_t e = cudaFuncSetAttribute(attn_cluster_kernel<HS, CL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set_for = smem;
+        }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)(n_kv_heads * p.chunks * CL));
+        cfg.blockDim = dim3(ATT_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = m->stream;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = m->use_pdl ? 2 : 1;
+        m->launches++;
+        return cudaLaunchKernelEx(&cfg, attn_cluster_kernel<HS, CL, G>, p, cap);
     }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3((unsigned)(n_kv_heads * p.chunks * cl));
-    cfg.blockDim = dim3(ATT_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = m->stream;
-    cudaLaunchAttribute attr[2];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[1].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = m->use_pdl ? 2 : 1;
-    m->launches++;
-    return cudaLaunchKernelEx(&cfg, attn_cluster_kernel<HS, CL>, p, cap);
 }
-template <int HS> static cudaError_t launch_attn_cluster_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+template <int HS, int CL> static cudaError_t launch_attn_cluster_g(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap, int g) {
+    switch (g) {
+        case 4: return launch_attn_cluster_t<HS, CL, 4>(m, p, n_kv_heads, cap);
+        case 2: return launch_attn_cluster_t<HS, CL, 2>(m, p, n_kv_heads, cap);
+        case 1: return launch_attn_cluster_t<HS, CL, 1>(m, p, n_kv_heads, cap);
+        default: return cudaErrorInvalidValue;
+    }
+}
+template <int HS> static cudaError_t launch_attn_cluster_hs(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap, int g) {
     switch (m->att_cl) {
-        case 8: return launch_attn_cluster_t<HS, 8>(m, p, n_kv_heads, cap);
-        case 4: return launch_attn_cluster_t<HS, 4>(m, p, n_kv_heads, cap);
-        case 2: return launch_attn_cluster_t<HS, 2>(m, p, n_kv_heads, cap);
-        case 1: return launch_attn_cluster_t<HS, 1>(m, p, n_kv_heads, cap);
+        case 8: return launch_attn_cluster_g<HS, 8>(m, p, n_kv_heads, cap, g);
+        case 4: return launch_attn_cluster_g<HS, 4>(m, p, n_kv_heads, cap, g);
         default: return cudaErrorInvalidValue;
     }
 }
-static cudaError_t launch_attn_cluster(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap) {
+static cudaError_t launch_attn_cluster(lmrs_b200* m, const AttnParams& p, int n_kv_heads, int cap, int g) {
     switch (m->args.head_size) {
-        case 64: return launch_attn_cluster_hs<64>(m, p, n_kv_heads, cap);
-        case 96: return launch_attn_cluster_hs<96>(m, p, n_kv_heads, cap);
-        case 128: return launch_attn_cluster_hs<128>(m, p, n_kv_heads, cap);
-        case 256: return launch_attn_cluster_hs<256>(m, p, n_kv_heads, cap);
+        case 64: return launch_attn_cluster_hs<64>(m, p, n_kv_heads, cap, g);
+        case 96: return launch_attn_cluster_hs<96>(m, p, n_kv_heads, cap, g);
+        case 128: return launch_attn_cluster_hs<128>(m, p, n_kv_heads, cap, g);
+        case 256: return launch_attn_cluster_hs<256>(m, p, n_kv_heads, cap, g);
         default: return cudaErrorInvalidValue;
     }
 }
-// position buckets of the cluster kernel: the largest context whose per-CTA state fits ~200 KB of shared memory, and two
-// smaller ones (short contexts then need little shared memory, so the neighbouring GEMVs' CTAs co-reside and prefetch)
+// Variants of the cluster kernel, one CUDA graph each: position buckets (short contexts need little shared memory, so
+// the neighbouring GEMVs' CTAs co-reside and prefetch) in the head-group layout, then -- when heads are grouped -- one
+// more bucket in the ungrouped layout, whose smaller V slices reach longer contexts within ~200 KB of shared memory.
 static void setup_attn_cluster(lmrs_b200* m) {
     const int hs = (int)m->args.head_size;
+    const int kv_mul = (int)(m->args.n_heads / m->args.n_kv_heads);
+    const int nh = std::min<int>(ATT_QH, kv_mul);
     int cl = env_int("LMRS_B200_ATT_CLUSTER", ATTC_MAX_CL);
-    if (cl < 0) cl = 0;
-    if (cl > ATTC_MAX_CL) cl = ATTC_MAX_CL;
-    while (cl > 1 && ((cl & (cl - 1)) != 0 || hs % (4 * cl) != 0)) cl--;
+    cl = cl >= 8 ? 8 : (cl >= 4 ? 4 : 0);
     m->att_cl = cl;
+    m->att_nvar = 0;
     if (cl == 0) return;
-    int cap = 0;
-    while (cap + 32 <= ATT_SC_CAP && attc_smem_floats(hs, cap + 32, cl) * 4 <= (size_t)200 * 1024) cap += 32;
-    if (cap < 64) { m->att_cl = 0; return; }
-    m->att_caps[2] = cap;
-    m->att_caps[1] = ((cap / 2) + 31) & ~31;
-    m->att_caps[0] = ((cap * 5 / 16) + 31) & ~31;
+    // every chunk of query heads (4, and kv_mul % 4 for the last one) must split evenly into the groups
+    int g = kv_mul % 4 == 0 ? 4 : (kv_mul % 4 == 2 ? 2 : 1);
+    g = std::min(g, env_int("LMRS_B200_ATT_GROUPS", 4));
+    while (g > 1 && (cl % g != 0 || hs % (4 * (cl / g)) != 0)) g /= 2;
+    auto max_cap = [&](int gg) {
+        int cap = 0;
+        while (cap + 32 <= ATT_SC_CAP && attc_smem_floats(hs, cap + 32, cl, gg, nh) * 4 <= (size_t)200 * 1024) cap += 32;
+        return cap;
+    };
+    const int cap_g = max_cap(g);
+    if (cap_g < 64) { m->att_cl = 0; return; }
+    const int num[4] = {5, 8, 12, 16};
+    int prev = 0;
+    for (int b = 0; b < 4; b++) {
+        const int cap = std::min(cap_g, ((cap_g * num[b] / 16) + 31) & ~31);
+        if (cap > prev) { m->att_var[m->att_nvar].cap = cap; m->att_var[m->att_nvar].g = g; m->att_nvar++; prev = cap; }
+    }
+    if (g > 1) {
+        const int cap_1 = max_cap(1);
+        if (cap_1 > prev) { m->att_var[m->att_nvar].cap = cap_1; m->att_var[m->att_nvar].g = 1; m->att_nvar++; }
+    }
 }
 static int attn_variant_for(const lmrs_b200* m, uint32_t pos) {
-    if (m->att_cl == 0 || (m->use_mega && m->world == 1)) return 3;
-    for (int b = 0; b < 3; b++)
-        if ((int)pos + 1 <= m->att_caps[b]) return b;
-    return 3;
+    if (m->att_cl == 0 || (m->use_mega && m->world == 1)) return ATT_LEGACY;
+    for (int b = 0; b < m->att_nvar; b++)
+        if ((int)pos + 1 <= m->att_var[b].cap) return b;
+    return ATT_LEGACY;
 }
 
 // ---- TMA descriptors (driver entry point resolved at run time: no link-time dependency on libcuda) ---------------
@@ -704,7 +733,13 @@ static std::vector<MegaPhase> make_phases(lmrs_b200* m, bool serial_prefill) {
 static int enqueue_phases_multi(lmrs_b200* m, const std::vector<MegaPhase>& ph) {
     const bool pdl = m->use_pdl;
     bool first = true;
-    for (const MegaPhase& P : ph) {
+    int slot = 0;
+    for (const MegaPhase& P0 : ph) {
+        MegaPhase P = P0;
+        P.g.trace_slot = P.a.trace_slot = -1;
+        if (m->d_trace && P.kind == PH_GEMV) P.g.trace_slot = slot;
+        if (m->d_trace && P.kind == PH_ATTN) P.a.trace_slot = slot;
+        slot++;
         // the first kernel of a step is an ordinary launch: it starts after EVERYTHING earlier in the stream has
         // completed, which is what lets later kernels of the step touch older KV rows before their dependency wait
         m->use_pdl = pdl && !first;
@@ -714,7 +749,7 @@ static int enqueue_phases_multi(lmrs_b200* m, const std::vector<MegaPhase>& ph) 
             if (m->world > 1 && P.pad == 1) { if (shard_allreduce(m->shard, P.g.out, m->args.dim, m->stream)) return fail(shard_error()); m->launches++; }
             if (m->world > 1 && P.pad == 2) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
         } else if (P.kind == PH_ATTN) {
-            if (m->att_variant < 3) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_caps[m->att_variant]));
+            if (m->att_variant != ATT_LEGACY) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g));
             else CK(launch_attn(m, P.a, m->l_kv_heads));
         } else {
             CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r));
@@ -1034,7 +1069,7 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     if (!m) return;
     cudaSetDevice(m->device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
-    for (int v = 0; v < 4; v++) {
+    for (int v = 0; v < 8; v++) {
         if (m->g_decode[v]) cudaGraphExecDestroy(m->g_decode[v]);
         if (m->g_prefill[v]) cudaGraphExecDestroy(m->g_prefill[v]);
     }
@@ -1099,7 +1134,7 @@ extern "C" int lmrs_b200_bench_attn_pass(lmrs_b200_t* m, uint32_t pos, int* n_la
         if (P0.kind == PH_ATTN) {
             MegaPhase P = P0;
             P.a.dev_skip = dev_skip;
-            if (m->att_variant < 3) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_caps[m->att_variant]));
+            if (m->att_variant != ATT_LEGACY) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g));
             else CK(launch_attn(m, P.a, m->l_kv_heads));
             n++;
         }
@@ -1169,7 +1204,7 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
         m->d_rows = nullptr;
         CK(cudaMalloc(&m->d_rows, n * dim * 4));
         m->rows_cap = n * dim;
-        for (int v = 0; v < 4; v++)
+        for (int v = 0; v < 8; v++)
             if (m->g_prefill[v]) { cudaGraphExecDestroy(m->g_prefill[v]); m->g_prefill[v] = nullptr; }
         if (upload_phases(m, false)) return 1;   // the phase table embeds the staging buffer's address
     }
@@ -1207,7 +1242,7 @@ extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* o
     else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
     else if (nm == "trace_reset") {   // the device-side counter restarts with every launch
         CK(cudaStreamSynchronize(m->stream));
-        if (m->d_trace) CK(cudaMemset(m->d_trace, 0, 2 * 8192 * 8));
+        if (m->d_trace) CK(cudaMemsetAsync(m->d_trace, 0, 2 * 8192 * 8, m->stream));
         *n = 0;
         return 0;
     }

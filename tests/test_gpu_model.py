@@ -192,9 +192,10 @@ def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
 
 
 @pytest.mark.parametrize("env", [{"LMRS_B200_MEGA": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"}, {"LMRS_B200_GEMM": "0"},
-                                 {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "2"}])
+                                 {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "4"}, {"LMRS_B200_ATT_GROUPS": "1"}])
 def test_alternative_execution_modes_stay_bit_exact(env):
-    """persistent megakernel / no graph, no PDL / serial prefill / GPU-wide score kernel: same bits as the default path."""
+    """persistent megakernel / no graph, no PDL / serial prefill / GPU-wide score kernel / single-CTA attention / clusters
+    of 4 / ungrouped heads: same bits as the default path."""
     import subprocess
     import sys
     code = r'''
