@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, out_dir, name):
+def _worker(rank, world, port, out_dir, name, expect_error=None):
     for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     import torch
@@ -29,6 +29,12 @@ def _worker(rank, world, port, out_dir, name):
         idt = torch.frombuffer(bytearray(lmrs_b200.nccl_unique_id()), dtype=torch.uint8).cuda()
     dist.broadcast(idt, 0)
     buf = lf.write_synthetic(lf.model_args(name, 1))
+    if expect_error:   # shapes whose shards would split a 128-element quantization group are refused at load, on every rank
+        with pytest.raises(lmrs_b200.LmrsError, match=expect_error):
+            lmrs_b200.Transformer.new_sharded(buf, rank, rank, world, bytes(idt.cpu().numpy().tobytes()))
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     m, _ = lmrs_b200.Transformer.new_sharded(buf, rank, rank, world, bytes(idt.cpu().numpy().tobytes()))
     toks = np.random.default_rng(1).integers(0, m.args.vocab_size, 10)
     worst = 0.0
@@ -52,11 +58,19 @@ def _worker(rank, world, port, out_dir, name):
 
 # tiny models only: on deeper random-weight models any f32 re-association flips activation-quantization codes and the
 # deviation is amplified far beyond 1e-3, which is exactly what the partial sums of N > 1 do
-@pytest.mark.parametrize("name", ["tiny-llama", "tiny-phi"])
-def test_two_gpu_sharded_forward_matches_oracle(tmp_path, name):
+def test_two_gpu_sharded_forward_matches_oracle(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), name), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "tiny-llama"), nprocs=2, join=True)
     assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
+
+
+def test_two_gpu_rejects_shapes_that_split_a_quantization_group(tmp_path):
+    """tiny-phi: att_dim 384 / 2 ranks = 192 is not a multiple of the 128-element group of Wo's input -> loud error."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "tiny-phi", "multiple of 128"), nprocs=2, join=True)
