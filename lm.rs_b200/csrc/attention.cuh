@@ -708,19 +708,16 @@ __global__ void embed_kernel(const EmbedParams p) {
 }  // namespace lmrs
 
 // =====================================================================================================================
-// Two-kernel form of the same exact attention (used by the kernel-per-phase decode chain and by batched prefill).
-//
-// The per-position dot products are independent, so `attn_scores_kernel` spreads them over the whole GPU (grid =
-// kv heads x position splits [x token rows]): thread = cached position, four query heads per thread (ILP 4), the K row
-// read straight from L2 into registers -- no tile staging, no block barriers in the loop.  The two serial chains of the
-// reference (softmax sum over t, a*v accumulation over t) then run in `attn_softmax_av_kernel`, one CTA per kv head,
-// thread = (head, dim), V read through L1 (the four heads of a GQA group share every V row) with an 8-deep register
-// prefetch.  Arithmetic and operation order are identical to attn_decode_body: bit-identical results.
+// Score kernel for batched prefill (and LMRS_B200_ATT_SPLIT=1 decode): the per-position dot products are independent, so
+// `attn_scores_kernel` spreads them over the whole GPU (grid = kv heads x position splits [x token rows]): thread =
+// cached position, four query heads per thread (ILP 4), the K row read straight from L2 into registers -- no tile
+// staging, no block barriers in the loop.  The two serial chains of the reference (softmax sum over t, a*v accumulation
+// over t) then run in attn_decode_kernel with `scores_ready`.  Arithmetic and operation order are identical to
+// attn_decode_body: bit-identical results.
 // =====================================================================================================================
 namespace lmrs {
 
 constexpr int ATTS_THREADS = 64;    // scores kernel: positions per CTA pass
-constexpr int ATTV_THREADS = 256;   // softmax/AV kernel
 
 template <int HS>
 __global__ void __launch_bounds__(ATTS_THREADS) attn_scores_kernel(const AttnParams p, const int nsplit) {
@@ -805,108 +802,6 @@ __global__ void __launch_bounds__(ATTS_THREADS) attn_scores_kernel(const AttnPar
                 sc_out[(size_t)h * p.seq_len + t] = score;
             }
         }
-    }
-}
-
-template <int HS>
-__global__ void __launch_bounds__(ATTV_THREADS) attn_softmax_av_kernel(const AttnParams p) {
-    extern __shared__ __align__(16) float av_smem[];      // [ATT_QH][cap] probabilities
-    __shared__ float red[ATT_QH * (ATTV_THREADS / 32) + ATT_QH];
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int NW = ATTV_THREADS / 32;
-    const int kvh = blockIdx.x / p.chunks, chunk = blockIdx.x % p.chunks;
-    const int brow = p.batch ? (int)blockIdx.y : 0;
-    const int h0 = kvh * p.kv_mul + chunk * ATT_QH;
-    const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);
-    pdl_launch_dependents();
-    pdl_wait();
-    const int pos = (int)p.step->pos + brow;
-    const int T = pos + 1;
-    const int cap = p.q_stride ? ATT_SC_CAP : ATT_SC_CAP;
-    const bool in_smem = T <= cap;
-    float* sc_g = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
-    float* sc_base = in_smem ? av_smem : sc_g;
-    const int sc_stride = in_smem ? cap : p.seq_len;
-    float* out_row = p.out + (size_t)brow * p.q_stride;
-
-    // scores -> shared memory, per-head max on the way (src/functional.rs:123-130)
-    for (int h = 0; h < nh; h++) {
-        float mx = -INFINITY;
-        for (int t = tid; t < T; t += ATTV_THREADS) {
-            const float v = __ldcg(sc_g + (size_t)h * p.seq_len + t);
-            if (in_smem) av_smem[h * cap + t] = v;
-            mx = fmaxf(mx, v);
-        }
-        mx = warp_max(mx);
-        if (lane == 0) red[h * NW + warp] = mx;
-    }
-    __syncthreads();
-    for (int h = 0; h < nh; h++) {
-        float* sc = sc_base + (size_t)h * sc_stride;
-        float mx = red[h * NW];
-#pragma unroll
-        for (int w = 1; w < NW; w++) mx = fmaxf(mx, red[h * NW + w]);
-        for (int t = tid; t < T; t += ATTV_THREADS) sc[t] = expf_glibc(__fsub_rn(sc[t], mx));
-    }
-    __syncthreads();
-    if (lane == 0 && warp < nh) {   // the reference's `sum += x[i]` chain: one thread per head, in different warps
-        const float* sc = sc_base + (size_t)warp * sc_stride;
-        float sum = 0.0f;
-        int t = 0;
-        if (T >= 24) {
-            float4 a = *reinterpret_cast<const float4*>(sc), b = *reinterpret_cast<const float4*>(sc + 4);
-            float4 c = *reinterpret_cast<const float4*>(sc + 8), d = *reinterpret_cast<const float4*>(sc + 12);
-            for (; t + 24 <= T; t += 8) {
-                const float4 e = *reinterpret_cast<const float4*>(sc + t + 16), f = *reinterpret_cast<const float4*>(sc + t + 20);
-                sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
-                sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-                a = c; b = d; c = e; d = f;
-            }
-            sum = __fadd_rn(sum, a.x); sum = __fadd_rn(sum, a.y); sum = __fadd_rn(sum, a.z); sum = __fadd_rn(sum, a.w);
-            sum = __fadd_rn(sum, b.x); sum = __fadd_rn(sum, b.y); sum = __fadd_rn(sum, b.z); sum = __fadd_rn(sum, b.w);
-            sum = __fadd_rn(sum, c.x); sum = __fadd_rn(sum, c.y); sum = __fadd_rn(sum, c.z); sum = __fadd_rn(sum, c.w);
-            sum = __fadd_rn(sum, d.x); sum = __fadd_rn(sum, d.y); sum = __fadd_rn(sum, d.z); sum = __fadd_rn(sum, d.w);
-            t += 16;
-        }
-        for (; t < T; t++) sum = __fadd_rn(sum, sc[t]);
-        red[ATT_QH * NW + warp] = sum;
-    }
-    __syncthreads();
-    for (int h = 0; h < nh; h++) {
-        float* sc = sc_base + (size_t)h * sc_stride;
-        const float sum = red[ATT_QH * NW + h];
-        for (int t = tid; t < T; t += ATTV_THREADS) sc[t] = __fdiv_rn(sc[t], sum);
-    }
-    __syncthreads();
-    // out[h][d] = sum_t a[h][t] * v[t][d]: thread = (h, d); V through L1, eight rows prefetched ahead of the chain
-    for (int idx = tid; idx < nh * HS; idx += ATTV_THREADS) {
-        const int h = idx / HS, d = idx - h * HS;
-        const float* a = sc_base + (size_t)h * sc_stride;
-        const float* vcol = p.vcache + (size_t)kvh * HS + d;
-        float x = 0.0f;
-        int t = 0;
-        if (T >= 16) {
-            float v[8], nv[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) v[u] = vcol[(size_t)u * p.kv_dim];
-            for (; t + 16 <= T; t += 8) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) nv[u] = vcol[(size_t)(t + 8 + u) * p.kv_dim];
-                const float4 a4 = *reinterpret_cast<const float4*>(a + t), b4 = *reinterpret_cast<const float4*>(a + t + 4);
-                const float p0 = __fmul_rn(a4.x, v[0]), p1 = __fmul_rn(a4.y, v[1]), p2 = __fmul_rn(a4.z, v[2]), p3 = __fmul_rn(a4.w, v[3]);
-                const float p4 = __fmul_rn(b4.x, v[4]), p5 = __fmul_rn(b4.y, v[5]), p6 = __fmul_rn(b4.z, v[6]), p7 = __fmul_rn(b4.w, v[7]);
-                x = __fadd_rn(x, p0); x = __fadd_rn(x, p1); x = __fadd_rn(x, p2); x = __fadd_rn(x, p3);
-                x = __fadd_rn(x, p4); x = __fadd_rn(x, p5); x = __fadd_rn(x, p6); x = __fadd_rn(x, p7);
-#pragma unroll
-                for (int u = 0; u < 8; u++) v[u] = nv[u];
-            }
-            const float4 a4 = *reinterpret_cast<const float4*>(a + t), b4 = *reinterpret_cast<const float4*>(a + t + 4);
-            x = __fadd_rn(x, __fmul_rn(a4.x, v[0])); x = __fadd_rn(x, __fmul_rn(a4.y, v[1])); x = __fadd_rn(x, __fmul_rn(a4.z, v[2])); x = __fadd_rn(x, __fmul_rn(a4.w, v[3]));
-            x = __fadd_rn(x, __fmul_rn(b4.x, v[4])); x = __fadd_rn(x, __fmul_rn(b4.y, v[5])); x = __fadd_rn(x, __fmul_rn(b4.z, v[6])); x = __fadd_rn(x, __fmul_rn(b4.w, v[7]));
-            t += 8;
-        }
-        for (; t < T; t++) x = __fadd_rn(x, __fmul_rn(a[t], vcol[(size_t)t * p.kv_dim]));
-        out_row[(size_t)(h0 + h) * HS + d] = x;
     }
 }
 

@@ -267,47 +267,6 @@ LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint
 }
 
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
-// NB groups at once (one float4 per lane per group): the NB warp-max reductions and divisions are interleaved by hand
-// so that their shuffle/divide latencies overlap (one group at a time is a ~700-cycle dependent chain)
-template <int QT, int NB>
-LMRS_DEVINL void quantize_groups_to_smem(const float4 (&y)[NB], int g0, int gstride, int G, uint8_t* xq, float* xs, int* xsum, int n) {
-    const int lane = threadIdx.x & 31;
-    float m[NB];
-#pragma unroll
-    for (int u = 0; u < NB; u++) m[u] = fmaxf(fmaxf(fabsf(y[u].x), fabsf(y[u].y)), fmaxf(fabsf(y[u].z), fabsf(y[u].w)));
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int u = 0; u < NB; u++) m[u] = fmaxf(m[u], __shfl_xor_sync(0xffffffffu, m[u], o));
-    }
-    if (QT == 1) {
-        float sc[NB];
-#pragma unroll
-        for (int u = 0; u < NB; u++) sc[u] = __fdiv_rn(m[u], 127.0f);
-        uint32_t pk[NB];
-#pragma unroll
-        for (int u = 0; u < NB; u++) {
-            const int a = round_sat_i8(__fdiv_rn(y[u].x, sc[u])), b = round_sat_i8(__fdiv_rn(y[u].y, sc[u]));
-            const int c = round_sat_i8(__fdiv_rn(y[u].z, sc[u])), d = round_sat_i8(__fdiv_rn(y[u].w, sc[u]));
-            pk[u] = (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
-        }
-#pragma unroll
-        for (int u = 0; u < NB; u++) {
-            const int g = g0 + u * gstride;
-            if (g < G) {
-                reinterpret_cast<uint32_t*>(xq + (size_t)g * GS)[lane] = pk[u];
-                if (lane == 0) xs[g] = sc[u];
-            }
-        }
-    } else {
-#pragma unroll
-        for (int u = 0; u < NB; u++) {
-            const int g = g0 + u * gstride;
-            if (g < G) quantize_group_to_smem<QT>(y[u], g, xq, xs, xsum, n);
-        }
-    }
-}
-
 template <int QT, int WARPS>
 LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
     constexpr int THREADS = WARPS * 32;
