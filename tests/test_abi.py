@@ -47,6 +47,34 @@ def test_no_gpu_means_loud_failure_not_fallback(gpu_lib, lf):
         gpu_lib.functional.softmax(np.zeros(4, np.float32))
 
 
+def test_sass_contains_the_cluster_and_tensor_core_paths():
+    """Decode attention pushes scores between the CTAs of a cluster with st.async (SASS STAS) and stages K/V with
+    cp.async (LDGSTS); the prefill GEMM issues tcgen05 int8 MMAs (UTCIMMA) fed by 2-D TMA loads (UTMALDG)."""
+    import shutil
+    import subprocess
+    so = os.path.join(ROOT, "lm.rs_b200", "lmrs_b200", "liblmrs_b200.so")
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cuobjdump, "-sass", so], capture_output=True, text=True).stdout
+    for mnemonic in ("STAS", "LDGSTS", "UCGABAR_ARV", "UTCIMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_compiled_caller_links_against_the_c_abi_and_fails_loudly_without_a_gpu(lf, tmp_path):
+    """lm.rs_b200/examples/generate.cpp: the chat.rs greedy loop written against include/lmrs_b200.h only."""
+    import subprocess
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "lm.rs_b200"), "-s", "examples"])
+    exe = os.path.join(ROOT, "lm.rs_b200", "examples", "generate")
+    path = tmp_path / "tiny.lmrs"
+    lf.write_synthetic(lf.model_args("tiny-llama", 1)).tofile(path)
+    r = subprocess.run([exe, str(path), "4", "3", "5"], capture_output=True, text=True)
+    if os.path.exists("/dev/nvidia0"):
+        assert r.returncode == 0 and len(r.stdout.split()) == 4, r.stderr
+    else:
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
 def test_oracle_is_not_linked_into_the_product():
     import subprocess
     so = os.path.join(ROOT, "lm.rs_b200", "lmrs_b200", "liblmrs_b200.so")
