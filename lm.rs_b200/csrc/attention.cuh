@@ -1,11 +1,17 @@
-// attention.cuh -- decode-step attention for sm_100a: RoPE + QK^T + soft-cap/window + softmax + .V in ONE
-// kernel over the HBM-resident f32 KV cache.  Replaces src/transformer.rs:443-544 for sl = 1.
+// attention.cuh -- attention for sm_100a: RoPE + QK^T + soft-cap/window + softmax + .V in ONE kernel over the
+// HBM-resident f32 KV cache.  Replaces src/transformer.rs:443-544.
 //
-// Grid n_kv_heads * head_chunks: a CTA serves up to 4 query heads that share one KV head (GQA: K rows are
-// staged once for all of them).  RoPE uses cos/sin tables computed at load time on the HOST with the same libm
-// calls as the reference (powf/cosf/sinf, src/transformer.rs:447-482).  The new K row arrives un-rotated in a
-// staging row written by the QKV GEMV; the CTA rotates it, uses it from shared memory and stores it into the
-// cache.  All f32 arithmetic follows the reference's operation order exactly (see the kernel comment).
+//   attn_cluster_kernel  decode steps: a thread-block cluster per KV head, scores exchanged through distributed shared
+//                        memory (second half of this file)
+//   attn_decode_kernel   one CTA per KV head (x chunks of 4 query heads): batched prefill rows, contexts beyond the
+//                        cluster kernel's shared-memory buckets, and the body the persistent megakernel runs
+//   attn_scores_kernel   q.k products of batched prefill spread over the whole GPU
+//
+// A CTA (or cluster) serves up to 4 query heads that share one KV head (GQA: K rows are staged once for all of them).
+// RoPE uses cos/sin tables computed at load time on the HOST with the same libm calls as the reference (powf/cosf/sinf,
+// src/transformer.rs:447-482).  The new K row arrives un-rotated in a staging row written by the QKV GEMV; the kernel
+// rotates it, uses it from shared memory and stores it into the cache.  All f32 arithmetic follows the reference's
+// operation order exactly (see the kernel comments).
 #pragma once
 #include "common.cuh"
 #include "exact_math.cuh"
