@@ -137,3 +137,20 @@ def test_fill_kv_cache_equals_token_by_token_for_llama(ref, lf):
     ka, va = a.kv_cache(); kb, vb = b.kv_cache()
     assert np.array_equal(ka[:, :6], kb[:, :6]) and np.array_equal(va[:, :6], vb[:, :6])
     assert np.array_equal(a.forward(11, 6), b.forward(11, 6))
+
+
+@pytest.mark.parametrize("name,q_type", [("tiny-llama", 1), ("tiny-phi", 1), ("tiny-gemma", 1), ("tiny-llama", 2)])
+def test_oracle_forward_agrees_with_an_independent_numpy_forward(ref, lf, name, q_type):
+    """tests/numpy_forward.py restates Transformer::forward (src/transformer.rs:316-657) a second time, vectorised and
+    with f64 float reductions (only the integer group dot products are shared with the oracle).  The two must agree far
+    inside the 1e-3 logits tolerance on 2-layer models: a wrong head mapping, RoPE pairing, residual order or Gemma
+    quirk in either restatement shows up as an O(1) difference."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from numpy_forward import NumpyForward
+    buf = lf.write_synthetic(lf.model_args(name, q_type))
+    cpu, nf = ref.RefTransformer(buf), NumpyForward(buf, lf, ref)
+    for pos, tok in enumerate([3, 17, 5, 200, 9, 1]):
+        a, b = cpu.forward(tok, pos).copy(), nf.forward(tok, pos)
+        assert float(np.abs(a - b).max()) <= 1e-4, (name, pos)
