@@ -247,6 +247,77 @@ __global__ void __launch_bounds__(NTHR) k(float* out, long long* cyc, float x0) 
             if ((tid & 31) == 0) xs[c >> 5] = scale;
         }
     } END();
+    BEGIN(); {   // 20: score loop, K row pulled into registers with volatile ld.shared.v4 before the chains start
+        constexpr int HS = 64, C4 = 16; const int myrows = 76, nh = 4, npair = 2;
+        const float* q_s = xf; const float* kt = big;
+        for (int idx = tid; idx < myrows * npair; idx += NTHR) {
+            const int hp = idx / myrows, r = idx - hp * myrows;
+            const int ha = hp * 2, hb = min(hp * 2 + 1, nh - 1);
+            const float4* qa = reinterpret_cast<const float4*>(q_s + ha * HS);
+            const float4* qb = reinterpret_cast<const float4*>(q_s + hb * HS);
+            float4 kr[C4];
+            { int c = r % C4;
+#pragma unroll
+              for (int d4 = 0; d4 < C4; d4++) {
+                  const uint32_t a = smem_u32(kt + r * HS + c * 4);
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(kr[d4].x), "=f"(kr[d4].y), "=f"(kr[d4].z), "=f"(kr[d4].w) : "r"(a));
+                  c = (c + 1 == C4) ? 0 : c + 1;
+              } }
+            float sa = 0.0f, sb = 0.0f;
+#pragma unroll
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 kv = kr[d4], q0 = qa[d4], q1 = qb[d4];
+                sa = __fadd_rn(sa, __fmul_rn(q0.x, kv.x)); sb = __fadd_rn(sb, __fmul_rn(q1.x, kv.x));
+                sa = __fadd_rn(sa, __fmul_rn(q0.y, kv.y)); sb = __fadd_rn(sb, __fmul_rn(q1.y, kv.y));
+                sa = __fadd_rn(sa, __fmul_rn(q0.z, kv.z)); sb = __fadd_rn(sb, __fmul_rn(q1.z, kv.z));
+                sa = __fadd_rn(sa, __fmul_rn(q0.w, kv.w)); sb = __fadd_rn(sb, __fmul_rn(q1.w, kv.w));
+            }
+            sc_s[ha * SCS + r] = __fdiv_rn(sa, 8.0f);
+            sc_s[hb * SCS + r] = __fdiv_rn(sb, 8.0f);
+        }
+    } END();
+    BEGIN(); {   // 21: score loop, thread = (row, head): one chain per thread, all 8 warps busy (304 items)
+        constexpr int HS = 64, C4 = 16; const int myrows = 76, nh = 4;
+        const float* q_s = xf; const float* kt = big;
+        for (int idx = tid; idx < myrows * nh; idx += NTHR) {
+            const int h = idx / myrows, r = idx - h * myrows;
+            const float4* qa = reinterpret_cast<const float4*>(q_s + h * HS);
+            const float4* k4 = reinterpret_cast<const float4*>(kt + r * HS);
+            float sa = 0.0f;
+            int c = r % C4;
+#pragma unroll
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 kv = k4[c], q0 = qa[d4];
+                c = (c + 1 == C4) ? 0 : c + 1;
+                sa = __fadd_rn(sa, __fmul_rn(q0.x, kv.x)); sa = __fadd_rn(sa, __fmul_rn(q0.y, kv.y));
+                sa = __fadd_rn(sa, __fmul_rn(q0.z, kv.z)); sa = __fadd_rn(sa, __fmul_rn(q0.w, kv.w));
+            }
+            sc_s[h * SCS + r] = __fdiv_rn(sa, 8.0f);
+        }
+    } END();
+    BEGIN(); {   // 22: score loop, q in registers (thread = row, head pair fixed per warp half): K via LDS, no q LDS in the loop
+        constexpr int HS = 64, C4 = 16; const int myrows = 76, nh = 4, npair = 2;
+        const float* q_s = xf; const float* kt = big;
+        for (int idx = tid; idx < myrows * npair; idx += NTHR) {
+            const int hp = idx / myrows, r = idx - hp * myrows;
+            const int ha = hp * 2, hb = min(hp * 2 + 1, nh - 1);
+            const float4* k4 = reinterpret_cast<const float4*>(kt + r * HS);
+            float sa = 0.0f, sb = 0.0f;
+            int c = r % C4;
+#pragma unroll 4
+            for (int d4 = 0; d4 < C4; d4++) {
+                const float4 kv = k4[c];
+                const float4 q0 = *reinterpret_cast<const float4*>(q_s + ha * HS + d4 * 4), q1 = *reinterpret_cast<const float4*>(q_s + hb * HS + d4 * 4);
+                c = (c + 1 == C4) ? 0 : c + 1;
+                sa = __fadd_rn(sa, __fmul_rn(q0.x, kv.x)); sb = __fadd_rn(sb, __fmul_rn(q1.x, kv.x));
+                sa = __fadd_rn(sa, __fmul_rn(q0.y, kv.y)); sb = __fadd_rn(sb, __fmul_rn(q1.y, kv.y));
+                sa = __fadd_rn(sa, __fmul_rn(q0.z, kv.z)); sb = __fadd_rn(sb, __fmul_rn(q1.z, kv.z));
+                sa = __fadd_rn(sa, __fmul_rn(q0.w, kv.w)); sb = __fadd_rn(sb, __fmul_rn(q1.w, kv.w));
+            }
+            sc_s[ha * SCS + r] = __fdiv_rn(sa, 8.0f);
+            sc_s[hb * SCS + r] = __fdiv_rn(sb, 8.0f);
+        }
+    } END();
     out[tid] = sink + sc_s[tid] + vt[tid] + big[tid];
 }
 int main() {
@@ -261,9 +332,10 @@ int main() {
     const char* names[] = {"exp loop as shipped", "exp ILP2", "exp ILP4", "exp ILP8", "div as shipped", "div ILP4", "div ILP8",
                            "serial_sum_f32 T=577", "serial_av_f32 T=577", "exact_rnorm n=2048", "rnorm chain v1 n=2048",
                            "exact_rnorm n=4096", "rnorm chain v1 n=4096", "max phase", "quantize 2048", "exact_rnorm_sq n=2048",
-                           "a*v in place + strided sum", "serial_av_f32<32> T=577", "score loop 76 rows x 4 heads", "quantize 2048 rcp+fallback"};
+                           "a*v in place + strided sum", "serial_av_f32<32> T=577", "score loop 76 rows x 4 heads", "quantize 2048 rcp+fallback",
+                           "score loop, volatile K row loads", "score loop, one chain per thread", "score loop, rolled (unroll 4)"};
     printf("%s\n", cudaGetErrorString(cudaGetLastError()));
-    for (int i = 0; i < 20; i++) printf("%-30s %8lld cycles   (first launch, cold: %lld)\n", names[i], h[i], h0[i]);
+    for (int i = 0; i < 23; i++) printf("%-30s %8lld cycles   (first launch, cold: %lld)\n", names[i], h[i], h0[i]);
     printf("  (of test 16: in-place scaling alone %lld cycles)\n", h[30]);
     return 0;
 }
