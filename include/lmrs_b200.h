@@ -104,11 +104,16 @@ int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* out, size_t*
  *   matmul_q8   src/functional.rs:173-214    xout[rows*o];  x {q i8[rows*n], s f32[rows*n/gs]};  w {q i8[o*n], s}
  *   matmul_q4   src/functional.rs:216-250    4-bit x and w, two values per byte, low nibble = even index
  *   quantize    src/quantization.rs:44-67    quantize_q4  src/quantization.rs:69-95
- *   rmsnorm     src/functional.rs:48-78      softmax      src/functional.rs:122-140 */
+ *   rmsnorm     src/functional.rs:48-78      softmax      src/functional.rs:122-140
+ *   matmul (f32) src/functional.rs:142-171   xout[rows*o] = x[rows*n] . w[o*n]^T, 8-lane chunks reduced then added
+ *                                            serially; the n % 8 tail is dropped like the reference does
+ *   matmul_rest src/functional.rs:252-280    any n; its tail reads x[r] of row 0 (reference quirk, kept) */
 int lmrs_b200_matmul_q8(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
                         int rows, int n, int o, int gs);
 int lmrs_b200_matmul_q4(float* xout, const uint8_t* xq, const float* xs, const uint8_t* wq, const float* ws,
                         int rows, int n, int o, int gs);
+int lmrs_b200_matmul_f32(float* xout, const float* x, const float* w, int rows, int n, int o);
+int lmrs_b200_matmul_rest(float* xout, const float* x, const float* w, int rows, int n, int o);
 int lmrs_b200_quantize_q8(int8_t* q, float* s, const float* x, int n, int gs);
 int lmrs_b200_quantize_q4(uint8_t* q, float* s, const float* x, int n, int gs);
 int lmrs_b200_rmsnorm(float* o, const float* x, const float* w, int size, float eps, int add_unit_offset);

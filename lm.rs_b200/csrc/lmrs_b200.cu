@@ -21,6 +21,7 @@
 #include "gemv.cuh"
 #include "mega.cuh"
 #include "misc.cuh"
+#include "f32_ops.cuh"
 #include "shard.h"
 
 using namespace lmrs;

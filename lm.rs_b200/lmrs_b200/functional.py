@@ -31,6 +31,22 @@ def matmul_q4(xout: np.ndarray, x, w, n: int, o: int, gs: int) -> None:
     check(lib().lmrs_b200_matmul_q4(_vp(xout), _vp(xq), _vp(xs), _vp(wq), _vp(ws), rows, n, o, gs))
 
 
+def matmul(xout: np.ndarray, x, w, n: int, o: int) -> None:
+    """src/functional.rs:142-171: unquantized operands, xout[rows*o] = x[rows*n] . w[o*n]^T (the n % 8 tail is dropped)."""
+    rows = xout.size // o
+    x, w = _c(x, np.float32), _c(w, np.float32)
+    assert xout.dtype == np.float32 and xout.flags.c_contiguous
+    check(lib().lmrs_b200_matmul_f32(_vp(xout), _vp(x), _vp(w), rows, n, o))
+
+
+def matmul_rest(xout: np.ndarray, x, w, n: int, o: int) -> None:
+    """src/functional.rs:252-280: any n; the tail elements read row 0 of x (reference quirk, kept)."""
+    rows = xout.size // o
+    x, w = _c(x, np.float32), _c(w, np.float32)
+    assert xout.dtype == np.float32 and xout.flags.c_contiguous
+    check(lib().lmrs_b200_matmul_rest(_vp(xout), _vp(x), _vp(w), rows, n, o))
+
+
 def rmsnorm(o: np.ndarray, x, weight, size: int, eps: float, add_unit_offset: bool) -> None:
     """src/functional.rs:48-78"""
     x, weight = _c(x, np.float32), _c(weight, np.float32)

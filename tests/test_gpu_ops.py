@@ -110,3 +110,23 @@ def test_softmax(gpu_lib, ref, n):
     got = x.copy()
     gpu_lib.functional.softmax(got)
     assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+@pytest.mark.parametrize("rows,n,o", [(1, 64, 8), (3, 588, 12), (2, 1024, 1024), (577, 1024, 64), (5, 7, 4), (4, 37, 20)])
+@pytest.mark.parametrize("rest", [False, True])
+def test_matmul_f32_and_matmul_rest_bit_exact(gpu_lib, ref, rows, n, o, rest):
+    """`matmul` / `matmul_rest` (src/functional.rs:142-171, 252-280; the CLIP patch embedding has n = 588): one thread per
+    output element running the function bodies that tests/test_f32_ops_host.py pins against the oracle on the host."""
+    rng = np.random.default_rng(rows * 1000 + n + o)
+    x = (rng.standard_normal(rows * n) * 3).astype(np.float32)
+    w = (rng.standard_normal(o * n) * 0.7).astype(np.float32)
+    x[::17] = -0.0
+    exp = ref.matmul_f32(x, w, rows, n, o, rest=rest)
+    got = np.full(rows * o, np.nan, np.float32)
+    (gpu_lib.functional.matmul_rest if rest else gpu_lib.functional.matmul)(got, x, w, n, o)
+    assert np.array_equal(got.view(np.uint32), exp.view(np.uint32)), f"mismatches {(got != exp).sum()}"
+
+
+def test_matmul_f32_refuses_an_output_count_the_reference_would_truncate(gpu_lib):
+    with pytest.raises(gpu_lib.LmrsError, match="multiple of 4"):
+        gpu_lib.functional.matmul(np.zeros(6, np.float32), np.zeros(8, np.float32), np.zeros(48, np.float32), 8, 6)
