@@ -34,19 +34,21 @@ tr = acc[-1]
 t0 = tr[5, 0]
 print("launch kind    start   wait_ret  pro_end   end    | prewait  handoff  prologue  main   total-since-prev-end [us]")
 rows = {}
+def plausible(v):   # a stamp that was never written (0) or belongs to another clock domain is left out of the table
+    return abs(int(v) - int(t0)) < 100_000_000
 for i in range(nl):
     kind = names[i % 5] if i < nl - 1 else "cls"
-    s, w, pe, e = (tr[i, 0] - t0) / 1e3, (tr[i, 1] - t0) / 1e3, (tr[i, 2] - t0) / 1e3, (tr[i, 3] - t0) / 1e3
-    prev_end = (tr[i - 1, 3] - t0) / 1e3 if i else 0.0
-    rows.setdefault(kind, []).append((w - s, w - prev_end, pe - w, e - pe, e - prev_end))
-    if i < 5:
+    if i < 5 or not all(plausible(tr[j, k]) for j in (i - 1, i) for k in range(4)):
         continue
+    s, w, pe, e = (tr[i, 0] - t0) / 1e3, (tr[i, 1] - t0) / 1e3, (tr[i, 2] - t0) / 1e3, (tr[i, 3] - t0) / 1e3
+    prev_end = (tr[i - 1, 3] - t0) / 1e3
+    rows.setdefault(kind, []).append((w - s, w - prev_end, pe - w, e - pe, e - prev_end))
     if 10 <= i < 15 or i == nl - 1:
         print(f"{i:4d} {kind:7s} {s:8.2f} {w:8.2f} {pe:8.2f} {e:8.2f} | {w - s:7.2f} {w - prev_end:7.2f} {pe - w:8.2f} {e - pe:7.2f} {e - prev_end:7.2f}")
 print(f"step: {(tr[-1, 3] - t0) / 1e3:.1f} us (first start -> last end)")
 print("kind      n   handoff(prev end -> all waits returned)  prologue   main    per-launch   sum")
 for k, v in rows.items():
-    v = np.array(v[1:] if len(v) > 1 else v)
+    v = np.array(v)
     print(f"{k:7s} {len(v):3d}   {v[:, 1].mean():8.2f}   {v[:, 2].mean():8.2f}  {v[:, 3].mean():8.2f}  {v[:, 4].mean():8.2f}  {v[:, 4].sum():8.1f}")
 
 ghz = 1.965
