@@ -67,6 +67,17 @@ int lmrs_b200_args(const lmrs_b200_t* m, lmrs_args_t* out);
  * sampler does, src/sampler.rs:115-117). */
 int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, float** logits_host);
 
+/* ---- Sampler::sample at temperature 0 == Sampler::sample_argmax      src/sampler.rs:29-41,112-113 ------------
+ * forward + the greedy pick fused on the device: 4 bytes come back instead of vocab_size floats.  The scan order of
+ * the reference (strict `>`: the FIRST maximum wins, NaN never wins, NaN at index 0 answers 0) is reproduced exactly.
+ * The logits of the step stay readable through lmrs_b200_logits_device(). */
+int lmrs_b200_forward_argmax(lmrs_b200_t* m, uint32_t token, uint32_t pos, uint32_t* next_token);
+/* The generate loop of src/bin/chat.rs:188-226 at temperature 0: feeds first_token at pos, then every picked token at
+ * the next position, up to max_new tokens or until `eos` (< 0: none) is produced; the picked token is handed to the next
+ * step on the device (no host round trip per token).  out_tokens[0..*n_out) = the picked ids (eos included). */
+int lmrs_b200_generate_greedy(lmrs_b200_t* m, uint32_t first_token, uint32_t pos, uint32_t max_new, int32_t eos,
+                              uint32_t* out_tokens, uint32_t* n_out);
+
 /* ---- Transformer::get_embeddings(&self, &[u32]) -> Vec<f32>      src/transformer.rs:659-669 ----------- */
 int lmrs_b200_get_embeddings(const lmrs_b200_t* m, const uint32_t* tokens, size_t n_tokens, float* out);
 

@@ -28,13 +28,15 @@ constexpr int ATT_SC_CAP = 2048; // positions whose scores are kept in shared me
 template <bool BIG> __host__ __device__ constexpr int att_nt() { return BIG ? 3 : 4; }
 
 struct AttnParams {
-    const float* q;        // [att_dim] un-rotated
-    const float* k_new;    // [kv_dim]  un-rotated K of this step
+    const void* q;         // [att_dim] un-rotated                      (f32, or LL words when ll: common.cuh)
+    const void* k_new;     // [kv_dim]  un-rotated K of this step        (same)
+    const void* v_new;     // ll only: [kv_dim] V of this step (plain mode: the QKV GEMV wrote row `pos` of the cache itself)
     float* kcache;         // layer base [seq_len][kv_dim]
-    const float* vcache;   // layer base (row `pos` already written by the QKV GEMV)
+    float* vcache;         // layer base
     const float* rope_cos; // [seq_len][hs/2]
     const float* rope_sin;
-    float* out;            // [att_dim]
+    void* out;             // [att_dim]                                  (f32 or LL words)
+    int ll, ll_nowait;     // decode chain: activations in/out are LL words, no griddepcontrol.wait
     float* scores;         // scratch [n_heads][seq_len] used when pos+1 > ATT_SC_CAP
     int kv_dim, kv_mul, chunks, gemma, seq_len;
     int batch, q_stride;   // batched prefill: grid.y = token index; pos = step->pos + blockIdx.y, q/out rows strided
@@ -47,7 +49,7 @@ struct AttnParams {
 
 template <int HS, bool BIG = false> __host__ __device__ constexpr int att_tile_rows() { return (BIG ? 128 : 64) / (HS <= 64 ? 1 : (HS <= 128 ? 2 : 4)); }
 template <int HS, bool BIG = false> __host__ __device__ constexpr size_t attn_smem_bytes() {
-    return (size_t)(ATT_QH * HS + HS + att_nt<BIG>() * att_tile_rows<HS, BIG>() * HS + ATT_QH * ATT_SC_CAP + 128 + 64) * 4;
+    return (size_t)(ATT_QH * HS + 2 * HS + att_nt<BIG>() * att_tile_rows<HS, BIG>() * HS + ATT_QH * ATT_SC_CAP + 128 + 64) * 4;
 }
 
 LMRS_DEVINL void cp_async16(void* dst_smem, const void* src_gmem) {
@@ -202,7 +204,8 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     constexpr int PERT = (CHUNKS + NTHR - 1) / NTHR;
     float* q_s = att_smem;                             // [ATT_QH][HS]
     float* k_s = q_s + ATT_QH * HS;                    // [HS] rotated new K row
-    float* tile = k_s + HS;                            // [ATT_NT][TILE][HS]
+    float* v_s = k_s + HS;                             // [HS] new V row (LL mode: arrives in a staging row, filed into the cache here)
+    float* tile = v_s + HS;                            // [ATT_NT][TILE][HS]
     float* sc_s = tile + ATT_NT * TILE * HS;           // [ATT_QH][ATT_SC_CAP]
     float* red = sc_s + ATT_QH * ATT_SC_CAP;           // [128]: per-head per-warp maxima, then sums at [96..]
     uint64_t* exp_tab = reinterpret_cast<uint64_t*>(red + 128);   // [32] expf table copy
@@ -211,9 +214,15 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     const int brow = p.batch ? (int)blockIdx.y : 0;
     const int pos = (int)p.step->pos + brow;
     const uint32_t mask_base = p.step->mask_base;
-    const float* q_in = p.q + (size_t)brow * p.q_stride;
-    float* out_row = p.out + (size_t)brow * p.q_stride;
+    const bool ll = p.ll != 0;                   // (never with batch)
+    const bool nowait = p.ll_nowait != 0;
+    const uint32_t seq = ll ? p.step->seq : 0u;
+    const float* q_in = reinterpret_cast<const float*>(p.q) + (size_t)brow * p.q_stride;
+    const llword_t* q_ll = reinterpret_cast<const llword_t*>(p.q);
+    float* out_row = reinterpret_cast<float*>(p.out) + (size_t)brow * p.q_stride;
+    llword_t* out_ll = reinterpret_cast<llword_t*>(p.out);
     const bool have_knew = p.k_new != nullptr;   // decode: K row of this step arrives un-rotated in a staging row
+    const bool have_vnew = ll;                   // ... and so does the V row in LL mode
     const int T = pos + 1;
     const bool in_smem = T <= ATT_SC_CAP;
     float* const sc_glob = p.scores + ((size_t)brow * p.kv_mul * (gridDim.x / p.chunks) + h0) * p.seq_len;
@@ -232,7 +241,7 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
                 const int e = tid + i * NTHR;
                 if (e < CHUNKS) {
                     const int r = e / C4, c = e - r * C4, t = tl * TILE + r;
-                    if (t < T && !(rotate && have_knew && t == pos)) {
+                    if (t < T && !((rotate ? have_knew : have_vnew) && t == pos)) {
                         int cc = c;
                         if (rotate) { cc = c + r; cc = cc % C4; }
                         cp_async16(tb + r * HS + cc * 4, base + (size_t)t * p.kv_dim + (size_t)kvh * HS + c * 4);
@@ -250,20 +259,25 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         for (int k = 0; k < ATT_NT - 1; k++) issue_tile(p.kcache, k, true);
     }
 
+    if (ll) ll_canary_wait(q_ll + (size_t)h0 * HS, seq, nowait);   // park the CTA until the QKV kernel starts delivering
     // RoPE on q and on the new k row (rotate-half pairs j, j+HS/2), src/transformer.rs:480-492
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
     const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
     for (int i = tid; i < nh * (HS / 2); i += NTHR) {
         const int h = i / (HS / 2), j = i - h * (HS / 2);
         const float fcr = cs[j], fci = sn[j];
-        const float v0 = __ldcg(q_in + (size_t)(h0 + h) * HS + j), v1 = __ldcg(q_in + (size_t)(h0 + h) * HS + j + HS / 2);
+        const size_t qi = (size_t)(h0 + h) * HS + j;
+        const float v0 = ll ? ll_wait1(q_ll + qi, seq, nowait) : __ldcg(q_in + qi);
+        const float v1 = ll ? ll_wait1(q_ll + qi + HS / 2, seq, nowait) : __ldcg(q_in + qi + HS / 2);
         q_s[h * HS + j] = p.batch ? v0 : __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));       // batched prefill: q rows
         q_s[h * HS + j + HS / 2] = p.batch ? v1 : __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));   // were rotated by rope_rows_kernel
     }
     if (have_knew && !p.scores_ready)
     for (int j = tid; j < HS / 2; j += NTHR) {
         const float fcr = cs[j], fci = sn[j];
-        const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
+        const size_t ki = (size_t)kvh * HS + j;
+        const float v0 = ll ? ll_wait1(reinterpret_cast<const llword_t*>(p.k_new) + ki, seq, nowait) : __ldcg(reinterpret_cast<const float*>(p.k_new) + ki);
+        const float v1 = ll ? ll_wait1(reinterpret_cast<const llword_t*>(p.k_new) + ki + HS / 2, seq, nowait) : __ldcg(reinterpret_cast<const float*>(p.k_new) + ki + HS / 2);
         const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
         const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
         k_s[j] = r0; k_s[j + HS / 2] = r1;
@@ -271,6 +285,12 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
             p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j] = r0;
             p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + j + HS / 2] = r1;
         }
+    }
+    if (have_vnew)
+    for (int d = tid; d < HS; d += NTHR) {
+        const float vv = ll_wait1(reinterpret_cast<const llword_t*>(p.v_new) + (size_t)kvh * HS + d, seq, nowait);
+        v_s[d] = vv;
+        if (write_k) p.vcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + d] = vv;
     }
     __syncthreads();
 
@@ -385,6 +405,10 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
     for (int k = 0; k < MAXCH; k++) { acca[k] = 0.0f; accb[k] = 0.0f; }
     for (int tl = 0; tl < ntiles; tl++) {
         cp_async_wait<ATT_NT - 2>();
+        if (have_vnew && pos / TILE == tl) {           // the new V row comes from shared memory
+            float* tw = tile + (tl % ATT_NT) * TILE * HS + (pos - tl * TILE) * HS;
+            for (int d = tid; d < HS; d += NTHR) tw[d] = v_s[d];
+        }
         __syncthreads();
         issue_tile(p.vcache, tl + ATT_NT - 1, false);
         const float* tb = tile + (tl % ATT_NT) * TILE * HS;
@@ -411,8 +435,13 @@ LMRS_DEVINL void attn_decode_body(const AttnParams& p, float* att_smem, const in
         const int idx = tid + k * NTHR;
         if (idx < npair * HS) {
             const int hp = idx / HS, d = idx - hp * HS;
-            out_row[(size_t)(h0 + hp * 2) * HS + d] = acca[k];
-            if (hp * 2 + 1 < nh) out_row[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
+            if (ll) {
+                ll_store(out_ll + (size_t)(h0 + hp * 2) * HS + d, acca[k], seq);
+                if (hp * 2 + 1 < nh) ll_store(out_ll + (size_t)(h0 + hp * 2 + 1) * HS + d, accb[k], seq);
+            } else {
+                out_row[(size_t)(h0 + hp * 2) * HS + d] = acca[k];
+                if (hp * 2 + 1 < nh) out_row[(size_t)(h0 + hp * 2 + 1) * HS + d] = accb[k];
+            }
         }
     }
     };
@@ -428,7 +457,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_decode_kernel(const AttnPara
     const int h0 = kvh * p.kv_mul + chunk * ATT_QH;                  // first query head of this CTA
     const int nh = min(ATT_QH, p.kv_mul - chunk * ATT_QH);           // query heads served here
     pdl_launch_dependents();
-    pdl_wait();
+    if (!p.ll) pdl_wait();
     attn_decode_body<HS, ATT_THREADS, BIG>(p, att_smem_dyn, kvh, h0, nh, chunk == 0);
 }
 
@@ -552,23 +581,78 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnPar
     if (warp == NWARP - 1) exp_tab[lane] = kExp2fTab[lane];
     if (blockIdx.x == 0 && tid == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
-    pdl_wait();
+    const bool ll = p.ll != 0, nowait = p.ll_nowait != 0;
+    const uint32_t seq = ll ? p.step->seq : 0u;
+    if (!ll) pdl_wait();
+    else ll_canary_wait(reinterpret_cast<const llword_t*>(p.q) + (size_t)h0 * HS, seq, nowait);   // park until the QKV kernel delivers
     if (tid == 0) { ktrace(p.trace_slot, 1); ktrace_c(p.trace_slot, 1, c0); }
-    if (tid < DC) cp_async16(vt + pos * DS + tid * 4, p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + part * DS + tid * 4);
+    // this step's inputs: q (all heads of the KV head), the new K row (only the CTA that scores position `pos`) and the new
+    // V row slice.  LL mode: every load of a thread is issued before any is validated (one L2 round trip on the critical
+    // path, not one per input), and only incomplete words are polled again.
+    constexpr int QK = (ATT_QH * (HS / 2) + NTHR - 1) / NTHR;
+    const bool own_pos = pos >= r0 && pos < r1;        // exactly one CTA of the cluster scores (and publishes) the new row
+    float kn0 = 0.0f, kn1 = 0.0f;
+    float qv0[QK], qv1[QK];
+    if (!ll) {
+        if (tid < DC) cp_async16(vt + pos * DS + tid * 4, p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + part * DS + tid * 4);
+        if (own_pos && tid < HS / 2) {
+            const float* kn = reinterpret_cast<const float*>(p.k_new) + (size_t)kvh * HS + tid;
+            kn0 = __ldcg(kn); kn1 = __ldcg(kn + HS / 2);
+        }
+#pragma unroll
+        for (int k = 0; k < QK; k++) {
+            const int i = tid + k * NTHR;
+            qv0[k] = qv1[k] = 0.0f;
+            if (i < nh * (HS / 2)) {
+                const int h = i / (HS / 2), jj = i - h * (HS / 2);
+                const float* qp = reinterpret_cast<const float*>(p.q) + (size_t)(h0 + h) * HS + jj;
+                qv0[k] = __ldcg(qp); qv1[k] = __ldcg(qp + HS / 2);
+            }
+        }
+    } else {
+        const llword_t* vn = reinterpret_cast<const llword_t*>(p.v_new) + (size_t)kvh * HS + part * DS + tid * 4;
+        const llword_t* kn = reinterpret_cast<const llword_t*>(p.k_new) + (size_t)kvh * HS + tid;
+        const bool want_v = tid < DC, want_k = own_pos && tid < HS / 2;
+        bool got_v = !want_v, got_k = !want_k, got_q[QK];
+        float4 vv = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < QK; k++) { got_q[k] = !(tid + k * NTHR < nh * (HS / 2)); qv0[k] = qv1[k] = 0.0f; }
+        const LLSpin sp = ll_spin_begin();
+        for (;;) {
+            bool all = true;
+            llword_t wk0 = 0, wk1 = 0, wq0[QK], wq1[QK];
+            if (!got_k) { wk0 = ll_ld1(kn); wk1 = ll_ld1(kn + HS / 2); }
+#pragma unroll
+            for (int k = 0; k < QK; k++)
+                if (!got_q[k]) {
+                    const int i = tid + k * NTHR, h = i / (HS / 2), jj = i - h * (HS / 2);
+                    const llword_t* qp = reinterpret_cast<const llword_t*>(p.q) + (size_t)(h0 + h) * HS + jj;
+                    wq0[k] = ll_ld1(qp); wq1[k] = ll_ld1(qp + HS / 2);
+                }
+            if (!got_v) { if (ll_try4(vn, seq, nowait, vv)) got_v = true; else all = false; }
+            if (!got_k) { if (nowait || (ll_ok(wk0, seq) && ll_ok(wk1, seq))) { kn0 = ll_val(wk0); kn1 = ll_val(wk1); got_k = true; } else all = false; }
+#pragma unroll
+            for (int k = 0; k < QK; k++)
+                if (!got_q[k]) { if (nowait || (ll_ok(wq0[k], seq) && ll_ok(wq1[k], seq))) { qv0[k] = ll_val(wq0[k]); qv1[k] = ll_val(wq1[k]); got_q[k] = true; } else all = false; }
+            if (all) break;
+            __nanosleep(20);
+            ll_spin_check(sp);
+        }
+        if (want_v) {
+            *reinterpret_cast<float4*>(vt + pos * DS + tid * 4) = vv;
+            if (grp == 0 && chunk == 0) *reinterpret_cast<float4*>(p.vcache + (size_t)pos * p.kv_dim + (size_t)kvh * HS + part * DS + tid * 4) = vv;   // filed for later steps
+        }
+    }
     cp_async_commit();
 
     // RoPE on q and on the new k row (src/transformer.rs:480-492)
-    const bool own_pos = pos >= r0 && pos < r1;        // exactly one CTA of the cluster scores (and publishes) the new row
-    float kn0 = 0.0f, kn1 = 0.0f;
-    if (own_pos && tid < HS / 2) { kn0 = __ldcg(p.k_new + (size_t)kvh * HS + tid); kn1 = __ldcg(p.k_new + (size_t)kvh * HS + tid + HS / 2); }
 #pragma unroll
-    for (int k = 0; k < (ATT_QH * (HS / 2) + NTHR - 1) / NTHR; k++) {
+    for (int k = 0; k < QK; k++) {
         const int i = tid + k * NTHR;
         if (i < nh * (HS / 2)) {
-            const int h = i / (HS / 2), j = i - h * (HS / 2);
-            const float v0 = __ldcg(p.q + (size_t)(h0 + h) * HS + j), v1 = __ldcg(p.q + (size_t)(h0 + h) * HS + j + HS / 2);
-            q_s[h * HS + j] = __fsub_rn(__fmul_rn(v0, fcr[k]), __fmul_rn(v1, fci[k]));
-            q_s[h * HS + j + HS / 2] = __fadd_rn(__fmul_rn(v0, fci[k]), __fmul_rn(v1, fcr[k]));
+            const int h = i / (HS / 2), jj = i - h * (HS / 2);
+            q_s[h * HS + jj] = __fsub_rn(__fmul_rn(qv0[k], fcr[k]), __fmul_rn(qv1[k], fci[k]));
+            q_s[h * HS + jj + HS / 2] = __fadd_rn(__fmul_rn(qv0[k], fci[k]), __fmul_rn(qv1[k], fcr[k]));
         }
     }
     if (own_pos && tid < HS / 2) {                      // (tid < HS/2 <= NTHR/2: these threads hold factor j = tid in slot 0)
@@ -676,7 +760,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnPar
     // chain each (serial_av_f32: loads two blocks ahead, products one block ahead of the dependent adds)
     if (tid < nhl * DS && !(skip & 8)) {
         const int hl = tid / DS, d = tid - hl * DS;
-        p.out[(size_t)(h0 + grp * nhl + hl) * HS + part * DS + d] = serial_av_f32<DS>(sc_s + hl * SCS, vt + d, T);
+        const float o = serial_av_f32<DS>(sc_s + hl * SCS, vt + d, T);
+        const size_t oi = (size_t)(h0 + grp * nhl + hl) * HS + part * DS + d;
+        if (ll) ll_store(reinterpret_cast<llword_t*>(p.out) + oi, o, seq);
+        else reinterpret_cast<float*>(p.out)[oi] = o;
     }
     if (own_pos && chunk == 0 && tid < HS / 2) {       // the rotated K row of this step enters the cache
         p.kcache[(size_t)pos * p.kv_dim + (size_t)kvh * HS + tid] = kn0;
@@ -745,7 +832,7 @@ __global__ void __launch_bounds__(ATTS_THREADS) attn_scores_kernel(const AttnPar
     const bool have_knew = p.k_new != nullptr;
     const bool owns_pos = have_knew && pos >= t0 && pos < t1;
     if (t0 >= t1) return;
-    const float* q_in = p.q + (size_t)brow * p.q_stride;
+    const float* q_in = reinterpret_cast<const float*>(p.q) + (size_t)brow * p.q_stride;   // (plain mode only)
     const float* cs = p.rope_cos + (size_t)pos * (HS / 2);
     const float* sn = p.rope_sin + (size_t)pos * (HS / 2);
     for (int i = tid; i < ATT_QH * (HS / 2); i += ATTS_THREADS) {
@@ -761,7 +848,8 @@ __global__ void __launch_bounds__(ATTS_THREADS) attn_scores_kernel(const AttnPar
     if (owns_pos) {
         for (int j = tid; j < HS / 2; j += ATTS_THREADS) {
             const float fcr = cs[j], fci = sn[j];
-            const float v0 = __ldcg(p.k_new + (size_t)kvh * HS + j), v1 = __ldcg(p.k_new + (size_t)kvh * HS + j + HS / 2);
+            const float* kn = reinterpret_cast<const float*>(p.k_new);
+            const float v0 = __ldcg(kn + (size_t)kvh * HS + j), v1 = __ldcg(kn + (size_t)kvh * HS + j + HS / 2);
             const float r0 = __fsub_rn(__fmul_rn(v0, fcr), __fmul_rn(v1, fci));
             const float r1 = __fadd_rn(__fmul_rn(v0, fci), __fmul_rn(v1, fcr));
             k_s[j] = r0; k_s[j + HS / 2] = r1;

@@ -68,6 +68,62 @@ LMRS_DEVINL void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t by
 LMRS_DEVINL void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 LMRS_DEVINL void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// ---- "LL" activation exchange between co-resident kernels of one decode step --------------------------------
+// A gpu-scope release/acquire pair costs ~1 us on B200 (each fence ~0.5 us, tools/micro/barrier_probe.cu) and a
+// kernel boundary 2-3 us (griddepcontrol.wait + first loads).  The decode chain therefore hands activations over
+// WITHOUT fences: every element travels as one 64-bit word (f32 bits | step sequence number << 32) written with a
+// single relaxed 8-byte store (single-copy atomic), and a consumer polls the words themselves until they carry the
+// sequence number of the current step.  Every buffer is written once per step (one buffer per phase), steps are
+// separated by an ordinary, fully ordered launch, so there is no reuse hazard.  `nowait` (measurement passes that run
+// only some of the kernels): accept whatever is there.
+typedef unsigned long long llword_t;
+LMRS_DEVINL void ll_store(llword_t* p, float v, uint32_t seq) {
+    asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v)) : "memory");
+}
+LMRS_DEVINL void ll_ld2(const llword_t* p, llword_t& a, llword_t& b) {
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+LMRS_DEVINL llword_t ll_ld1(const llword_t* p) {
+    llword_t a;
+    asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+LMRS_DEVINL bool ll_ok(llword_t w, uint32_t seq) { return (uint32_t)(w >> 32) == seq; }
+LMRS_DEVINL float ll_val(llword_t w) { return __uint_as_float((uint32_t)w); }
+// a spinning consumer gives up loudly (trap -> launch failure) instead of hanging the GPU if its producer never runs
+struct LLSpin { long long t0; };
+LMRS_DEVINL LLSpin ll_spin_begin() { LLSpin s; s.t0 = clock64(); return s; }
+LMRS_DEVINL void ll_spin_check(const LLSpin& s) { if (clock64() - s.t0 > 6000000000LL) __trap(); }
+// Whole-CTA wait for a "canary" word of a vector another kernel is still producing: ONE thread polls (with a short
+// back-off), the others sit in the barrier.  Kernels of later phases are resident long before their inputs exist; if all
+// their threads polled, the L2 would be saturated by polling traffic (measured: the step got SLOWER than with kernel-
+// boundary hand-overs).  After the canary the caller gathers its elements (each still validated individually).
+LMRS_DEVINL void ll_canary_wait(const llword_t* p, uint32_t seq, bool nowait) {
+    if (!nowait && threadIdx.x == 0) {
+        const LLSpin sp = ll_spin_begin();
+        while (!ll_ok(ll_ld1(p), seq)) { __nanosleep(40); ll_spin_check(sp); }
+    }
+    __syncthreads();
+}
+// one element / four consecutive elements (32-byte aligned), spinning until they belong to step `seq`
+LMRS_DEVINL float ll_wait1(const llword_t* p, uint32_t seq, bool nowait) {
+    llword_t w = ll_ld1(p);
+    if (!nowait && !ll_ok(w, seq)) { const LLSpin sp = ll_spin_begin(); do { __nanosleep(20); ll_spin_check(sp); w = ll_ld1(p); } while (!ll_ok(w, seq)); }
+    return ll_val(w);
+}
+LMRS_DEVINL bool ll_try4(const llword_t* p, uint32_t seq, bool nowait, float4& out) {
+    llword_t a, b, c, d;
+    ll_ld2(p, a, b); ll_ld2(p + 2, c, d);
+    if (!nowait && !(ll_ok(a, seq) && ll_ok(b, seq) && ll_ok(c, seq) && ll_ok(d, seq))) return false;
+    out = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+    return true;
+}
+LMRS_DEVINL float4 ll_wait4(const llword_t* p, uint32_t seq, bool nowait) {
+    float4 v;
+    if (!ll_try4(p, seq, nowait, v)) { const LLSpin sp = ll_spin_begin(); do { __nanosleep(20); ll_spin_check(sp); } while (!ll_try4(p, seq, nowait, v)); }
+    return v;
+}
+
 // ---- integer dot products ------------------------------------------------------------------------------
 LMRS_DEVINL int dp4a_ss(int a, int b, int c) { return __dp4a(a, b, c); }
 // a: 4 x s8, b: 4 x u8

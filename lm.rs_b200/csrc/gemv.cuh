@@ -22,6 +22,13 @@
 // follows the reference bit for bit: term = ((ival as f32) * ws) * xs, and terms are added to the row
 // accumulator in ascending group order starting from 0.0 (a 16-step shuffle scan per half-warp), so
 // matmul_q8/matmul_q4 results are BIT-IDENTICAL to the CPU path; -fmad=false keeps mul/add unfused.
+//
+// The kernel is specialised on (prologue, epilogue, exchange mode): a launch only carries the code it runs (round 1
+// shipped ONE kernel with three prologues x five epilogues whose top stall was instruction fetch).  Exchange mode LL:
+// the activations between the kernels of a decode step travel as (value, sequence) words polled by the consumer
+// (common.cuh), the kernels are launched early (programmatic dependent launch) and never call griddepcontrol.wait, so
+// consecutive kernels are co-resident (<= 128 registers, two CTAs per SM) and a hand-over costs a poll, not a kernel
+// boundary.  Plain mode (operator ABI, batched prefill rows, NCCL-sharded steps): f32 arrays + griddepcontrol.wait.
 #pragma once
 #include "common.cuh"
 #include "exact_math.cuh"
@@ -46,17 +53,21 @@ struct GemvParams {
     const uint8_t* wq_a; const float* ws_a;   // matrix A: block-packed (BP16) weights; ws_* unused (scales ride in the blocks)
     const uint8_t* wq_b; const float* ws_b;   // matrix B (GLU: w3), else unused
     int n, o, row_gran;
-    int pro;
-    const float* x_in; const float* delta; const float* w_post; const float* w_norm; float* x_out;
+    int pro, epi;      // host-side dispatch (the kernels are specialised on both)
+    int ll;            // host-side dispatch: activation pointers below are LL word arrays (llword_t) instead of f32 arrays
+    int ll_nowait;     // LL measurement passes: do not wait for the sequence number
+    int warm;          // run the prologue and the first stage once on dummy data BEFORE waiting for the inputs (see the kernel)
+    // activations in/out: `const float*` in plain mode, `const llword_t*` in LL mode (same element indexing)
+    const void* x_in; const void* delta; const float* w_post; const float* w_norm; void* x_out;
+    int x_in_plain;    // LL mode: x_in is nevertheless a plain f32 array (serial prefill: the staged embedding rows)
     int x_in_stride;   // serial prefill: x_in += step->token * x_in_stride (row of the staged embeddings)
     int xout_all;      // batched prefill (one CTA per row): every CTA writes its x_out
     float eps; int unit_offset;
     // PRO_NORM may take x_in from the embedding table instead (decode step, src/transformer.rs:324-332):
     const uint8_t* emb_q; const float* emb_s; int emb_qtype; float emb_mul; int emb_apply_mul;   // emb_q: BP16 table
-    const float* act_in;
+    const void* act_in;
     const uint8_t* raw_q; const float* raw_s;
-    int epi;
-    float* out; float* out_k; float* out_v;
+    void* out; void* out_k; void* out_v;   // EPI_QKV: q / new K row / V (plain: cache base, row `pos`; LL: staging row); EPI_LOGITS: always f32
     int att_dim, kv_dim;
     const StepParams* step;
     int softcap_rows;
@@ -266,16 +277,74 @@ LMRS_DEVINL void issue_stage(const WarpStreams<QT>& w, int s, uint8_t* buf, uint
     if (h1) bulk_g2s_hint(buf + BLK, w.src1 + (size_t)s * BLK, BLK, bar, pol);
 }
 
+// ---- activation access, plain f32 arrays or LL word arrays (common.cuh) ----------------------------------------------
+// gather this thread's float4 chunks c = tid + k*THREADS (< nchunks) of an LL vector: all loads of a round are issued
+// together and only the chunks that were not complete yet are polled again
+template <int NC, int THREADS>
+LMRS_DEVINL void ll_gather(const llword_t* base, int nchunks, uint32_t seq, bool nowait, float4 (&v)[NC]) {
+    const int tid = threadIdx.x;
+    bool done[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) { done[k] = !(tid + k * THREADS < nchunks); v[k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+    const LLSpin sp = ll_spin_begin();
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < NC; k++)
+            if (!done[k]) {
+                if (ll_try4(base + 4 * (size_t)(tid + k * THREADS), seq, nowait, v[k])) done[k] = true;
+                else all = false;
+            }
+        if (all) break;
+        __nanosleep(20);
+        ll_spin_check(sp);
+    }
+}
+// two vectors at once (residual stream + pending contribution): one L2 round trip instead of two on the critical path
+template <int NC, int THREADS>
+LMRS_DEVINL void ll_gather2(const llword_t* base_a, const llword_t* base_b, int nchunks, uint32_t seq, bool nowait, float4 (&va)[NC], float4 (&vb)[NC]) {
+    const int tid = threadIdx.x;
+    bool da[NC], db[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) {
+        da[k] = db[k] = !(tid + k * THREADS < nchunks);
+        va[k] = vb[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const LLSpin sp = ll_spin_begin();
+    for (;;) {
+        bool all = true;
+#pragma unroll
+        for (int k = 0; k < NC; k++) {
+            if (!da[k]) { if (ll_try4(base_a + 4 * (size_t)(tid + k * THREADS), seq, nowait, va[k])) da[k] = true; else all = false; }
+            if (!db[k]) { if (ll_try4(base_b + 4 * (size_t)(tid + k * THREADS), seq, nowait, vb[k])) db[k] = true; else all = false; }
+        }
+        if (all) break;
+        __nanosleep(20);
+        ll_spin_check(sp);
+    }
+}
+LMRS_DEVINL void ll_store4(llword_t* p, float4 v, uint32_t seq) {
+    const unsigned long long hi = (unsigned long long)seq << 32;
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(hi | __float_as_uint(v.x)), "l"(hi | __float_as_uint(v.y)) : "memory");
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p + 2), "l"(hi | __float_as_uint(v.z)), "l"(hi | __float_as_uint(v.w)) : "memory");
+}
+template <bool LL> LMRS_DEVINL void act_store(void* base, size_t i, float v, uint32_t seq) {
+    if constexpr (LL) ll_store(reinterpret_cast<llword_t*>(base) + i, v, seq);
+    else reinterpret_cast<float*>(base)[i] = v;
+}
+
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
-template <int QT, int WARPS>
-LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
+// `real == false`: the warm-up pass -- same instructions on zeros, no waits, no loads of upstream data, no global stores
+template <int QT, int WARPS, int PRO, bool LL>
+LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const uint32_t seq, const bool real) {
     constexpr int THREADS = WARPS * 32;
     constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
+    const bool nowait = LL && p.ll_nowait;
     const long long cP = ktrace_c0();
-    trace_event(100 + p.pro);
-    if (p.pro == PRO_NORM) {
+    trace_event(100 + PRO);
+    if constexpr (PRO == PRO_NORM) {
         const int nchunks = n / 4;
         float4 v[NORM_MAXC], wnv[NORM_MAXC];
         {   // the norm weights do not depend on the previous phase: get them in flight first
@@ -286,6 +355,13 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 wnv[k] = c < nchunks ? wn[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
+        if (!real) {
+#pragma unroll
+            for (int k = 0; k < NORM_MAXC; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else {
+        if constexpr (!LL) pdl_wait();   // plain mode: upstream activations are complete and visible from here on
+        // LL: the pending residual contribution is this kernel's freshest input -- park the CTA on one of its words
+        if (LL && p.delta) ll_canary_wait(reinterpret_cast<const llword_t*>(p.delta), seq, nowait);
         if (p.emb_q) {   // embedding row dequantized on the fly: code as f32 * scale (src/quantization.rs:25-42)
             const uint32_t tok = p.step->token;
 #pragma unroll
@@ -299,8 +375,11 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 }
                 v[k] = t;
             }
+        } else if (LL && !p.x_in_plain) {
+            // gathered together with delta below (one round trip); a vector without a pending contribution is read alone
+            if (!p.delta) ll_gather<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.x_in), nchunks, seq, nowait, v);
         } else {
-            const float4* xin = reinterpret_cast<const float4*>(p.x_in + (size_t)(p.x_in_stride ? p.step->token : 0u) * p.x_in_stride);
+            const float4* xin = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x_in) + (size_t)(p.x_in_stride ? p.step->token : 0u) * p.x_in_stride);
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 const int c = tid + k * THREADS;
@@ -308,13 +387,24 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
             }
         }
         if (p.delta) {
-            const float4* din = reinterpret_cast<const float4*>(p.delta);
             float4 dv[NORM_MAXC], wpv[NORM_MAXC];
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 const int c = tid + k * THREADS;
-                dv[k] = c < nchunks ? __ldcg(&din[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
                 wpv[k] = (p.w_post && c < nchunks) ? reinterpret_cast<const float4*>(p.w_post)[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            if constexpr (LL) {
+                if (!p.emb_q && !p.x_in_plain)
+                    ll_gather2<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.x_in), reinterpret_cast<const llword_t*>(p.delta), nchunks, seq, nowait, v, dv);
+                else
+                    ll_gather<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.delta), nchunks, seq, nowait, dv);
+            } else {
+                const float4* din = reinterpret_cast<const float4*>(p.delta);
+#pragma unroll
+                for (int k = 0; k < NORM_MAXC; k++) {
+                    const int c = tid + k * THREADS;
+                    dv[k] = c < nchunks ? __ldcg(&din[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
             if (p.w_post) {  // Gemma: x += rmsnorm(delta, w_post) with unit offset (src/transformer.rs:564,645)
 #pragma unroll
@@ -342,12 +432,15 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 v[k].z = __fadd_rn(v[k].z, dv[k].z); v[k].w = __fadd_rn(v[k].w, dv[k].w);
             }
         }
-        if (p.x_out && (blockIdx.x == 0 || p.xout_all)) {  // decode: exactly one CTA publishes the updated residual stream
-            float4* xo = reinterpret_cast<float4*>(p.x_out);
+        }   // real
+        if (real && p.x_out && (blockIdx.x == 0 || p.xout_all)) {  // decode: exactly one CTA publishes the updated residual stream
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 const int c = tid + k * THREADS;
-                if (c < nchunks) xo[c] = v[k];
+                if (c < nchunks) {
+                    if constexpr (LL) ll_store4(reinterpret_cast<llword_t*>(p.x_out) + 4 * (size_t)c, v[k], seq);
+                    else reinterpret_cast<float4*>(p.x_out)[c] = v[k];
+                }
             }
         }
 #pragma unroll
@@ -356,10 +449,10 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
             if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = v[k];
         }
         __syncthreads();
-        if (lane == 0) ktrace_c(p.trace_slot, 4, cP);   // inputs loaded, residual formed
+        if (real && lane == 0) ktrace_c(p.trace_slot, 4, cP);   // inputs loaded, residual formed
         trace_event(110);
         const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
-        if (lane == 0) ktrace_c(p.trace_slot, 5, cP);   // 1/rms known
+        if (real && lane == 0) ktrace_c(p.trace_slot, 5, cP);   // 1/rms known
         trace_event(111);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
@@ -379,14 +472,41 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 quantize_group_to_smem<QT>(y, c >> 5, sm.xq, sm.xs, sm.xsum, n);
             }
         }
-    } else if (p.pro == PRO_QUANT) {
-        const float4* ain = reinterpret_cast<const float4*>(p.act_in);
+    } else if constexpr (PRO == PRO_QUANT) {
+        if (real) {
+            if constexpr (LL) ll_canary_wait(reinterpret_cast<const llword_t*>(p.act_in), seq, nowait);
+            else pdl_wait();
+        }
         for (int g0 = warp; g0 < G; g0 += WARPS * 8) {   // 8 groups per warp in flight: one L2 round trip, not eight
             float4 y[8];
+            if (!real) {
 #pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const int g = g0 + u * WARPS;
-                y[u] = g < G ? __ldcg(&ain[g * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int u = 0; u < 8; u++) y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else if constexpr (LL) {
+                const llword_t* ain = reinterpret_cast<const llword_t*>(p.act_in);
+                bool done[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) { done[u] = !(g0 + u * WARPS < G); y[u] = make_float4(0.f, 0.f, 0.f, 0.f); }
+                const LLSpin sp = ll_spin_begin();
+                for (;;) {
+                    bool all = true;
+#pragma unroll
+                    for (int u = 0; u < 8; u++)
+                        if (!done[u]) {
+                            if (ll_try4(ain + 4 * ((size_t)(g0 + u * WARPS) * 32 + lane), seq, nowait, y[u])) done[u] = true;
+                            else all = false;
+                        }
+                    if (__all_sync(0xffffffffu, all)) break;
+                    __nanosleep(20);
+                    ll_spin_check(sp);
+                }
+            } else {
+                const float4* ain = reinterpret_cast<const float4*>(p.act_in);
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    const int g = g0 + u * WARPS;
+                    y[u] = g < G ? __ldcg(&ain[g * 32 + lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
 #pragma unroll
             for (int u = 0; u < 8; u++) {
@@ -394,7 +514,8 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
                 if (g < G) quantize_group_to_smem<QT>(y[u], g, sm.xq, sm.xs, sm.xsum, n);
             }
         }
-    } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
+    } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales (never warmed)
+        pdl_wait();
         if (QT == 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_q);
             for (int i = tid; i < n / 4; i += THREADS) reinterpret_cast<uint32_t*>(sm.xq)[i] = src[i];
@@ -415,7 +536,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm) {
         }
     }
     __syncthreads();
-    if (lane == 0) ktrace_c(p.trace_slot, 6, cP);       // quantized activations in shared memory
+    if (real && lane == 0) ktrace_c(p.trace_slot, 6, cP);       // quantized activations in shared memory
     trace_event(119);
 }
 
@@ -449,23 +570,30 @@ LMRS_DEVINL float glu_act(int epi, float val, const uint64_t* exp_tab = kExp2fTa
     }
     return __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc_t(-val, exp_tab))));   // SiLU (:617), exp = glibc expf
 }
-LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos) {
-    if (p.epi == EPI_QKV) {
-        if (row < p.att_dim) p.out[row] = v;
-        else if (row < p.att_dim + p.kv_dim) p.out_k[row - p.att_dim] = v;
-        else p.out_v[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = v;
-    } else if (p.epi == EPI_LOGITS && row < p.softcap_rows) {
-        float t = __fdiv_rn(v, 30.0f);   // src/transformer.rs:375-381
-        t = (float)tanh((double)t);
-        p.out[row] = __fmul_rn(t, 30.0f);
+template <int EPI, bool LL>
+LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos, uint32_t seq, const bool dry) {
+    if (dry) return;
+    if constexpr (EPI == EPI_QKV) {
+        if (row < p.att_dim) act_store<LL>(p.out, row, v, seq);
+        else if (row < p.att_dim + p.kv_dim) act_store<LL>(p.out_k, row - p.att_dim, v, seq);
+        else if constexpr (LL) act_store<true>(p.out_v, row - p.att_dim - p.kv_dim, v, seq);   // staging row: the attention kernel files it
+        else reinterpret_cast<float*>(p.out_v)[(size_t)pos * p.kv_dim + (row - p.att_dim - p.kv_dim)] = v;
+    } else if constexpr (EPI == EPI_LOGITS) {
+        if (row < p.softcap_rows) {
+            float t = __fdiv_rn(v, 30.0f);   // src/transformer.rs:375-381
+            t = (float)tanh((double)t);
+            v = __fmul_rn(t, 30.0f);
+        }
+        reinterpret_cast<float*>(p.out)[row] = v;   // logits leave the step: plain f32
     } else {
-        p.out[row] = v;
+        act_store<LL>(p.out, row, v, seq);
     }
 }
-template <int QT>
+template <int QT, int EPI, bool LL>
 LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, int s, const uint8_t* buf, const GemvSmem& sm,
-                               Consumer<QT>& c, uint32_t pos) {
+                               Consumer<QT>& c, uint32_t pos, uint32_t seq, const bool dry) {
     constexpr int QB = QTraits<QT>::QB;
+    constexpr bool GLU = (EPI == EPI_GLU_SILU || EPI == EPI_GLU_GELU);
     const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
     const int n = p.n, G = w.G;
     const RowRange rr = half ? w.r1 : w.r0;
@@ -522,17 +650,20 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
         for (int j = 0; j < SG; j++) a = __fadd_rn(a, __shfl_sync(0xffffffffu, t, j, 16));
         c.acc = a;
         const bool row_done = (c.g_base + SG == G);
-        if (w.glu) {
+        if constexpr (GLU) {
             const float up = __shfl_sync(0xffffffffu, a, 16);
-            if (row_done && lane == 0 && valid) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, a, sm.exp_tab), up);
+            if (row_done && lane == 0 && valid) {
+                const float hv = __fmul_rn(glu_act(EPI, a, sm.exp_tab), up);
+                if (!dry) act_store<LL>(p.out, rr.row0 + row_l, hv, seq);
+            }
         } else if (row_done && l16 == 0 && valid) {
-            store_row(p, rr.row0 + row_l, a, pos);
+            store_row<EPI, LL>(p, rr.row0 + row_l, a, pos, seq, dry);
         }
         c.g_base += SG;
         if (c.g_base == G) { c.g_base = 0; c.row_l++; }
         return;
     }
-    // generic path (G not a multiple of 16: tiny test models): rows may start/end anywhere inside the stage
+    // generic path (G not a multiple of 16: tiny test models, Gemma-2-9B's dim 3584): rows may start/end anywhere inside the stage
     const bool is_last = valid && (g == G - 1);
     const uint32_t first_mask = __ballot_sync(0xffffffffu, valid && g == 0) >> (half * 16);
     float mine = 0.0f, acc = c.acc;
@@ -543,11 +674,14 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
         if (j == l16) mine = acc;
     }
     c.acc = acc;
-    if (w.glu) {
+    if constexpr (GLU) {
         const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
-        if (is_last && half == 0) p.out[rr.row0 + row_l] = __fmul_rn(glu_act(p.epi, mine, sm.exp_tab), up);
+        if (is_last && half == 0) {
+            const float hv = __fmul_rn(glu_act(EPI, mine, sm.exp_tab), up);
+            if (!dry) act_store<LL>(p.out, rr.row0 + row_l, hv, seq);
+        }
     } else if (is_last) {
-        store_row(p, rr.row0 + row_l, mine, pos);
+        store_row<EPI, LL>(p, rr.row0 + row_l, mine, pos, seq, dry);
     }
 }
 
@@ -564,15 +698,18 @@ LMRS_DEVINL GemvSmem carve_gemv_smem(uint8_t* base, int n, int n_bars) {
     return sm;
 }
 
-template <int QT, int WARPS, int DEPTH>
-__global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p) {
+// the quantized matrix-vector kernel (name chosen not to collide with library GEMV symbols in launch classifiers)
+template <int QT, int WARPS, int DEPTH, int PRO, int EPI, bool LL>
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) lmrs_q_matvec_kernel(const GemvParams p) {
     constexpr int STAGE = gemv_stage_bytes<QT>();
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* ring = smem;
     GemvSmem sm = carve_gemv_smem(ring + (size_t)WARPS * DEPTH * STAGE, p.n, WARPS * DEPTH);
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm.red + 64) + warp * DEPTH;
-    const WarpStreams<QT> w = make_streams<QT>(stream_desc(p), blockIdx.x * WARPS + warp, gridDim.x * WARPS);
+    StreamDesc sd = stream_desc(p);
+    sd.epi = EPI;
+    const WarpStreams<QT> w = make_streams<QT>(sd, blockIdx.x * WARPS + warp, gridDim.x * WARPS);
 
     if (lane == 0) {
 #pragma unroll
@@ -581,31 +718,43 @@ __global__ void __launch_bounds__(WARPS * 32, 1) gemv_kernel(const GemvParams p)
     }
     __syncwarp();
     const uint64_t pol = l2_policy_evict_first();
-    if (lane == 0)   // weights never depend on the previous kernel: start streaming before griddepcontrol.wait
+    if (lane == 0)   // weights never depend on the previous kernel: start streaming before anything else
         for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     const long long c0 = ktrace_c0();
     if (blockIdx.x == 0 && threadIdx.x == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
-    if (p.epi == EPI_GLU_SILU) {   // expf table -> shared memory (last 256 B), by the LAST warp, after the weight prefetch was issued
-        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (p.pro == PRO_NORM ? (size_t)p.n * 4 : 0));
+    if constexpr (EPI == EPI_GLU_SILU) {   // expf table -> shared memory (last 256 B), by the LAST warp, after the weight prefetch was issued
+        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (PRO == PRO_NORM ? (size_t)p.n * 4 : 0));
         if (warp == WARPS - 1) tab[lane] = kExp2fTab[lane];
         sm.exp_tab = tab;
     }
-    pdl_wait();  // upstream activations are complete and visible from here on
+    // Plain mode: upstream activations are complete and visible after griddepcontrol.wait (inside the prologue's real
+    // pass).  LL mode: no wait at all -- the prologue polls the activation words; the step parameters were written before
+    // the step's first (ordinary) launch.
+    // Warm-up pass (p.warm): a kernel of the chain is resident microseconds before its inputs exist, and every launch
+    // starts on a cold instruction cache (five different kernels per block evict each other; round 1 measured the exact
+    // rmsnorm chain at 5093 cycles cold against 2858 warm).  So the SAME loop body runs once on zeros first -- prologue,
+    // first ring stage, epilogue arithmetic, stores suppressed -- and the real pass finds its instructions cached.
+    const uint32_t seq = LL ? p.step->seq : 0u;
     if (lane == 0) { ktrace(p.trace_slot, 1); ktrace_c(p.trace_slot, 1, c0); }
-
-    gemv_prologue<QT, WARPS>(p, sm);
-    if (lane == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 2, c0); }
-
-    const uint32_t pos = (p.epi == EPI_QKV) ? p.step->pos : 0u;
-    Consumer<QT> cs;
-    consumer_begin<QT>(cs, w, sm);
-    for (int s = 0; s < w.nst; s++) {
-        const int d = s % DEPTH;
-        mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
-        consume_stage<QT>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, cs, pos);
-        __syncwarp();
-        if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
+    uint32_t pos = 0u;
+#pragma unroll 1
+    for (int pass = (p.warm && PRO != PRO_RAW) ? 0 : 1; pass < 2; pass++) {
+        const bool real = pass == 1;
+        gemv_prologue<QT, WARPS, PRO, LL>(p, sm, seq, real);
+        if (real && lane == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 2, c0); }
+        if (real && EPI == EPI_QKV && !LL) pos = p.step->pos;
+        Consumer<QT> cs;
+        consumer_begin<QT>(cs, w, sm);
+        const int nst = real ? w.nst : min(w.nst, 1);
+        for (int s = 0; s < nst; s++) {
+            const int d = s % DEPTH;
+            mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
+            consume_stage<QT, EPI, LL>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, cs, pos, seq, !real);
+            __syncwarp();
+            if (real && lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
+        }
+        if (!real) __syncthreads();   // nobody re-stages the activation while a warp still reads the dummy one
     }
     if (lane == 0) { ktrace(p.trace_slot, 3); ktrace_c(p.trace_slot, 3, c0); }
 }

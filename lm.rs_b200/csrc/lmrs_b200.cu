@@ -19,12 +19,24 @@
 #include "common.cuh"
 #include "gemm.cuh"
 #include "gemv.cuh"
-#include "mega.cuh"
 #include "misc.cuh"
 #include "f32_ops.cuh"
 #include "shard.h"
 
+#include <map>
+
 using namespace lmrs;
+
+// one phase of a step (src/transformer.rs:316-384 + :388-657): a quantized matrix-vector product with its fused glue,
+// the attention of a block, or the pending-residual write-back of a serial fill_kv_cache step
+enum { PH_GEMV = 0, PH_ATTN = 1, PH_FINALIZE = 2 };
+struct Phase {
+    int kind;
+    int comm;     // row-sharded (NCCL) mode: 1 = all-reduce the output, 2 = all-gather the logits
+    GemvParams g;
+    AttnParams a;
+    ResidualParams r;
+};
 
 static thread_local std::string g_err;
 extern "C" const char* lmrs_b200_last_error(void) { return g_err.c_str(); }
@@ -84,17 +96,21 @@ struct lmrs_b200 {
     StepParams* h_step_ring = nullptr;  // pinned
     int step_slot = 0;
     float* h_logits = nullptr;  // pinned
+    // on-device greedy sampler (src/sampler.rs:29-41): per-CTA partials, ticket, the chosen token ids of a generate call
+    float* d_amax = nullptr; int* d_aidx = nullptr; unsigned* d_ticket = nullptr; uint32_t* d_next = nullptr;
+    uint32_t* d_gen = nullptr; uint32_t* h_gen = nullptr; size_t gen_cap = 0;
     cudaStream_t stream = nullptr, own_stream = nullptr;
-    MegaPhase *d_ph_decode = nullptr, *d_ph_prefill = nullptr;   // device copies of the phase tables
-    StreamDesc *d_sd_decode = nullptr, *d_sd_prefill = nullptr;
-    std::vector<MegaPhase> ph_decode, ph_prefill;
-    unsigned long long* d_bar = nullptr;      // [2] grid-barrier counters (decode, prefill variants)
+    std::vector<Phase> ph_decode, ph_prefill;
     unsigned long long* d_trace = nullptr;
-    unsigned long long* d_timing = nullptr;   // LMRS_B200_TIMING=1: per-phase globaltimer stamps of the last decode step
-    uint32_t seq_decode = 0, seq_prefill = 0;
-    bool use_mega = true;
-    int mega_depth = 4;
-    size_t mega_smem = 0;
+    // LL exchange (common.cuh): one (value, sequence) word buffer per activation per layer, written once per step;
+    // step_seq numbers the steps of this handle (decode and serial prefill alike), 0 is never used
+    llword_t* d_ll = nullptr;
+    size_t ll_words = 0;
+    bool use_ll = true;
+    bool use_warm = true;   // instruction-cache warm-up pass in the chain's kernels (gemv.cuh)
+    uint32_t step_seq = 0;
+    float* d_fin_scratch = nullptr;
+    std::map<const void*, size_t> smem_optin;   // per handle (= per device): kernels whose >48 KB opt-in has been set
     // one CUDA graph per attention variant: 0..5 = cluster attention variants (setup_attn_cluster), 7 = single-CTA kernel
     cudaGraphExec_t g_decode[8] = {}, g_prefill[8] = {};
     cudaStream_t g_decode_stream[8] = {}, g_prefill_stream[8] = {};
@@ -106,9 +122,11 @@ struct lmrs_b200 {
     uint64_t launches = 0;
     int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
-    int gemv_cfg = 0, gemv_cfg_long = 0, gemv_ctas_per_sm = 1;
+    int gemv_cfg = 0, gemv_ctas_per_sm = 1;
     Shard shard;  // multi-GPU exchange (shard.h); inert when world == 1
 };
+
+static cudaError_t smem_optin(lmrs_b200* m, const void* fn, size_t smem);
 
 // ---- kernel launch helper (optionally with the programmatic-dependent-launch attribute) -------------------
 template <typename... KArgs, typename... Args>
@@ -123,31 +141,54 @@ static cudaError_t launch(lmrs_b200* m, void (*kernel)(KArgs...), dim3 grid, dim
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = m->use_pdl ? 1 : 0;
+    cudaError_t ce = smem_optin(m, (const void*)kernel, smem);
+    if (ce != cudaSuccess) return ce;
     m->launches++;
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+// function attributes are per device: the opt-in to > 48 KB of dynamic shared memory is tracked per handle
+// Every kernel also asks for the maximum shared-memory carveout: an SM re-partitions L1/shared memory only when it is
+// idle, so a kernel that prefers a different carveout than the one resident cannot start next to it (measured: the
+// attention kernel of the LL chain started only after the QKV kernel had drained).  With one carveout for all kernels
+// consecutive kernels of the chain are co-resident as far as registers and shared memory allow.
+static cudaError_t smem_optin(lmrs_b200* m, const void* fn, size_t smem) {
+    auto it = m->smem_optin.find(fn);
+    if (it == m->smem_optin.end()) {
+        static const int carve = env_int("LMRS_B200_CARVEOUT", 100);   // developer knob: -1 = leave the driver's default
+        cudaError_t e = carve >= 0 ? cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, carve) : cudaSuccess;
+        if (e != cudaSuccess) return e;
+        it = m->smem_optin.emplace(fn, (size_t)0).first;
+    }
+    if (smem <= it->second || smem <= 48 * 1024) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) it->second = smem;
+    return e;
+}
+
 // ---- GEMV dispatch ----------------------------------------------------------------------------------------
+// ring geometries (warps, stages per warp); 8 warps x <= 128 registers: two CTAs (consecutive kernels of the chain) per SM
 struct GemvCfg { int warps, depth; };
-static const GemvCfg kGemvCfgs[] = {{8, 2}, {8, 3}, {16, 2}, {8, 4}, {4, 4}};
+static const GemvCfg kGemvCfgs[] = {{8, 2}, {8, 3}};
+constexpr int N_GEMV_CFG = 2;
 typedef void (*gemv_fn)(const GemvParams);
-template <int QT> static gemv_fn gemv_kernel_for(int cfg) {
-    switch (cfg) {
-        case 0: return gemv_kernel<QT, 8, 2>;
-        case 1: return gemv_kernel<QT, 8, 3>;
-        case 2: return gemv_kernel<QT, 16, 2>;
-        case 3: return gemv_kernel<QT, 8, 4>;
-        default: return gemv_kernel<QT, 4, 4>;
+template <int QT, int W, int D, bool LL> static gemv_fn gemv_kernel_pe(int pro, int epi) {
+    if (pro == PRO_RAW) return LL ? nullptr : (gemv_fn)lmrs_q_matvec_kernel<QT, W, D, PRO_RAW, EPI_STORE, false>;
+    if (pro == PRO_QUANT) return epi == EPI_STORE ? (gemv_fn)lmrs_q_matvec_kernel<QT, W, D, PRO_QUANT, EPI_STORE, LL> : nullptr;
+    switch (epi) {
+        case EPI_QKV: return lmrs_q_matvec_kernel<QT, W, D, PRO_NORM, EPI_QKV, LL>;
+        case EPI_GLU_SILU: return lmrs_q_matvec_kernel<QT, W, D, PRO_NORM, EPI_GLU_SILU, LL>;
+        case EPI_GLU_GELU: return lmrs_q_matvec_kernel<QT, W, D, PRO_NORM, EPI_GLU_GELU, LL>;
+        case EPI_LOGITS: return lmrs_q_matvec_kernel<QT, W, D, PRO_NORM, EPI_LOGITS, LL>;
+        default: return nullptr;
     }
 }
+template <int QT> static gemv_fn gemv_kernel_for(int cfg, int pro, int epi, bool ll) {
+    if (cfg == 1) return ll ? gemv_kernel_pe<QT, 8, 3, true>(pro, epi) : gemv_kernel_pe<QT, 8, 3, false>(pro, epi);
+    return ll ? gemv_kernel_pe<QT, 8, 2, true>(pro, epi) : gemv_kernel_pe<QT, 8, 2, false>(pro, epi);
+}
 template <int QT> static size_t gemv_smem_for(int cfg, int n, bool norm) {
-    switch (cfg) {
-        case 0: return gemv_smem_bytes<QT, 8, 2>(n, norm);
-        case 1: return gemv_smem_bytes<QT, 8, 3>(n, norm);
-        case 2: return gemv_smem_bytes<QT, 16, 2>(n, norm);
-        case 3: return gemv_smem_bytes<QT, 8, 4>(n, norm);
-        default: return gemv_smem_bytes<QT, 4, 4>(n, norm);
-    }
+    return cfg == 1 ? gemv_smem_bytes<QT, 8, 3>(n, norm) : gemv_smem_bytes<QT, 8, 2>(n, norm);
 }
 // stream boundaries must fall on BP16 block boundaries: row0 * G must be a multiple of 16 groups
 static int gran_for(int n) {
@@ -168,17 +209,13 @@ static cudaError_t repack_bp16(int q_type, uint8_t* dst, const uint8_t* src_q, c
 }
 
 static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
-    // long activation vectors (the down projection quantizes hidden_dim elements in its prologue) get more warps
-    const int cfg = (p.pro == PRO_QUANT && p.n >= 4096) ? m->gemv_cfg_long : m->gemv_cfg;
+    const int cfg = m->gemv_cfg;
     const GemvCfg c = kGemvCfgs[cfg];
-    gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(cfg) : gemv_kernel_for<2>(cfg);
+    gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(cfg, p.pro, p.epi, p.ll != 0) : gemv_kernel_for<2>(cfg, p.pro, p.epi, p.ll != 0);
+    if (!fn) return cudaErrorInvalidValue;
     size_t smem = q_type == 1 ? gemv_smem_for<1>(cfg, p.n, p.pro == PRO_NORM) : gemv_smem_for<2>(cfg, p.n, p.pro == PRO_NORM);
-    static thread_local size_t max_set[2][8] = {};
-    if (smem > max_set[q_type - 1][cfg]) {
-        cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        max_set[q_type - 1][cfg] = smem;
-    }
+    cudaError_t se = smem_optin(m, (const void*)fn, smem);
+    if (se != cudaSuccess) return se;
     int grid = m->sms * m->gemv_ctas_per_sm;
     // never launch more CTAs than there are row units to hand out (tiny matrices)
     const bool glu = p.epi == EPI_GLU_SILU || p.epi == EPI_GLU_GELU;
@@ -197,14 +234,12 @@ static GemvParams gemv_base(const Mat& a, const Mat* b) {
 }
 
 template <int HS, bool BIG> static cudaError_t launch_attn_grid_hs(lmrs_b200* m, const AttnParams& p0, int n_kv_heads, int rows) {
-    static thread_local bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(attn_decode_kernel<HS, BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)attn_smem_bytes<HS, BIG>());
+    {
+        cudaError_t e = smem_optin(m, (const void*)attn_decode_kernel<HS, BIG>, attn_smem_bytes<HS, BIG>());
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     AttnParams p = p0;
-    const bool split_scores = env_int("LMRS_B200_ATT_SPLIT", rows > 1 ? 1 : 0) != 0;   // decode: measured no gain (extra launch)
+    const bool split_scores = !p.ll && env_int("LMRS_B200_ATT_SPLIT", rows > 1 ? 1 : 0) != 0;   // decode: measured no gain (extra launch)
     if (split_scores) {
         // the independent q.k dot products cover the whole GPU (decode: position splits; prefill: token rows) ...
         int nsplit = 1;
@@ -237,11 +272,9 @@ template <int HS, int CL, int G> static cudaError_t launch_attn_cluster_t(lmrs_b
     } else {
         const int nh = std::min<int>(ATT_QH, p.kv_mul);
         const size_t smem = attc_smem_floats(HS, cap, CL, G, nh) * 4;
-        static thread_local size_t set_for = 0;
-        if (set_for < smem) {
-            cudaError_t e = cudaFuncSetAttribute(attn_cluster_kernel<HS, CL, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        {
+            cudaError_t e = smem_optin(m, (const void*)attn_cluster_kernel<HS, CL, G>, smem);
             if (e != cudaSuccess) return e;
-            set_for = smem;
         }
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3((unsigned)(n_kv_heads * p.chunks * CL));
@@ -318,7 +351,7 @@ static void setup_attn_cluster(lmrs_b200* m) {
     }
 }
 static int attn_variant_for(const lmrs_b200* m, uint32_t pos) {
-    if (m->att_cl == 0 || (m->use_mega && m->world == 1)) return ATT_LEGACY;
+    if (m->att_cl == 0) return ATT_LEGACY;
     for (int b = 0; b < m->att_nvar; b++)
         if ((int)pos + 1 <= m->att_var[b].cap) return b;
     return ATT_LEGACY;
@@ -357,8 +390,7 @@ static bool gemm_shape_ok(int n, int o) { return n % 128 == 0 && o % 128 == 0; }
 static int launch_gemm(lmrs_b200* m, const Mat& w, const uint8_t* xq, const float* xs, int T, GemmParams gp) {
     CUtensorMap ta;
     if (make_tmap_2d(&ta, xq, (size_t)w.n, (size_t)T)) return 1;
-    static thread_local bool attr = false;
-    if (!attr) { CK(cudaFuncSetAttribute(gemm_q8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM)); attr = true; }
+    CK(smem_optin(m, (const void*)gemm_q8_kernel, GEMM_SMEM));
     gp.T = T; gp.n = w.n; gp.o = w.o; gp.ws = w.ds; gp.xs = xs;
     dim3 grid(w.o / GEMM_N, (T + GEMM_M - 1) / GEMM_M);
     gemm_q8_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, m->stream>>>(ta, w.tmap, gp);
@@ -412,6 +444,19 @@ static void rope_freq(int model_type, float rope_theta, int head_size, int j, fl
     }
     *freq_out = freq;
     *mscale = scaling;
+}
+
+// ---- LL exchange buffers: per layer one word array per activation that crosses a kernel boundary ------------------
+struct LLLayout { size_t xo1, q, k_new, v_new, att, wo_out, xo0, h, down_out, per_layer; };
+static LLLayout ll_layout(const lmrs_b200* m) {
+    LLLayout L{};
+    size_t cur = 0;
+    auto take = [&](size_t n) { size_t o = cur; cur += (n + 15) / 16 * 16; return o; };   // 128-byte aligned slices
+    L.xo1 = take(m->args.dim); L.q = take(m->l_att_dim); L.k_new = take(m->l_kv_dim); L.v_new = take(m->l_kv_dim);
+    L.att = take(m->l_att_dim); L.wo_out = take(m->args.dim); L.xo0 = take(m->args.dim); L.h = take(m->l_hidden);
+    L.down_out = take(m->args.dim);
+    L.per_layer = cur;
+    return L;
 }
 
 // ---- loader ----------------------------------------------------------------------------------------------
@@ -627,6 +672,16 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     CK(cudaMalloc(&m->d_down_out, dim * 4));
     CK(cudaMalloc(&m->d_logits, (size_t)a.vocab_size * 4));
     CK(cudaMalloc(&m->d_scores, (size_t)m->l_heads * align_up(a.seq_len, 4) * 4));
+    {
+        const LLLayout Y0 = ll_layout(m);
+        m->ll_words = Y0.per_layer * L;
+        CK(cudaMalloc(&m->d_ll, m->ll_words * sizeof(llword_t)));
+        CK(cudaMemset(m->d_ll, 0, m->ll_words * sizeof(llword_t)));   // sequence number 0 = "never written"
+        CK(cudaMalloc(&m->d_fin_scratch, dim * 4));
+    }
+    CK(cudaMalloc(&m->d_amax, 256 * 4)); CK(cudaMalloc(&m->d_aidx, 256 * 4));
+    CK(cudaMalloc(&m->d_ticket, 4)); CK(cudaMemset(m->d_ticket, 0, 4));
+    CK(cudaMalloc(&m->d_next, 4));
     CK(cudaMalloc(&m->d_step, sizeof(StepParams)));
     CK(cudaMallocHost(&m->h_step_ring, sizeof(StepParams) * 64));
     CK(cudaMallocHost(&m->h_logits, (size_t)a.vocab_size * 4));
@@ -635,199 +690,181 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     return 0;
 }
 
-// ---- the decode step as a table of phases (src/transformer.rs:316-384 + :388-657 with sl = 1) -----------------
-// One table drives both execution modes: the persistent megakernel (mega.cuh) and the one-kernel-per-phase path
-// (multi-GPU, debugging).  `serial_prefill`: x comes from row `token` of the staged embeddings, no classifier, and
-// a final phase writes the residual stream back (fill_kv_cache semantics).
-static std::vector<MegaPhase> make_phases(lmrs_b200* m, bool serial_prefill) {
+// ---- the step as a table of phases (src/transformer.rs:316-384 + :388-657 with sl = 1) ------------------------------
+// `serial_prefill`: x comes from row `token` of the staged embeddings, no classifier, and a final phase writes the
+// residual stream back (fill_kv_cache semantics).  `ll`: the activations between the phases are LL word buffers (one per
+// phase output per layer) and the kernels never wait for a kernel boundary; otherwise plain f32 buffers reused by every
+// layer and griddepcontrol.wait (row-sharded NCCL mode, LMRS_B200_LL=0).
+static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
     const lmrs_args_t& a = m->args;
     const bool gemma = a.model_type == 0;
+    const bool ll = m->use_ll;
     const size_t L = a.n_layers;
-    std::vector<MegaPhase> ph;
-    const float* delta = nullptr;       // pending residual contribution
+    const LLLayout Y0 = ll_layout(m);
+    std::vector<Phase> ph;
+    const void* delta = nullptr;        // pending residual contribution
     const float* w_post = nullptr;      // Gemma: norm applied to it before the add
+    const void* x_cur = ll ? nullptr : (const void*)m->d_x[0];   // residual stream before the pending add
     auto gemv_phase = [&](const Mat& A, const Mat* B) {
-        MegaPhase P;
+        Phase P;
         memset(&P, 0, sizeof P);
         P.kind = PH_GEMV;
         P.g = gemv_base(A, B);
         P.g.step = m->d_step;
+        P.g.ll = ll;
+        P.g.warm = m->use_warm;
         return P;
     };
     for (size_t l = 0; l < L; l++) {
         const Layer& Y = m->layers[l];
         float* kc = m->d_kcache + l * (size_t)a.seq_len * m->l_kv_dim;
         float* vc = m->d_vcache + l * (size_t)a.seq_len * m->l_kv_dim;
+        llword_t* lb = m->d_ll + l * Y0.per_layer;
+        void* b_xo1 = ll ? (void*)(lb + Y0.xo1) : (void*)m->d_x[1];
+        void* b_q = ll ? (void*)(lb + Y0.q) : (void*)m->d_q;
+        void* b_knew = ll ? (void*)(lb + Y0.k_new) : (void*)m->d_knew;
+        void* b_vnew = ll ? (void*)(lb + Y0.v_new) : (void*)vc;
+        void* b_att = ll ? (void*)(lb + Y0.att) : (void*)m->d_att;
+        void* b_wo = ll ? (void*)(lb + Y0.wo_out) : (void*)m->d_wo_out;
+        void* b_xo0 = ll ? (void*)(lb + Y0.xo0) : (void*)m->d_x[0];
+        void* b_h = ll ? (void*)(lb + Y0.h) : (void*)m->d_h;
+        void* b_down = ll ? (void*)(lb + Y0.down_out) : (void*)m->d_down_out;
         {   // x(+delta) -> rmsnorm(w_rms_att) -> quantize -> [Wq;Wk;Wv]   (:409-431)
-            MegaPhase P = gemv_phase(Y.qkv, nullptr);
+            Phase P = gemv_phase(Y.qkv, nullptr);
             GemvParams& p = P.g;
-            p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
-            p.x_out = m->d_x[1]; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
+            p.pro = PRO_NORM; p.x_in = x_cur; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
+            p.x_out = b_xo1; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
             if (l == 0) {
-                if (serial_prefill) { p.x_in = m->d_rows; p.x_in_stride = (int)a.dim; }
+                if (serial_prefill) { p.x_in = m->d_rows; p.x_in_stride = (int)a.dim; p.x_in_plain = 1; }
                 else {   // embedding row (:324) with Gemma's sqrt(dim) scaling (:327-332) folded into the prologue
                     p.emb_q = m->emb.q; p.emb_s = m->emb.s; p.emb_qtype = a.q_type;
                     p.emb_apply_mul = gemma; p.emb_mul = sqrtf((float)a.dim);
                 }
             }
-            p.epi = EPI_QKV; p.out = m->d_q; p.out_k = m->d_knew; p.out_v = vc;
+            p.epi = EPI_QKV; p.out = b_q; p.out_k = b_knew; p.out_v = b_vnew;
             p.att_dim = m->l_att_dim; p.kv_dim = m->l_kv_dim;
             ph.push_back(P);
         }
         {   // RoPE + attention (:443-544)
-            MegaPhase P;
+            Phase P;
             memset(&P, 0, sizeof P);
             P.kind = PH_ATTN;
             AttnParams& p = P.a;
-            p.q = m->d_q; p.k_new = m->d_knew; p.kcache = kc; p.vcache = vc;
-            p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = m->d_att; p.scores = m->d_scores;
+            p.q = b_q; p.k_new = b_knew; p.v_new = ll ? b_vnew : nullptr; p.kcache = kc; p.vcache = vc;
+            p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin; p.out = b_att; p.scores = m->d_scores;
             p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
             p.chunks = m->att_chunks; p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4);
-            p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
+            p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step; p.ll = ll;
             ph.push_back(P);
         }
         {   // quantize(att) -> Wo (:546-560)
-            MegaPhase P = gemv_phase(Y.wo, nullptr);
-            P.g.pro = PRO_QUANT; P.g.act_in = m->d_att; P.g.epi = EPI_STORE; P.g.out = m->d_wo_out;
-            P.pad = 1;   // multi-GPU: all-reduce the output
+            Phase P = gemv_phase(Y.wo, nullptr);
+            P.g.pro = PRO_QUANT; P.g.act_in = b_att; P.g.epi = EPI_STORE; P.g.out = b_wo;
+            P.comm = 1;   // row-sharded mode: all-reduce the output
             ph.push_back(P);
         }
         {   // x += wo_out (Gemma: normed) -> rmsnorm -> quantize -> gate/up -> act*up (:562-624)
-            MegaPhase P = gemv_phase(Y.w1, &Y.w3);
+            Phase P = gemv_phase(Y.w1, &Y.w3);
             GemvParams& p = P.g;
-            p.pro = PRO_NORM; p.x_in = m->d_x[1]; p.delta = m->d_wo_out; p.w_post = gemma ? Y.rms_post_att : nullptr;
-            p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_x[0]; p.eps = a.rms_norm_eps;
-            p.unit_offset = gemma; p.epi = gemma ? EPI_GLU_GELU : EPI_GLU_SILU; p.out = m->d_h;
+            p.pro = PRO_NORM; p.x_in = b_xo1; p.delta = b_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
+            p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = b_xo0; p.eps = a.rms_norm_eps;
+            p.unit_offset = gemma; p.epi = gemma ? EPI_GLU_GELU : EPI_GLU_SILU; p.out = b_h;
             ph.push_back(P);
         }
         {   // quantize(hidden) -> W2 (:626-640)
-            MegaPhase P = gemv_phase(Y.w2, nullptr);
-            P.g.pro = PRO_QUANT; P.g.act_in = m->d_h; P.g.epi = EPI_STORE; P.g.out = m->d_down_out;
-            P.pad = 1;
+            Phase P = gemv_phase(Y.w2, nullptr);
+            P.g.pro = PRO_QUANT; P.g.act_in = b_h; P.g.epi = EPI_STORE; P.g.out = b_down;
+            P.comm = 1;
             ph.push_back(P);
         }
-        delta = m->d_down_out;
+        x_cur = b_xo0;
+        delta = b_down;
         w_post = gemma ? Y.rms_post_ffn : nullptr;   // (:642-656) applied by the next prologue
     }
     if (!serial_prefill) {   // final rmsnorm + classifier (:343-371) + Gemma soft-cap quirk (:375-381)
-        MegaPhase P = gemv_phase(m->cls, nullptr);
+        Phase P = gemv_phase(m->cls, nullptr);
         GemvParams& p = P.g;
-        p.pro = PRO_NORM; p.x_in = m->d_x[0]; p.delta = delta; p.w_post = w_post; p.w_norm = m->rms_final;
+        p.pro = PRO_NORM; p.x_in = x_cur; p.delta = delta; p.w_post = w_post; p.w_norm = m->rms_final;
         p.x_out = nullptr; p.eps = a.rms_norm_eps; p.unit_offset = gemma;
         p.epi = EPI_LOGITS; p.out = m->d_logits + m->vocab_off;
         int cap = gemma ? (int)a.dim - m->vocab_off : 0;
         p.softcap_rows = cap < 0 ? 0 : (cap > m->l_vocab ? m->l_vocab : cap);
-        P.pad = 2;   // multi-GPU: all-gather logits
+        P.comm = 2;   // row-sharded mode: all-gather logits
         ph.push_back(P);
     } else {                 // fill_kv_cache returns the residual stream: apply the pending add (:642-656)
-        MegaPhase P;
+        Phase P;
         memset(&P, 0, sizeof P);
         P.kind = PH_FINALIZE;
-        P.r.x_in = m->d_x[0]; P.r.delta = delta; P.r.w_post = w_post; P.r.n = a.dim; P.r.eps = a.rms_norm_eps;
-        P.r.rows = m->d_rows; P.r.step = m->d_step;
+        P.r.x_in = x_cur; P.r.delta = delta; P.r.w_post = w_post; P.r.n = a.dim; P.r.eps = a.rms_norm_eps;
+        P.r.rows = m->d_rows; P.r.step = m->d_step; P.r.ll = ll; P.r.scratch = m->d_fin_scratch;
         ph.push_back(P);
     }
     return ph;
 }
 
-// one kernel per phase (PDL-chained); the only mode with world > 1 (NCCL collectives between kernels)
-static int enqueue_phases_multi(lmrs_b200* m, const std::vector<MegaPhase>& ph) {
+// one kernel per phase, chained with programmatic dependent launch.  LL mode: the kernels are launched early and hand
+// their results over through the LL buffers (no griddepcontrol.wait); plain mode: every kernel waits for its predecessor
+// (the only mode with world > 1: NCCL collectives sit between the kernels).
+static int enqueue_step(lmrs_b200* m, bool decode, bool nowait = false, int only_kind = -1) {
+    const std::vector<Phase>& ph = decode ? m->ph_decode : m->ph_prefill;
     const bool pdl = m->use_pdl;
     bool first = true;
     int slot = 0;
-    for (const MegaPhase& P0 : ph) {
-        MegaPhase P = P0;
+    for (const Phase& P0 : ph) {
+        Phase P = P0;
         P.g.trace_slot = P.a.trace_slot = -1;
         if (m->d_trace && P.kind == PH_GEMV) P.g.trace_slot = slot;
         if (m->d_trace && P.kind == PH_ATTN) P.a.trace_slot = slot;
         slot++;
+        if (only_kind >= 0 && P.kind != only_kind) continue;
+        P.g.ll_nowait = P.a.ll_nowait = P.r.ll_nowait = nowait;
         // the first kernel of a step is an ordinary launch: it starts after EVERYTHING earlier in the stream has
-        // completed, which is what lets later kernels of the step touch older KV rows before their dependency wait
+        // completed, which is what lets later kernels of the step touch older KV rows (and reuse the LL buffers of the
+        // previous step) without any further synchronisation
         m->use_pdl = pdl && !first;
         first = false;
+        int rc = 0;
+        cudaError_t e = cudaSuccess;
         if (P.kind == PH_GEMV) {
-            CK(launch_gemv(m, m->args.q_type, P.g));
-            if (m->world > 1 && P.pad == 1) { if (shard_allreduce(m->shard, P.g.out, m->args.dim, m->stream)) return fail(shard_error()); m->launches++; }
-            if (m->world > 1 && P.pad == 2) { if (shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream)) return fail(shard_error()); m->launches++; }
+            e = launch_gemv(m, m->args.q_type, P.g);
+            if (e == cudaSuccess && m->world > 1 && P.comm == 1) { rc = shard_allreduce(m->shard, (float*)P.g.out, m->args.dim, m->stream); m->launches++; }
+            if (e == cudaSuccess && m->world > 1 && P.comm == 2) { rc = shard_allgather_logits(m->shard, m->d_logits, m->l_vocab, m->stream); m->launches++; }
         } else if (P.kind == PH_ATTN) {
-            if (m->att_variant != ATT_LEGACY) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g));
-            else CK(launch_attn(m, P.a, m->l_kv_heads));
+            if (m->att_variant != ATT_LEGACY) e = launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g);
+            else e = launch_attn(m, P.a, m->l_kv_heads);
         } else {
-            CK(launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r));
+            e = launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r);
+        }
+        if (e != cudaSuccess || rc) {
+            m->use_pdl = pdl;
+            return fail(rc ? std::string(shard_error()) : std::string("kernel launch: ") + cudaGetErrorString(e));
         }
     }
     m->use_pdl = pdl;
     return 0;
 }
 
-template <int QT, int HS> static cudaError_t launch_mega_t(lmrs_b200* m, const MegaParams& mp) {
-    static thread_local size_t set_for = 0;
-    if (set_for < m->mega_smem) {
-        cudaError_t e = cudaFuncSetAttribute(decode_mega_kernel<QT, HS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->mega_smem);
-        if (e != cudaSuccess) return e;
-        set_for = m->mega_smem;
-    }
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(m->sms);
-    cfg.blockDim = dim3(MEGA_WARPS * 32);
-    cfg.dynamicSmemBytes = m->mega_smem;
-    cfg.stream = m->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeCooperative;   // all CTAs co-resident: required by the in-kernel grid barriers
-    attr[0].val.cooperative = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    m->launches++;
-    return cudaLaunchKernelEx(&cfg, decode_mega_kernel<QT, HS>, mp);
-}
-template <int QT> static cudaError_t launch_mega_q(lmrs_b200* m, const MegaParams& mp) {
-    switch (m->args.head_size) {
-        case 64: return launch_mega_t<QT, 64>(m, mp);
-        case 96: return launch_mega_t<QT, 96>(m, mp);
-        case 128: return launch_mega_t<QT, 128>(m, mp);
-        case 256: return launch_mega_t<QT, 256>(m, mp);
-        default: return cudaErrorInvalidValue;
-    }
-}
-template <int HS> static size_t attn_smem_for() { return attn_smem_bytes<HS>(); }
-static size_t attn_smem_host(int hs) {
-    switch (hs) { case 64: return attn_smem_bytes<64>(); case 96: return attn_smem_bytes<96>(); case 128: return attn_smem_bytes<128>(); default: return attn_smem_bytes<256>(); }
-}
-
-static int enqueue_step(lmrs_b200* m, bool decode) {
-    const std::vector<MegaPhase>& ph = decode ? m->ph_decode : m->ph_prefill;
-    if (!m->use_mega || m->world > 1) return enqueue_phases_multi(m, ph);
-    MegaParams mp{};
-    mp.phases = decode ? m->d_ph_decode : m->d_ph_prefill;
-    mp.streams = decode ? m->d_sd_decode : m->d_sd_prefill;
-    mp.n_phases = (int)ph.size();
-    mp.depth = m->mega_depth;
-    mp.act_n = std::max<int>(m->args.dim, std::max<int>(m->l_hidden, m->l_att_dim));
-    mp.norm_n = m->args.dim;
-    mp.n_kv_heads = m->l_kv_heads; mp.att_chunks = m->att_chunks; mp.head_size = m->args.head_size;
-    mp.bar_ctr = m->d_bar + (decode ? 0 : 1);
-    mp.step = m->d_step;
-    mp.timing = decode ? m->d_timing : nullptr;
-    CK(m->args.q_type == 1 ? launch_mega_q<1>(m, mp) : launch_mega_q<2>(m, mp));
-    return 0;
-}
-
-// build (once) and replay the step as a CUDA graph (one cooperative launch, or the PDL-chained kernel sequence)
+// build (once) and replay the step as a CUDA graph of the PDL-chained kernel sequence
 static int run_graph(lmrs_b200* m, cudaGraphExec_t* exec, cudaStream_t* built_on, int* n_kernels, bool decode) {
     if (!m->use_graph) return enqueue_step(m, decode);
     if (!*exec || *built_on != m->stream) {
         if (*exec) { cudaGraphExecDestroy(*exec); *exec = nullptr; }
-        cudaGraph_t graph;
+        cudaGraph_t graph = nullptr;
         uint64_t before = m->launches;
         CK(cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal));
         int rc = enqueue_step(m, decode);
         cudaError_t e = cudaStreamEndCapture(m->stream, &graph);
-        if (rc) return 1;
-        if (e != cudaSuccess) return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        if (rc || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            m->launches = before;
+            if (rc) return 1;
+            return fail(std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        }
         *n_kernels = (int)(m->launches - before);
         m->launches = before;
-        CK(cudaGraphInstantiate(exec, graph, 0));
-        CK(cudaGraphDestroy(graph));
+        cudaError_t ie = cudaGraphInstantiate(exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ie != cudaSuccess) { *exec = nullptr; return fail(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ie)); }
         *built_on = m->stream;
     }
     CK(cudaGraphLaunch(*exec, m->stream));
@@ -835,43 +872,8 @@ static int run_graph(lmrs_b200* m, cudaGraphExec_t* exec, cudaStream_t* built_on
     return 0;
 }
 
-static int upload_phases(lmrs_b200* m, bool decode) {
-    std::vector<MegaPhase>& ph = decode ? m->ph_decode : m->ph_prefill;
-    MegaPhase** dptr = decode ? &m->d_ph_decode : &m->d_ph_prefill;
-    ph = make_phases(m, !decode);
-    if (*dptr) { cudaFree(*dptr); *dptr = nullptr; }
-    CK(cudaMalloc(dptr, ph.size() * sizeof(MegaPhase)));
-    CK(cudaMemcpy(*dptr, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    std::vector<StreamDesc> sd(ph.size());
-    for (size_t i = 0; i < ph.size(); i++) {
-        memset(&sd[i], 0, sizeof(StreamDesc));
-        if (ph[i].kind == PH_GEMV) sd[i] = {ph[i].g.wq_a, ph[i].g.ws_a, ph[i].g.wq_b, ph[i].g.ws_b, ph[i].g.n, ph[i].g.o, ph[i].g.row_gran, ph[i].g.epi};
-    }
-    StreamDesc** sptr = decode ? &m->d_sd_decode : &m->d_sd_prefill;
-    if (*sptr) { cudaFree(*sptr); *sptr = nullptr; }
-    CK(cudaMalloc(sptr, sd.size() * sizeof(StreamDesc)));
-    CK(cudaMemcpy(*sptr, sd.data(), sd.size() * sizeof(StreamDesc), cudaMemcpyHostToDevice));
-    return 0;
-}
-
-static int setup_mega(lmrs_b200* m) {
-    const int act_n = std::max<int>(m->args.dim, std::max<int>(m->l_hidden, m->l_att_dim));
-    const size_t uni = std::max(mega_act_bytes(act_n, m->args.dim), attn_smem_host(m->args.head_size));
-    const size_t stage = m->args.q_type == 1 ? gemv_stage_bytes<1>() : gemv_stage_bytes<2>();
-    const size_t limit = 227 * 1024;
-    int depth = env_int("LMRS_B200_MEGA_DEPTH", MEGA_MAX_DEPTH);
-    if (depth > MEGA_MAX_DEPTH) depth = MEGA_MAX_DEPTH;
-    const size_t fixed = MEGA_WARPS * MEGA_MAX_DEPTH * 8 + mega_desc_bytes(5 * m->args.n_layers + 2) + 2 * mega_phase_bytes() + uni;
-    while (depth > 1 && MEGA_WARPS * depth * stage + fixed > limit) depth--;
-    m->mega_depth = depth;
-    m->mega_smem = MEGA_WARPS * depth * stage + fixed;
-    if (m->mega_smem > limit) m->use_mega = false;   // does not fit: fall back to one kernel per phase
-    CK(cudaMalloc(&m->d_bar, 2 * sizeof(unsigned long long)));
-    CK(cudaMemset(m->d_bar, 0, 2 * sizeof(unsigned long long)));
+static int setup_trace(lmrs_b200* m) {
     if (env_int("LMRS_B200_TIMING", 0)) {
-        size_t n = (size_t)(5 * m->args.n_layers + 2) * 4 * m->sms;
-        CK(cudaMalloc(&m->d_timing, n * 8));
-        CK(cudaMemset(m->d_timing, 0, n * 8));
         unsigned long long* tb;
         CK(cudaMalloc(&tb, 2 * 8192 * 8));
         CK(cudaMemset(tb, 0, 2 * 8192 * 8));
@@ -881,7 +883,12 @@ static int setup_mega(lmrs_b200* m) {
     return 0;
 }
 
-static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_base, uint32_t seq) {
+static uint32_t next_seq(lmrs_b200* m) {   // LL sequence numbers: one per step of this handle, never 0
+    if (++m->step_seq == 0) ++m->step_seq;
+    return m->step_seq;
+}
+static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_base) {
+    const uint32_t seq = next_seq(m);
     if (m->step_slot == 64) { CK(cudaStreamSynchronize(m->stream)); m->step_slot = 0; }
     StepParams* s = &m->h_step_ring[m->step_slot++];
     s->token = token; s->pos = pos; s->mask_base = mask_base; s->seq = seq;
@@ -894,7 +901,7 @@ static int push_step(lmrs_b200* m, uint32_t token, uint32_t pos, uint32_t mask_b
 // reference's batched forward_layer; the Gemma window quirk is reproduced through mask_base.
 static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
     for (size_t i = 0; i < n; i++) {
-        if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos, m->seq_prefill++)) return 1;
+        if (push_step(m, (uint32_t)i, pos + (uint32_t)i, pos)) return 1;
         const int v = m->att_variant = attn_variant_for(m, pos + (uint32_t)i);
         if (run_graph(m, &m->g_prefill[v], &m->g_prefill_stream[v], &m->n_prefill_kernels[v], false)) return 1;
     }
@@ -928,18 +935,20 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
     const lmrs_args_t& a = m->args;
     const int T = (int)n, dim = a.dim, att = m->l_att_dim, kvd = m->l_kv_dim, hid = m->l_hidden;
     const bool gemma = a.model_type == 0;
+    const size_t sc_stride = align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // batched rows: pos + n <= ATT_SC_CAP
     if (m->pf_cap < n) {
-        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
+        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down, (void*)m->pf_scores}) cudaFree(p);
+        m->pf_xq = nullptr; m->pf_xs = m->pf_q = m->pf_att = m->pf_wo = m->pf_g = m->pf_u = m->pf_h = m->pf_down = m->pf_scores = nullptr;
+        m->pf_cap = 0;   // a failed allocation below must not leave a capacity behind
         const size_t nmax = std::max<size_t>(std::max<size_t>(dim, att), hid);
         CK(cudaMalloc(&m->pf_xq, n * nmax)); CK(cudaMalloc(&m->pf_xs, n * (nmax / GS) * 4));
         CK(cudaMalloc(&m->pf_q, n * att * 4)); CK(cudaMalloc(&m->pf_att, n * att * 4)); CK(cudaMalloc(&m->pf_wo, n * dim * 4));
         CK(cudaMalloc(&m->pf_g, n * hid * 4)); CK(cudaMalloc(&m->pf_u, n * hid * 4)); CK(cudaMalloc(&m->pf_h, n * hid * 4));
         CK(cudaMalloc(&m->pf_down, n * dim * 4));
-        cudaFree(m->pf_scores); m->pf_scores = nullptr;
-        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * align_up(a.seq_len, 4) * 4));
+        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * sc_stride * 4));
         m->pf_cap = n;
     }
-    if (push_step(m, 0, pos, pos, 0)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
+    if (push_step(m, 0, pos, pos)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
     const float* delta = nullptr;
     const float* w_post = nullptr;
     for (size_t l = 0; l < a.n_layers; l++) {
@@ -964,7 +973,7 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
             AttnParams p{};
             p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
             p.out = m->pf_att; p.scores = m->pf_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
-            p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4); p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
+            p.gemma = gemma; p.seq_len = (int)sc_stride; p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
             p.batch = 1; p.q_stride = att;
             bool pdl = m->use_pdl; m->use_pdl = false;
             cudaError_t e = launch_attn_grid(m, p, m->l_kv_heads, T);
@@ -1033,21 +1042,20 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     m->use_graph = env_int("LMRS_B200_GRAPH", 1) != 0;
     m->use_pdl = env_int("LMRS_B200_PDL", 1) != 0;
     m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 0);
-    if (m->gemv_cfg < 0 || m->gemv_cfg > 4) m->gemv_cfg = 0;
-    m->gemv_cfg_long = env_int("LMRS_B200_GEMV_CFG_LONG", m->gemv_cfg == 0 ? 2 : m->gemv_cfg);   // 16 warps: measured ~1% of the step
-    if (m->gemv_cfg_long < 0 || m->gemv_cfg_long > 4) m->gemv_cfg_long = m->gemv_cfg;
+    if (m->gemv_cfg < 0 || m->gemv_cfg >= N_GEMV_CFG) m->gemv_cfg = 0;
     m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
+    // LL hand-over between the kernels of a step (common.cuh); the NCCL-sharded mode keeps kernel-boundary hand-overs
+    m->use_ll = env_int("LMRS_B200_LL", 1) != 0 && world == 1;
+    m->use_warm = env_int("LMRS_B200_WARM", 1) != 0;
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
     if ((int)m->args.dim > NORM_MAX_DIM) {
         lmrs_b200_destroy(m);
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
-    // default: one kernel per phase chained with programmatic dependent launch (measured faster than the persistent
-    // megakernel, whose 80 grid barriers cost ~1.3-2 us each); LMRS_B200_MEGA=1 selects the megakernel
-    m->use_mega = env_int("LMRS_B200_MEGA", 0) != 0;
     setup_attn_cluster(m);
-    if (setup_mega(m) || upload_phases(m, true)) { lmrs_b200_destroy(m); return 1; }
+    if (setup_trace(m)) { lmrs_b200_destroy(m); return 1; }
+    m->ph_decode = make_phases(m, false);
     *out = m;
     return 0;
 }
@@ -1079,7 +1087,9 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->pf_scores); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
     cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
-    cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ph_decode); cudaFree(m->d_ph_prefill); cudaFree(m->d_sd_decode); cudaFree(m->d_sd_prefill); cudaFree(m->d_bar);
+    cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ll); cudaFree(m->d_fin_scratch);
+    cudaFree(m->d_amax); cudaFree(m->d_aidx); cudaFree(m->d_ticket); cudaFree(m->d_next); cudaFree(m->d_gen);
+    if (m->h_gen) cudaFreeHost(m->h_gen);
     if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -1097,7 +1107,7 @@ extern "C" int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t
     if (token >= m->args.vocab_size) return fail("token out of range");
     if (pos >= m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
     CK(cudaSetDevice(m->device));
-    if (push_step(m, token, pos, pos, m->seq_decode++)) return 1;
+    if (push_step(m, token, pos, pos)) return 1;
     const int v = m->att_variant = attn_variant_for(m, pos);
     return run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true);
 }
@@ -1111,15 +1121,81 @@ extern "C" int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, f
     return 0;
 }
 
+// ---- greedy sampling on the device (Sampler::sample with temperature 0 -> sample_argmax, src/sampler.rs:29-41,112-113)
+static int ensure_gen(lmrs_b200* m, size_t n) {
+    if (m->gen_cap >= n) return 0;
+    cudaFree(m->d_gen); m->d_gen = nullptr;
+    if (m->h_gen) { cudaFreeHost(m->h_gen); m->h_gen = nullptr; }
+    m->gen_cap = 0;
+    CK(cudaMalloc(&m->d_gen, n * 4));
+    CK(cudaMallocHost(&m->h_gen, n * 4));
+    m->gen_cap = n;
+    return 0;
+}
+static int launch_argmax(lmrs_b200* m, uint32_t* d_out, bool advance) {
+    ArgmaxParams ap{};
+    ap.x = m->d_logits; ap.n = (int)m->args.vocab_size; ap.pmax = m->d_amax; ap.pidx = m->d_aidx; ap.ticket = m->d_ticket;
+    ap.out = d_out; ap.advance = advance ? m->d_step : nullptr;
+    int grid = (int)std::min<size_t>((size_t)m->sms, (m->args.vocab_size + 1023) / 1024);
+    if (grid < 1) grid = 1;
+    if (grid > 256) grid = 256;
+    CK(launch(m, argmax_kernel, dim3(grid), dim3(256), 0, ap));   // PDL: waits for the classifier (griddepcontrol.wait)
+    return 0;
+}
+extern "C" int lmrs_b200_forward_argmax(lmrs_b200_t* m, uint32_t token, uint32_t pos, uint32_t* next_token) {
+    if (!next_token) return fail("null argument");
+    if (m && m->world > 1) return fail("forward_argmax: single-GPU handles only");
+    if (lmrs_b200_forward_device(m, token, pos)) return 1;
+    if (ensure_gen(m, 64)) return 1;
+    if (launch_argmax(m, m->d_next, false)) return 1;
+    CK(cudaMemcpyAsync(m->h_gen, m->d_next, 4, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    *next_token = m->h_gen[0];
+    return 0;
+}
+// the generate loop of src/bin/chat.rs:188-226 at temperature 0 with the sampled token fed back ON THE DEVICE: the
+// argmax kernel writes the next step's parameters (token, pos + 1), so consecutive steps need no host round trip; the
+// host only reads the produced ids back in chunks to look for `eos` (steps enqueued past it only touch cache rows that
+// a later call overwrites).
+extern "C" int lmrs_b200_generate_greedy(lmrs_b200_t* m, uint32_t first_token, uint32_t pos, uint32_t max_new, int32_t eos,
+                                         uint32_t* out_tokens, uint32_t* n_out) {
+    if (!m || !out_tokens || !n_out) return fail("null argument");
+    if (m->world > 1) return fail("generate_greedy: single-GPU handles only");
+    if (first_token >= m->args.vocab_size) return fail("token out of range");
+    if ((size_t)pos + max_new > m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
+    CK(cudaSetDevice(m->device));
+    *n_out = 0;
+    if (max_new == 0) return 0;
+    if (ensure_gen(m, max_new)) return 1;
+    const uint32_t chunk = 32;
+    for (uint32_t i0 = 0; i0 < max_new; i0 += chunk) {
+        const uint32_t i1 = std::min(max_new, i0 + chunk);
+        for (uint32_t i = i0; i < i1; i++) {
+            if (i == 0) { if (push_step(m, first_token, pos, pos)) return 1; }
+            else next_seq(m);   // the device advanced (token, pos, seq) itself: keep the host's sequence counter in step
+            const int v = m->att_variant = attn_variant_for(m, pos + i);
+            if (run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true)) return 1;
+            if (launch_argmax(m, m->d_gen + i, true)) return 1;
+        }
+        CK(cudaMemcpyAsync(m->h_gen + i0, m->d_gen + i0, (size_t)(i1 - i0) * 4, cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        for (uint32_t i = i0; i < i1; i++) {
+            out_tokens[i] = m->h_gen[i];
+            *n_out = i + 1;
+            if (eos >= 0 && m->h_gen[i] == (uint32_t)eos) return 0;
+        }
+    }
+    return 0;
+}
+
 extern "C" int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches) {
     if (!m) return fail("null handle");
     if (pos >= m->args.seq_len) return fail("position out of range");
     CK(cudaSetDevice(m->device));
-    if (push_step(m, 0, pos, pos, m->seq_decode)) return 1;
-    int n = 0;
-    for (const MegaPhase& P : m->ph_decode)
-        if (P.kind == PH_GEMV) { CK(launch_gemv(m, m->args.q_type, P.g)); n++; }
-    if (n_launches) *n_launches = n;
+    if (push_step(m, 0, pos, pos)) return 1;
+    const uint64_t before = m->launches;
+    if (enqueue_step(m, true, /*nowait=*/true, PH_GEMV)) return 1;   // LL kernels take whatever their input buffers hold
+    if (n_launches) *n_launches = (int)(m->launches - before);
     return 0;
 }
 
@@ -1127,19 +1203,11 @@ extern "C" int lmrs_b200_bench_attn_pass(lmrs_b200_t* m, uint32_t pos, int* n_la
     if (!m) return fail("null handle");
     if (pos >= m->args.seq_len) return fail("position out of range");
     CK(cudaSetDevice(m->device));
-    if (push_step(m, 0, pos, pos, m->seq_decode)) return 1;
+    if (push_step(m, 0, pos, pos)) return 1;
     m->att_variant = attn_variant_for(m, pos);
-    const int dev_skip = env_int("LMRS_B200_DEV_SKIP", 0);   // honoured by -DLMRS_DEV_PROBES builds only
-    int n = 0;
-    for (const MegaPhase& P0 : m->ph_decode)
-        if (P0.kind == PH_ATTN) {
-            MegaPhase P = P0;
-            P.a.dev_skip = dev_skip;
-            if (m->att_variant != ATT_LEGACY) CK(launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g));
-            else CK(launch_attn(m, P.a, m->l_kv_heads));
-            n++;
-        }
-    if (n_launches) *n_launches = n;
+    const uint64_t before = m->launches;
+    if (enqueue_step(m, true, /*nowait=*/true, PH_ATTN)) return 1;
+    if (n_launches) *n_launches = (int)(m->launches - before);
     return 0;
 }
 
@@ -1207,7 +1275,7 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
         m->rows_cap = n * dim;
         for (int v = 0; v < 8; v++)
             if (m->g_prefill[v]) { cudaGraphExecDestroy(m->g_prefill[v]); m->g_prefill[v] = nullptr; }
-        if (upload_phases(m, false)) return 1;   // the phase table embeds the staging buffer's address
+        m->ph_prefill = make_phases(m, true);   // the phase table embeds the staging buffer's address
     }
     CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));
     if (prefill_batched(m, n, pos)) return 1;
@@ -1231,35 +1299,45 @@ extern "C" int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, 
 extern "C" int lmrs_b200_debug_buffer(lmrs_b200_t* m, const char* name, float* out, size_t* n) {
     if (!m || !name || !out || !n) return fail("null argument");
     const std::string nm(name);
-    const float* src = nullptr;
-    size_t cnt = 0;
-    if (nm == "x0") { src = m->d_x[0]; cnt = m->args.dim; }
-    else if (nm == "x1") { src = m->d_x[1]; cnt = m->args.dim; }
-    else if (nm == "q") { src = m->d_q; cnt = m->l_att_dim; }
-    else if (nm == "k_new") { src = m->d_knew; cnt = m->l_kv_dim; }
-    else if (nm == "att") { src = m->d_att; cnt = m->l_att_dim; }
-    else if (nm == "wo_out") { src = m->d_wo_out; cnt = m->args.dim; }
-    else if (nm == "h") { src = m->d_h; cnt = m->l_hidden; }
-    else if (nm == "down_out") { src = m->d_down_out; cnt = m->args.dim; }
-    else if (nm == "trace_reset") {   // the device-side counter restarts with every launch
+    CK(cudaSetDevice(m->device));
+    if (nm == "trace_reset") {   // the device-side counter restarts with every launch
         CK(cudaStreamSynchronize(m->stream));
         if (m->d_trace) CK(cudaMemsetAsync(m->d_trace, 0, 2 * 8192 * 8, m->stream));
         *n = 0;
         return 0;
     }
-    else if (nm == "trace") {
+    if (nm == "trace") {
         if (!m->d_trace) return fail("trace not enabled (LMRS_B200_TIMING=1)");
-        src = (const float*)m->d_trace; cnt = 2 * 8192 * 2;
+        const size_t cnt = 2 * 8192 * 2;
+        if (*n < cnt) return fail("buffer too small");
+        CK(cudaStreamSynchronize(m->stream));
+        CK(cudaMemcpy(out, m->d_trace, cnt * 4, cudaMemcpyDeviceToHost));
+        *n = cnt;
+        return 0;
     }
-    else if (nm == "timing") {   // raw 64-bit stamps viewed as pairs of floats: [n_phases][4][sms] u64
-        if (!m->d_timing) return fail("timing not enabled (LMRS_B200_TIMING=1)");
-        src = (const float*)m->d_timing; cnt = (size_t)m->ph_decode.size() * 4 * m->sms * 2;
-    }
+    // activation buffers of the LAST block: plain f32 arrays, or LL word arrays whose low halves are the values
+    const LLLayout Y0 = ll_layout(m);
+    const llword_t* lb = m->d_ll + (size_t)(m->args.n_layers - 1) * Y0.per_layer;
+    const float* src = nullptr; const llword_t* lsrc = nullptr;
+    size_t cnt = 0;
+    if (nm == "x0") { src = m->d_x[0]; lsrc = lb + Y0.xo0; cnt = m->args.dim; }
+    else if (nm == "x1") { src = m->d_x[1]; lsrc = lb + Y0.xo1; cnt = m->args.dim; }
+    else if (nm == "q") { src = m->d_q; lsrc = lb + Y0.q; cnt = m->l_att_dim; }
+    else if (nm == "k_new") { src = m->d_knew; lsrc = lb + Y0.k_new; cnt = m->l_kv_dim; }
+    else if (nm == "att") { src = m->d_att; lsrc = lb + Y0.att; cnt = m->l_att_dim; }
+    else if (nm == "wo_out") { src = m->d_wo_out; lsrc = lb + Y0.wo_out; cnt = m->args.dim; }
+    else if (nm == "h") { src = m->d_h; lsrc = lb + Y0.h; cnt = m->l_hidden; }
+    else if (nm == "down_out") { src = m->d_down_out; lsrc = lb + Y0.down_out; cnt = m->args.dim; }
     else return fail("unknown buffer name");
     if (*n < cnt) return fail("buffer too small");
-    CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
-    CK(cudaMemcpy(out, src, cnt * 4, cudaMemcpyDeviceToHost));
+    if (m->use_ll) {
+        std::vector<llword_t> w(cnt);
+        CK(cudaMemcpy(w.data(), lsrc, cnt * sizeof(llword_t), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; i++) { const uint32_t b = (uint32_t)w[i]; memcpy(&out[i], &b, 4); }
+    } else {
+        CK(cudaMemcpy(out, src, cnt * 4, cudaMemcpyDeviceToHost));
+    }
     *n = cnt;
     return 0;
 }

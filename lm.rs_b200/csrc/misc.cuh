@@ -11,29 +11,40 @@ namespace lmrs {
 // transformer block (src/transformer.rs:642-656); in the decode chain it is folded into the next GEMV prologue,
 // fill_kv_cache needs it materialised because the caller gets the residual stream back (:678).
 struct ResidualParams {
-    const float* x_in; const float* delta; const float* w_post;
+    const void* x_in; const void* delta; const float* w_post;   // f32 arrays, or LL words when ll (common.cuh)
     int n; float eps;
     float* rows;               // [n_rows][n]; row index = step->token
     const StepParams* step;
     int row_from_block;        // batched prefill: row = blockIdx.x and x_in/delta are row-strided too
+    int ll, ll_nowait;         // serial prefill inside the LL decode chain (never with row_from_block)
+    float* scratch;            // ll: [n] f32 scratch for the Gemma post-norm chain
 };
 LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
     const size_t row = p.row_from_block ? (size_t)blockIdx.x : (size_t)p.step->token;
     float* out = p.rows + row * p.n;
-    const float* x_in = p.x_in + (p.row_from_block ? row * p.n : 0);
-    const float* delta = p.delta + (p.row_from_block ? row * p.n : 0);
+    const float* x_in = reinterpret_cast<const float*>(p.x_in) + (p.row_from_block ? row * p.n : 0);
+    const float* delta = reinterpret_cast<const float*>(p.delta) + (p.row_from_block ? row * p.n : 0);
+    const uint32_t seq = p.ll ? p.step->seq : 0u;
+    if (p.ll) {   // unpack delta once (the exact chain below wants a plain array)
+        ll_canary_wait(reinterpret_cast<const llword_t*>(p.delta), seq, p.ll_nowait != 0);
+        for (int i = threadIdx.x; i < p.n; i += blockDim.x)
+            p.scratch[i] = ll_wait1(reinterpret_cast<const llword_t*>(p.delta) + i, seq, p.ll_nowait != 0);
+        __syncthreads();
+        delta = p.scratch;
+    }
     float r = 1.0f;
     if (p.w_post) r = exact_rnorm(delta, p.n, p.eps, red);   // chains read global memory directly
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-        float d = __ldcg(delta + i);
+        float d = p.ll ? delta[i] : __ldcg(delta + i);
         if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
-        out[i] = __fadd_rn(__ldcg(x_in + i), d);
+        const float xv = p.ll ? ll_wait1(reinterpret_cast<const llword_t*>(p.x_in) + i, seq, p.ll_nowait != 0) : __ldcg(x_in + i);
+        out[i] = __fadd_rn(xv, d);
     }
 }
 __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualParams p) {
     __shared__ float red[32];
     pdl_launch_dependents();
-    pdl_wait();
+    if (!p.ll) pdl_wait();
     residual_finalize_body(p, red);
 }
 
@@ -51,12 +62,13 @@ __global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_
     sm.red = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(sm.xs) + ((G * 8 + 127) / 128) * 128);
     sm.xf = sm.red + 64;
     sm.exp_tab = kExp2fTab;
-    if (p.x_in) p.x_in += row * n;
-    if (p.delta) p.delta += row * n;
-    if (p.x_out) p.x_out += row * n;
-    if (p.act_in) p.act_in += row * n;
+    if (p.x_in) p.x_in = reinterpret_cast<const float*>(p.x_in) + row * n;
+    if (p.delta) p.delta = reinterpret_cast<const float*>(p.delta) + row * n;
+    if (p.x_out) p.x_out = reinterpret_cast<float*>(p.x_out) + row * n;
+    if (p.act_in) p.act_in = reinterpret_cast<const float*>(p.act_in) + row * n;
     p.xout_all = 1;
-    gemv_prologue<1, 8>(p, sm);
+    if (p.pro == PRO_NORM) gemv_prologue<1, 8, PRO_NORM, false>(p, sm, 0u, true);
+    else gemv_prologue<1, 8, PRO_QUANT, false>(p, sm, 0u, true);
     for (int i = threadIdx.x; i < n / 16; i += 256) reinterpret_cast<int4*>(xq_out + row * n)[i] = reinterpret_cast<const int4*>(sm.xq)[i];
     for (int g = threadIdx.x; g < G; g += 256) xs_out[row * G + g] = sm.xs[g];
 }
@@ -81,6 +93,82 @@ __global__ void __launch_bounds__(256) rope_rows_kernel(float* q, float* kcache,
 __global__ void glu_rows_kernel(float* h, const float* gate, const float* up, size_t count, int epi) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count) h[i] = __fmul_rn(glu_act(epi, gate[i]), up[i]);
+}
+
+// ---- greedy sampler on the device: Sampler::sample_argmax (src/sampler.rs:29-41) -------------------------------------
+// The reference scans the logits serially with a strict `>`: the FIRST maximum wins, a NaN never replaces the running
+// maximum, and a NaN at index 0 makes every comparison false (result 0).  (value, index) pairs ordered by
+// "greater value, then lower index" reproduce that scan exactly under any reduction tree; NaNs at i >= 1 are mapped to
+// -inf (they can never win) and a NaN at index 0 is answered directly.  One launch: every CTA reduces a contiguous slice,
+// the last CTA to arrive (atomic ticket) reduces the per-CTA partials and writes the 4-byte token id.
+struct ArgmaxParams {
+    const float* x; int n;
+    float* pmax; int* pidx;        // [gridDim.x] per-CTA partials
+    unsigned* ticket;              // zero on entry, left zero
+    uint32_t* out;                 // device word the host copies back (4 bytes instead of vocab * 4)
+    StepParams* advance;           // device-side generate loop: feed the token into the next step (token, pos+1, seq+1)
+};
+LMRS_DEVINL bool argmax_better(float va, int ia, float vb, int ib) { return va > vb || (va == vb && ia < ib); }
+LMRS_DEVINL void argmax_block_reduce(float& v, int& i, float* sv, int* si) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+        if (argmax_better(ov, oi, v, i)) { v = ov; i = oi; }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sv[warp] = v; si[warp] = i; }
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < (int)(blockDim.x >> 5) ? sv[lane] : -INFINITY;
+        i = lane < (int)(blockDim.x >> 5) ? si[lane] : 0x7fffffff;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (argmax_better(ov, oi, v, i)) { v = ov; i = oi; }
+        }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(256) argmax_kernel(const ArgmaxParams p) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    __shared__ bool last;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int per = (p.n + gridDim.x - 1) / gridDim.x;
+    const int i0 = blockIdx.x * per, i1 = min(p.n, i0 + per);
+    float v = -INFINITY;
+    int idx = 0x7fffffff;
+    for (int i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
+        float t = __ldcg(p.x + i);
+        if (t != t) t = -INFINITY;
+        if (argmax_better(t, i, v, idx)) { v = t; idx = i; }
+    }
+    argmax_block_reduce(v, idx, sv, si);
+    if (threadIdx.x == 0) {
+        p.pmax[blockIdx.x] = v; p.pidx[blockIdx.x] = idx;
+        __threadfence();
+        last = atomicAdd(p.ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    v = -INFINITY; idx = 0x7fffffff;
+    for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        const float t = __ldcg(p.pmax + c);
+        const int ti = __ldcg(p.pidx + c);
+        if (argmax_better(t, ti, v, idx)) { v = t; idx = ti; }
+    }
+    argmax_block_reduce(v, idx, sv, si);
+    if (threadIdx.x == 0) {
+        const float x0 = __ldcg(p.x);
+        const uint32_t tok = (x0 != x0 || idx == 0x7fffffff) ? 0u : (uint32_t)idx;
+        *p.out = tok;
+        *p.ticket = 0u;
+        if (p.advance) { p.advance->token = tok; p.advance->pos += 1u; p.advance->mask_base = p.advance->pos; p.advance->seq += 1u; if (p.advance->seq == 0u) p.advance->seq = 1u; }
+    }
 }
 
 // ---- operator-level kernels (any group size; one thread walks one group serially like the reference) -------

@@ -12,7 +12,7 @@ PKG_ROOT = os.path.dirname(_HERE)
 ABI_SYMBOLS = [
     "lmrs_b200_create", "lmrs_b200_create_sharded", "lmrs_b200_nccl_unique_id", "lmrs_b200_destroy",
     "lmrs_b200_args", "lmrs_b200_forward", "lmrs_b200_get_embeddings", "lmrs_b200_fill_kv_cache",
-    "lmrs_b200_forward_device", "lmrs_b200_logits_device", "lmrs_b200_set_stream", "lmrs_b200_synchronize",
+    "lmrs_b200_forward_argmax", "lmrs_b200_generate_greedy", "lmrs_b200_forward_device", "lmrs_b200_logits_device", "lmrs_b200_set_stream", "lmrs_b200_synchronize",
     "lmrs_b200_kernel_launches", "lmrs_b200_bench_gemv_pass", "lmrs_b200_bench_attn_pass", "lmrs_b200_read_kv", "lmrs_b200_debug_buffer", "lmrs_b200_matmul_q8", "lmrs_b200_matmul_q4", "lmrs_b200_matmul_f32", "lmrs_b200_matmul_rest",
     "lmrs_b200_quantize_q8", "lmrs_b200_quantize_q4", "lmrs_b200_rmsnorm", "lmrs_b200_softmax",
     "lmrs_b200_last_error", "lmrs_b200_version",
@@ -57,6 +57,8 @@ def lib():
     L.lmrs_b200_destroy.restype = None
     L.lmrs_b200_args.argtypes = [vp, C.POINTER(Args)]
     L.lmrs_b200_forward.argtypes = [vp, u32, u32, C.POINTER(_f32p)]
+    L.lmrs_b200_forward_argmax.argtypes = [vp, u32, u32, C.POINTER(u32)]
+    L.lmrs_b200_generate_greedy.argtypes = [vp, u32, u32, u32, C.c_int32, vp, C.POINTER(u32)]
     L.lmrs_b200_get_embeddings.argtypes = [vp, vp, sz, vp]
     L.lmrs_b200_fill_kv_cache.argtypes = [vp, vp, sz, u32, C.POINTER(u32)]
     L.lmrs_b200_forward_device.argtypes = [vp, u32, u32]

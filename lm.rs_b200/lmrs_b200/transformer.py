@@ -33,8 +33,8 @@ def _vp(a):
 
 
 class Transformer:
-    def __init__(self, handle, args, keepalive=None):
-        self._h, self.args, self._keep = handle, args, keepalive
+    def __init__(self, handle, args, keepalive=None, world=1):
+        self._h, self.args, self._keep, self._world = handle, args, keepalive, world
 
     @classmethod
     def new(cls, data, device: int = -1):
@@ -56,7 +56,7 @@ class Transformer:
         check(lib().lmrs_b200_create_sharded(_vp(buf), buf.size, device, rank, world, idbuf, C.byref(h), C.byref(end)))
         a = Args()
         check(lib().lmrs_b200_args(h, C.byref(a)))
-        return cls(h, a), end.value
+        return cls(h, a, world=world), end.value
 
     # -- the four methods of the drop-in boundary -------------------------------------------------------------
     def forward(self, token: int, pos: int) -> np.ndarray:
@@ -64,6 +64,18 @@ class Transformer:
         out = C.POINTER(C.c_float)()
         check(lib().lmrs_b200_forward(self._h, token, pos, C.byref(out)))
         return np.ctypeslib.as_array(out, shape=(self.args.vocab_size,))
+
+    def forward_argmax(self, token: int, pos: int) -> int:
+        """forward + Sampler::sample at temperature 0 (sample_argmax, src/sampler.rs:29-41) fused on the device."""
+        nxt = C.c_uint32()
+        check(lib().lmrs_b200_forward_argmax(self._h, token, pos, C.byref(nxt)))
+        return nxt.value
+
+    def generate_greedy(self, first_token: int, pos: int, max_new: int, eos: int = -1) -> np.ndarray:
+        """chat.rs:188-226 at temperature 0, token feedback on the device; returns the picked ids (eos included)."""
+        out, n = np.zeros(max(max_new, 1), np.uint32), C.c_uint32()
+        check(lib().lmrs_b200_generate_greedy(self._h, first_token, pos, max_new, eos, _vp(out), C.byref(n)))
+        return out[: n.value].copy()
 
     def get_embeddings(self, tokens) -> np.ndarray:
         t = np.ascontiguousarray(tokens, dtype=np.uint32)
@@ -111,7 +123,7 @@ class Transformer:
         return n.value
 
     def read_kv(self, layer: int, pos0: int, n: int):
-        kvd = self.args.head_size * self.args.n_kv_heads
+        kvd = self.args.head_size * self.args.n_kv_heads // self._world   # a sharded handle holds its own KV heads only
         k, v = np.zeros((n, kvd), np.float32), np.zeros((n, kvd), np.float32)
         check(lib().lmrs_b200_read_kv(self._h, layer, pos0, n, _vp(k), _vp(v)))
         return k, v

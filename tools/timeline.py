@@ -43,7 +43,7 @@ for i in range(nl):
     s, w, pe, e = (tr[i, 0] - t0) / 1e3, (tr[i, 1] - t0) / 1e3, (tr[i, 2] - t0) / 1e3, (tr[i, 3] - t0) / 1e3
     prev_end = (tr[i - 1, 3] - t0) / 1e3
     rows.setdefault(kind, []).append((w - s, w - prev_end, pe - w, e - pe, e - prev_end))
-    if 10 <= i < 15 or i == nl - 1:
+    if 10 <= i < 21 or i == nl - 1:
         print(f"{i:4d} {kind:7s} {s:8.2f} {w:8.2f} {pe:8.2f} {e:8.2f} | {w - s:7.2f} {w - prev_end:7.2f} {pe - w:8.2f} {e - pe:7.2f} {e - prev_end:7.2f}")
 print(f"step: {(tr[-1, 3] - t0) / 1e3:.1f} us (first start -> last end)")
 print("kind      n   handoff(prev end -> all waits returned)  prologue   main    per-launch   sum")
