@@ -9,9 +9,15 @@ A "step" is one decode pass (Transformer::forward, src/transformer.rs:316) of on
 synthetic LMRS file with the real model's shapes (no weights/tokenizers exist offline).  One JSON line:
   value     HBM-resident decode throughput: K forward steps enqueued back to back on the device (token ids and the
             KV cache already in HBM), timed with CUDA events on the launching stream, max over ranks.
-  e2e       the same metric through the reference-facing call `forward(token, pos) -> host logits` (C ABI
-            lmrs_b200_forward) in a greedy generate loop like src/bin/chat.rs:188-226 with --temperature 0:
-            per step 16 B of step parameters go host->device and the vocab*4-byte logits come device->host.
+  e2e       the same metric through the public API in a greedy generate loop like src/bin/chat.rs:188-226 with
+            --temperature 0.  Headline: `forward_argmax(token, pos) -> next token` (forward + Sampler::sample_argmax fused
+            on the device, src/sampler.rs:29-41): per step 16 B of step parameters go host->device and the 4-byte token id
+            comes back.  `e2e.logits_to_host` is the same loop through `forward(token, pos) -> host logits` (vocab*4 bytes
+            device->host per step + numpy argmax), `e2e.generate_greedy` the whole loop in ONE call with the token fed
+            back on the device.
+  parity    the timed workload replayed on the CPU oracle in the same run: the residual stream returned by the
+            512-embedding fill_kv_cache and the logits of the first greedy decode steps at pos 512+, max-abs difference and
+            bit-exactness.  (The oracle is a restatement, the Rust binary cannot be built here: parity is unpinned.)
   prefill   fill_kv_cache(P embeddings) (src/transformer.rs:672) timed end to end through the C ABI.
   roofline  decode is HBM-bound: algorithmic bytes per step (lmrs_file.decode_bytes_per_token: every weight byte and
             scale once + KV rows) / step time vs MEASURED_PEAKS.json hbm_gbs.
@@ -73,8 +79,10 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
-    """The reference arm / cpu_baseline: oracle/ (C restatement of the reference's CPU path) on the host cores."""
+def cpu_reference_run(buf, a, pos0, steps, warmup, prompt, keep_logits=0):
+    """The reference arm / cpu_baseline: oracle/ (C restatement of the reference's CPU path) on the host cores.
+    keep_logits: also return the prefill residual stream and the logits of the first `keep_logits` greedy steps from
+    (prompt[pos0], pos0) -- the parity reference for the GPU arm."""
     import lmrs_ref
     lmrs_ref.build()
     m = lmrs_ref.RefTransformer(buf)
@@ -95,6 +103,12 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
     t0 = time.perf_counter()
     m.fill_kv_cache(emb, 0)
     t_prefill = time.perf_counter() - t0
+    kept = []
+    tok = int(prompt[pos0])
+    for i in range(keep_logits):      # (rows >= pos are never read: the warm-up / timed steps below simply overwrite them)
+        lg = m.forward(tok, pos0 + i).copy()
+        kept.append(lg)
+        tok = int(np.argmax(lg))
     tok = int(prompt[pos0])
     for i in range(warmup):
         tok = int(np.argmax(m.forward(tok, pos0 + i)))
@@ -103,7 +117,7 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt):
         tok = int(np.argmax(m.forward(tok, pos0 + warmup + i)))
     dt = time.perf_counter() - t0
     return {"decode_tok_s": steps / dt, "ms_per_step": dt / steps * 1e3, "prefill_tok_s": pos0 / t_prefill,
-            "cores": lmrs_ref.lib().lmrs_ref_num_threads(), "steps": steps}
+            "cores": lmrs_ref.lib().lmrs_ref_num_threads(), "steps": steps, "prefill_stream": emb, "logits": kept}
 
 
 def load_gemv_traffic(model, quant):
@@ -130,6 +144,7 @@ def main():
     ap.add_argument("--quant", type=int, default=1, help="1 = Q8_0, 2 = Q4_0")
     ap.add_argument("--pos", type=int, default=512, help="prompt length / first decode position")
     ap.add_argument("--cpu-steps", type=int, default=16, help="decode steps of the bounded cpu_baseline sample")
+    ap.add_argument("--parity-steps", type=int, default=4, help="greedy decode steps replayed on the CPU oracle (0: skip the parity block)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -201,7 +216,15 @@ def main():
     t0 = time.perf_counter()
     newpos = m.fill_kv_cache(emb, 0)
     t_prefill = time.perf_counter() - t0
+    prefill_dev_ms = m.last_prefill_device_ms()
     assert newpos == args.pos
+    # ---- parity leg (GPU side): greedy steps from (prompt[P], P), logits kept; compared with the oracle further down ----
+    gpu_logits = []
+    tok = int(prompt[args.pos])
+    for i in range(args.parity_steps):
+        lg = m.forward(tok, args.pos + i).copy()
+        gpu_logits.append(lg)
+        tok = int(np.argmax(lg))
 
     # ---- decode, HBM-resident leg ("value") --------------------------------------------------------------------
     stream = torch.cuda.Stream()       # a real (non-default) stream: the library launches on it, the events time it
@@ -222,7 +245,7 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = m.kernel_launches() - l0
-    # ---- the dominant, HBM-bound kernel by itself: only the gemv_kernel launches of a step (no attention) -----------
+    # ---- the dominant, HBM-bound kernel by itself: only the lmrs_q_matvec_kernel launches of a step (no attention) -----------
     for i in range(args.warmup):
         n_gemv = m.bench_gemv_pass(args.pos + i)
     barrier()
@@ -239,18 +262,33 @@ def main():
     ms_per_step = dev_ms / args.steps
     value = 1e3 / ms_per_step
 
-    # ---- decode, end-to-end leg: forward() -> host logits -> greedy argmax (chat.rs generate loop, temperature 0) --
-    tok = int(prompt[args.pos])
-    pos = args.pos
-    for i in range(args.warmup):
-        tok = int(np.argmax(m.forward(tok, pos + (i % args.steps)))) % a.vocab_size
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        tok = int(np.argmax(m.forward(tok, pos))) % a.vocab_size; pos += 1
-    e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); e2e_s = float(t.item())
+    # ---- decode, end-to-end legs (chat.rs generate loop, temperature 0) ---------------------------------------------
+    def timed_loop(step_fn):
+        tok = int(prompt[args.pos])
+        for i in range(args.warmup):
+            tok = step_fn(tok, args.pos + (i % args.steps))
+        barrier()
+        t0 = time.perf_counter()
+        pos = args.pos
+        for i in range(args.steps):
+            tok = step_fn(tok, pos); pos += 1
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); dt = float(t.item())
+        return dt
+    # (a) forward() -> host logits -> numpy argmax: vocab*4 bytes device->host per step
+    e2e_logits_s = timed_loop(lambda tok, pos: int(np.argmax(m.forward(tok, pos))) % a.vocab_size)
+    if world == 1:
+        # (b) headline: forward_argmax() -- the greedy pick happens on the device, 4 bytes come back
+        e2e_s = timed_loop(lambda tok, pos: m.forward_argmax(tok, pos))
+        # (c) the whole loop in one call, token fed back on the device
+        m.generate_greedy(int(prompt[args.pos]), args.pos, min(args.warmup, args.steps))
+        t0 = time.perf_counter()
+        gen = m.generate_greedy(int(prompt[args.pos]), args.pos, args.steps)
+        gen_s = time.perf_counter() - t0
+        assert len(gen) == args.steps
+    else:
+        e2e_s, gen_s = e2e_logits_s, None      # the fused sampler is single-GPU (sharded logits are gathered to every rank)
     e2e = args.steps / e2e_s
     clocks = sampler.stop()
 
@@ -264,39 +302,59 @@ def main():
     peak *= args.gpus
     mid_pos = args.pos + args.steps // 2
     alg_bytes = lf.decode_bytes_per_token(a, mid_pos)
-    w_bytes = lf.decode_bytes_per_token(a)                      # weights + scales + norm vectors: what gemv_kernel streams
+    w_bytes = lf.decode_bytes_per_token(a)                      # weights + scales + norm vectors: what lmrs_q_matvec_kernel streams
     achieved = (w_bytes / n_gemv) / (gemv_ms / n_gemv * 1e-3) / 1e9
     step_gbs = alg_bytes / (ms_per_step * 1e-3) / 1e9
     traffic, traffic_src = load_gemv_traffic(args.model, args.quant)
-    roofline = {"bound": "hbm", "kernel": f"gemv_kernel ({n_gemv} launches per step: 4 per block + classifier)",
+    roofline = {"bound": "hbm", "kernel": f"lmrs_q_matvec_kernel ({n_gemv} launches per step: 4 per block + classifier)",
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src + (f" x {args.gpus} GPUs" if args.gpus > 1 else ""),
                 "algorithmic_bytes_per_launch": w_bytes / n_gemv, "avg_launch_us": gemv_ms / n_gemv * 1e3,
-                "how": "CUDA events around the step's gemv_kernel launches alone (PDL-chained, real prologues/epilogues, attention skipped)",
+                "how": "CUDA events around the step's lmrs_q_matvec_kernel launches alone (PDL-chained, real prologues/epilogues, attention skipped)",
                 "traffic": traffic, "traffic_source": traffic_src,
                 "whole_step": {"algorithmic_bytes_per_step": alg_bytes, "achieved": step_gbs, "frac": step_gbs / peak,
                                "launches_per_step": launches / args.steps,
                                "note": "includes the latency-bound exact-order attention (not an HBM-bound kernel)"}}
     cpu = None
-    if args.gpus == 1 and args.cpu_steps > 0:
-        r = cpu_reference_run(buf, a, args.pos, args.cpu_steps, 2, prompt)
-        cpu = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
-               "sample": f"{args.cpu_steps} greedy decode steps at pos {args.pos}+ after a {args.pos}-token batched prefill",
-               "prefill_tok_s": r["prefill_tok_s"]}
+    parity = None
+    if (args.gpus == 1 and args.cpu_steps > 0) or args.parity_steps > 0:
+        cpu_steps = args.cpu_steps if args.gpus == 1 else 0
+        r = cpu_reference_run(buf, a, args.pos, max(cpu_steps, 1), 2 if cpu_steps else 0, prompt, keep_logits=args.parity_steps)
+        if cpu_steps:
+            cpu = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"{args.cpu_steps} greedy decode steps at pos {args.pos}+ after a {args.pos}-token batched prefill",
+                   "prefill_tok_s": r["prefill_tok_s"]}
+        if args.parity_steps > 0:
+            d_stream = float(np.abs(emb - r["prefill_stream"]).max())
+            d_logits = [float(np.abs(g - c).max()) for g, c in zip(gpu_logits, r["logits"])]
+            parity = {"reference": "oracle/ (C restatement of the reference's CPU path; the Rust binary cannot be built here: parity unpinned)",
+                      "prefill_residual_stream": {"rows": args.pos, "max_abs": d_stream, "bit_exact": bool(np.array_equal(emb, r["prefill_stream"]))},
+                      "decode_logits": {"positions": [args.pos + i for i in range(len(d_logits))], "max_abs": max(d_logits) if d_logits else None,
+                                        "bit_exact": bool(all(np.array_equal(g, c) for g, c in zip(gpu_logits, r["logits"]))),
+                                        "greedy_tokens_equal": bool(all(int(np.argmax(g)) == int(np.argmax(c)) for g, c in zip(gpu_logits, r["logits"])))},
+                      "max_abs": max([d_stream] + d_logits), "tolerance": 1e-3,
+                      "bit_exact": bool(np.array_equal(emb, r["prefill_stream"]) and all(np.array_equal(g, c) for g, c in zip(gpu_logits, r["logits"])))}
     print(json.dumps({
         "metric": metric, "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int8 x int8 -> int32 groups, f32 accumulate", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": a.vocab_size * 4,
-                "ms_per_step": e2e_s / args.steps * 1e3},
-        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4 if world == 1 else a.vocab_size * 4,
+                "ms_per_step": e2e_s / args.steps * 1e3,
+                "api": "forward_argmax(token, pos) -> next token (greedy pick fused on the device)" if world == 1 else "forward(token, pos) -> host logits",
+                "logits_to_host": {"value": args.steps / e2e_logits_s, "ms_per_step": e2e_logits_s / args.steps * 1e3,
+                                   "d2h_bytes_per_step": a.vocab_size * 4, "api": "forward(token, pos) -> host logits + host argmax"},
+                "generate_greedy": None if gen_s is None else {"value": args.steps / gen_s, "ms_per_step": gen_s / args.steps * 1e3,
+                                                                "api": "generate_greedy(first_token, pos, n): one call, token fed back on the device"}},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
         "prefill": {"value": args.pos / t_prefill, "unit": "tok/s", "tokens": args.pos, "ms": t_prefill * 1e3,
+                    "device_ms": prefill_dev_ms, "device_tok_s": args.pos / (prefill_dev_ms * 1e-3) if prefill_dev_ms > 0 else None,
                     "h2d_bytes": int(emb.nbytes), "d2h_bytes": int(emb.nbytes),
                     "path": "fill_kv_cache end to end through the C ABI (host embeddings in, residual stream out)",
-                    "roofline": {"bound": "tensor", "unit": "TOP/s", "achieved": lf.prefill_int8_ops(a, args.pos) / t_prefill / 1e12,
+                    "roofline": {"bound": "tensor", "unit": "TOP/s", "achieved": lf.prefill_int8_ops(a, args.pos) / (prefill_dev_ms * 1e-3) / 1e12,
                                  "peak": 4500.0, "peak_source": "nominal dense int8 (B200_PROFILING.md); MEASURED_PEAKS.json has no int8 figure",
-                                 "frac": lf.prefill_int8_ops(a, args.pos) / t_prefill / 1e12 / 4500.0,
-                                 "note": "whole fill_kv_cache time (GEMMs + exact-order attention + row kernels + PCIe copies) over the matmul ops only"}},
+                                 "frac": lf.prefill_int8_ops(a, args.pos) / (prefill_dev_ms * 1e-3) / 1e12 / 4500.0,
+                                 "end_to_end_frac": lf.prefill_int8_ops(a, args.pos) / t_prefill / 1e12 / 4500.0,
+                                 "note": "device time of the whole fill_kv_cache (GEMMs + exact-order attention + row kernels, CUDA events) over the matmul ops only; end_to_end_frac includes the PCIe copies"}},
         "published_reference": {"value": 50, "unit": "tok/s", "hardware": "16-core AMD Epyc (README.md:38)"} if args.model == "llama-3.2-1b" and args.quant == 1 else None,
     }))
     if dist is not None:

@@ -102,6 +102,9 @@ int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches);
 /* same for the attention launches (one per block) of a decode step at position `pos`; rewrites K row `pos` of every
  * layer from whatever the staging row holds, so only call it on a handle used for measurement. */
 int lmrs_b200_bench_attn_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches);
+/* measurement aid: device time (CUDA events on the handle's stream) of the kernels of the last fill_kv_cache call, host
+ * copies excluded; -1 before the first call */
+int lmrs_b200_last_prefill_device_ms(const lmrs_b200_t* m, float* ms);
 /* test access: copy K and V rows [pos0, pos0+n) of one layer to host (f32 [n][kv_dim] each) */
 int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out);
 /* test access: copy one activation buffer of the LAST executed block to host.  name: "x0","x1" (residual

@@ -56,7 +56,7 @@ struct GemvParams {
     int pro, epi;      // host-side dispatch (the kernels are specialised on both)
     int ll;            // host-side dispatch: activation pointers below are LL word arrays (llword_t) instead of f32 arrays
     int ll_nowait;     // LL measurement passes: do not wait for the sequence number
-    int warm;          // run the prologue and the first stage once on dummy data BEFORE waiting for the inputs (see the kernel)
+    int pre_stages;    // plain mode: ring stages requested BEFORE griddepcontrol.wait (the rest right after it)
     // activations in/out: `const float*` in plain mode, `const llword_t*` in LL mode (same element indexing)
     const void* x_in; const void* delta; const float* w_post; const float* w_norm; void* x_out;
     int x_in_plain;    // LL mode: x_in is nevertheless a plain f32 array (serial prefill: the staged embedding rows)
@@ -118,7 +118,7 @@ template <int QT, int WARPS, int DEPTH> inline size_t gemv_smem_bytes(int n, boo
     size_t ring = (size_t)WARPS * DEPTH * gemv_stage_bytes<QT>();
     size_t xq = (size_t)n;                         // Q8: n codes; Q4: n/2 even + n/2 odd signed bytes
     size_t xs = (size_t)(n / GS) * 4 * 2;          // scales + per-group code sums (Q4)
-    size_t xf = norm ? (size_t)n * 4 : 0;          // PRO_NORM: f32 staging of the vector being normed
+    size_t xf = norm ? (size_t)n * 4 + 128 : 0;    // PRO_NORM: staging of the squares, eight padded chain rows (exact_rnorm_t)
     return ring + ((xq + 127) / 128) * 128 + ((xs + 127) / 128) * 128 + 64 * 4 + (size_t)WARPS * DEPTH * 8 + 128 + xf + 256;
 }
 
@@ -229,6 +229,52 @@ LMRS_DEVINL void quantize_group_to_smem(float4 y, int g, uint8_t* xq, float* xs,
 }
 
 
+// The same chain on a TRANSPOSED staging of the squares (what the GEMV prologues use): the owner of element e = 8j + k
+// stores x[e]*x[e] (the reference's unfused product, src/functional.rs:56) at row k, column j of eight rows padded to
+// n/8 + 4 floats, so chain k reads ITS products as consecutive float4 (one LDS.128 per four dependent adds, the eight
+// lanes on distinct banks) instead of one strided scalar load per add: the chain runs at the dependent-add latency.
+LMRS_DEVINL int rnorm_t_stride(int n) { return n / 8 + 4; }
+LMRS_DEVINL void rnorm_t_stage4(float* xt, int n, int c, float4 v) {   // chunk c = elements 4c .. 4c+3
+    const int st = rnorm_t_stride(n), k0 = 4 * (c & 1), j = c >> 1;
+    xt[(k0 + 0) * st + j] = __fmul_rn(v.x, v.x); xt[(k0 + 1) * st + j] = __fmul_rn(v.y, v.y);
+    xt[(k0 + 2) * st + j] = __fmul_rn(v.z, v.z); xt[(k0 + 3) * st + j] = __fmul_rn(v.w, v.w);
+}
+LMRS_DEVINL float exact_rnorm_t(const float* xt, int n, float eps, float* red) {   // n % 128 == 0
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float s = 0.0f;
+        if (lane < 8) {
+            const float4* row = reinterpret_cast<const float4*>(xt + lane * rnorm_t_stride(n));
+            const int nq = n / 32;   // float4 per chain; a multiple of 4
+            float4 a0 = row[0], a1 = row[1], a2 = row[2], a3 = row[3];
+            for (int q = 4; q < nq; q += 4) {   // loads run four float4 (16 adds = 64 cycles) ahead of the chain
+                const float4 b0 = row[q], b1 = row[q + 1], b2 = row[q + 2], b3 = row[q + 3];
+                s = __fadd_rn(s, a0.x); s = __fadd_rn(s, a0.y); s = __fadd_rn(s, a0.z); s = __fadd_rn(s, a0.w);
+                s = __fadd_rn(s, a1.x); s = __fadd_rn(s, a1.y); s = __fadd_rn(s, a1.z); s = __fadd_rn(s, a1.w);
+                s = __fadd_rn(s, a2.x); s = __fadd_rn(s, a2.y); s = __fadd_rn(s, a2.z); s = __fadd_rn(s, a2.w);
+                s = __fadd_rn(s, a3.x); s = __fadd_rn(s, a3.y); s = __fadd_rn(s, a3.z); s = __fadd_rn(s, a3.w);
+                a0 = b0; a1 = b1; a2 = b2; a3 = b3;
+            }
+            s = __fadd_rn(s, a0.x); s = __fadd_rn(s, a0.y); s = __fadd_rn(s, a0.z); s = __fadd_rn(s, a0.w);
+            s = __fadd_rn(s, a1.x); s = __fadd_rn(s, a1.y); s = __fadd_rn(s, a1.z); s = __fadd_rn(s, a1.w);
+            s = __fadd_rn(s, a2.x); s = __fadd_rn(s, a2.y); s = __fadd_rn(s, a2.z); s = __fadd_rn(s, a2.w);
+            s = __fadd_rn(s, a3.x); s = __fadd_rn(s, a3.y); s = __fadd_rn(s, a3.z); s = __fadd_rn(s, a3.w);
+        }
+        const float t = __fadd_rn(s, __shfl_sync(0xffffffffu, s, (lane + 4) & 31));   // lanes 0..3: a_l + a_{l+4}
+        const float u = __fadd_rn(t, __shfl_sync(0xffffffffu, t, (lane + 2) & 31));   // lane 0: s0+s2, lane 1: s1+s3
+        float ss = __fadd_rn(u, __shfl_sync(0xffffffffu, u, (lane + 1) & 31));        // lane 0: (s0+s2)+(s1+s3)
+        if (lane == 0) {
+            ss = __fdiv_rn(ss, (float)n);
+            ss = __fadd_rn(ss, eps);
+            red[0] = __fdiv_rn(1.0f, __fsqrt_rn(ss));
+        }
+    }
+    __syncthreads();
+    const float r = red[0];
+    __syncthreads();
+    return r;
+}
+
 // ---- shared-memory views of one CTA -----------------------------------------------------------------------------
 struct GemvSmem {
     uint8_t* xq;    // quantized activation (Q8: n codes; Q4: n/2 even + n/2 odd signed bytes)
@@ -334,9 +380,8 @@ template <bool LL> LMRS_DEVINL void act_store(void* base, size_t i, float v, uin
 }
 
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
-// `real == false`: the warm-up pass -- same instructions on zeros, no waits, no loads of upstream data, no global stores
 template <int QT, int WARPS, int PRO, bool LL>
-LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const uint32_t seq, const bool real) {
+LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const uint32_t seq) {
     constexpr int THREADS = WARPS * 32;
     constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -355,13 +400,6 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
                 wnv[k] = c < nchunks ? wn[c] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
-        if (!real) {
-#pragma unroll
-            for (int k = 0; k < NORM_MAXC; k++) v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        } else {
-        if constexpr (!LL) pdl_wait();   // plain mode: upstream activations are complete and visible from here on
-        // LL: the pending residual contribution is this kernel's freshest input -- park the CTA on one of its words
-        if (LL && p.delta) ll_canary_wait(reinterpret_cast<const llword_t*>(p.delta), seq, nowait);
         if (p.emb_q) {   // embedding row dequantized on the fly: code as f32 * scale (src/quantization.rs:25-42)
             const uint32_t tok = p.step->token;
 #pragma unroll
@@ -410,10 +448,10 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
                     const int c = tid + k * THREADS;
-                    if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = dv[k];
+                    if (c < nchunks) rnorm_t_stage4(sm.xf, n, c, dv[k]);
                 }
                 __syncthreads();
-                const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);
+                const float r = exact_rnorm_t(sm.xf, n, p.eps, sm.red);
 #pragma unroll
                 for (int k = 0; k < NORM_MAXC; k++) {
                     const int c = tid + k * THREADS;
@@ -432,8 +470,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
                 v[k].z = __fadd_rn(v[k].z, dv[k].z); v[k].w = __fadd_rn(v[k].w, dv[k].w);
             }
         }
-        }   // real
-        if (real && p.x_out && (blockIdx.x == 0 || p.xout_all)) {  // decode: exactly one CTA publishes the updated residual stream
+        if (p.x_out && (blockIdx.x == 0 || p.xout_all)) {  // decode: exactly one CTA publishes the updated residual stream
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
                 const int c = tid + k * THREADS;
@@ -446,13 +483,13 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
             const int c = tid + k * THREADS;
-            if (c < nchunks) reinterpret_cast<float4*>(sm.xf)[c] = v[k];
+            if (c < nchunks) rnorm_t_stage4(sm.xf, n, c, v[k]);
         }
         __syncthreads();
-        if (real && lane == 0) ktrace_c(p.trace_slot, 4, cP);   // inputs loaded, residual formed
+        if (lane == 0) ktrace_c(p.trace_slot, 4, cP);   // inputs loaded, residual formed
         trace_event(110);
-        const float r = exact_rnorm(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
-        if (real && lane == 0) ktrace_c(p.trace_slot, 5, cP);   // 1/rms known
+        const float r = exact_rnorm_t(sm.xf, n, p.eps, sm.red);   // src/functional.rs:48-62, exact order
+        if (lane == 0) ktrace_c(p.trace_slot, 5, cP);   // 1/rms known
         trace_event(111);
 #pragma unroll
         for (int k = 0; k < NORM_MAXC; k++) {
@@ -473,16 +510,9 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
             }
         }
     } else if constexpr (PRO == PRO_QUANT) {
-        if (real) {
-            if constexpr (LL) ll_canary_wait(reinterpret_cast<const llword_t*>(p.act_in), seq, nowait);
-            else pdl_wait();
-        }
         for (int g0 = warp; g0 < G; g0 += WARPS * 8) {   // 8 groups per warp in flight: one L2 round trip, not eight
             float4 y[8];
-            if (!real) {
-#pragma unroll
-                for (int u = 0; u < 8; u++) y[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            } else if constexpr (LL) {
+            if constexpr (LL) {
                 const llword_t* ain = reinterpret_cast<const llword_t*>(p.act_in);
                 bool done[8];
 #pragma unroll
@@ -514,8 +544,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
                 if (g < G) quantize_group_to_smem<QT>(y[u], g, sm.xq, sm.xs, sm.xsum, n);
             }
         }
-    } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales (never warmed)
-        pdl_wait();
+    } else {  // PRO_RAW: caller-supplied codes (Q8: i8[n]; Q4: packed nibbles u8[n/2]) and scales
         if (QT == 1) {
             const uint32_t* src = reinterpret_cast<const uint32_t*>(p.raw_q);
             for (int i = tid; i < n / 4; i += THREADS) reinterpret_cast<uint32_t*>(sm.xq)[i] = src[i];
@@ -536,7 +565,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
         }
     }
     __syncthreads();
-    if (real && lane == 0) ktrace_c(p.trace_slot, 6, cP);       // quantized activations in shared memory
+    if (lane == 0) ktrace_c(p.trace_slot, 6, cP);       // quantized activations in shared memory
     trace_event(119);
 }
 
@@ -571,8 +600,7 @@ LMRS_DEVINL float glu_act(int epi, float val, const uint64_t* exp_tab = kExp2fTa
     return __fmul_rn(val, __fdiv_rn(1.0f, __fadd_rn(1.0f, expf_glibc_t(-val, exp_tab))));   // SiLU (:617), exp = glibc expf
 }
 template <int EPI, bool LL>
-LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos, uint32_t seq, const bool dry) {
-    if (dry) return;
+LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos, uint32_t seq) {
     if constexpr (EPI == EPI_QKV) {
         if (row < p.att_dim) act_store<LL>(p.out, row, v, seq);
         else if (row < p.att_dim + p.kv_dim) act_store<LL>(p.out_k, row - p.att_dim, v, seq);
@@ -591,7 +619,7 @@ LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos, 
 }
 template <int QT, int EPI, bool LL>
 LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, int s, const uint8_t* buf, const GemvSmem& sm,
-                               Consumer<QT>& c, uint32_t pos, uint32_t seq, const bool dry) {
+                               Consumer<QT>& c, uint32_t pos, uint32_t seq) {
     constexpr int QB = QTraits<QT>::QB;
     constexpr bool GLU = (EPI == EPI_GLU_SILU || EPI == EPI_GLU_GELU);
     const int lane = threadIdx.x & 31, half = lane >> 4, l16 = lane & 15;
@@ -652,12 +680,9 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
         const bool row_done = (c.g_base + SG == G);
         if constexpr (GLU) {
             const float up = __shfl_sync(0xffffffffu, a, 16);
-            if (row_done && lane == 0 && valid) {
-                const float hv = __fmul_rn(glu_act(EPI, a, sm.exp_tab), up);
-                if (!dry) act_store<LL>(p.out, rr.row0 + row_l, hv, seq);
-            }
+            if (row_done && lane == 0 && valid) act_store<LL>(p.out, rr.row0 + row_l, __fmul_rn(glu_act(EPI, a, sm.exp_tab), up), seq);
         } else if (row_done && l16 == 0 && valid) {
-            store_row<EPI, LL>(p, rr.row0 + row_l, a, pos, seq, dry);
+            store_row<EPI, LL>(p, rr.row0 + row_l, a, pos, seq);
         }
         c.g_base += SG;
         if (c.g_base == G) { c.g_base = 0; c.row_l++; }
@@ -676,12 +701,9 @@ LMRS_DEVINL void consume_stage(const GemvParams& p, const WarpStreams<QT>& w, in
     c.acc = acc;
     if constexpr (GLU) {
         const float up = __shfl_sync(0xffffffffu, mine, l16 + 16);
-        if (is_last && half == 0) {
-            const float hv = __fmul_rn(glu_act(EPI, mine, sm.exp_tab), up);
-            if (!dry) act_store<LL>(p.out, rr.row0 + row_l, hv, seq);
-        }
+        if (is_last && half == 0) act_store<LL>(p.out, rr.row0 + row_l, __fmul_rn(glu_act(EPI, mine, sm.exp_tab), up), seq);
     } else if (is_last) {
-        store_row<EPI, LL>(p, rr.row0 + row_l, mine, pos, seq, dry);
+        store_row<EPI, LL>(p, rr.row0 + row_l, mine, pos, seq);
     }
 }
 
@@ -699,8 +721,11 @@ LMRS_DEVINL GemvSmem carve_gemv_smem(uint8_t* base, int n, int n_bars) {
 }
 
 // the quantized matrix-vector kernel (name chosen not to collide with library GEMV symbols in launch classifiers)
+#ifndef LMRS_GEMV_MINB
+#define LMRS_GEMV_MINB 2   // CTAs per SM the register allocation must allow: 2 = consecutive kernels of the chain co-reside
+#endif
 template <int QT, int WARPS, int DEPTH, int PRO, int EPI, bool LL>
-__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) lmrs_q_matvec_kernel(const GemvParams p) {
+__global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? LMRS_GEMV_MINB : 1) lmrs_q_matvec_kernel(const GemvParams p) {
     constexpr int STAGE = gemv_stage_bytes<QT>();
     extern __shared__ __align__(128) uint8_t smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -718,43 +743,50 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? 2 : 1) lmrs_q_matvec_
     }
     __syncwarp();
     const uint64_t pol = l2_policy_evict_first();
-    if (lane == 0)   // weights never depend on the previous kernel: start streaming before anything else
-        for (int s = 0; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     const long long c0 = ktrace_c0();
     if (blockIdx.x == 0 && threadIdx.x == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
+    const uint32_t seq = LL ? p.step->seq : 0u;
+    // LL mode: the kernel is resident long before its inputs exist.  It parks on ONE word of its freshest input (the pending
+    // residual contribution / the activation to quantize) and only then starts streaming: a weight prefetch issued at CTA
+    // start lands in the middle of the PREVIOUS kernel's latency-bound stream and delays it by more than it saves here
+    // (measured: co-resident prefetching kernels cost ~60 us per step), while after the canary it overlaps this kernel's
+    // own prologue.  Plain mode: stream first, then griddepcontrol.wait (inside the prologue).
+    if constexpr (LL) {
+        const void* fresh = PRO == PRO_NORM ? p.delta : (PRO == PRO_QUANT ? p.act_in : nullptr);
+        if (fresh) ll_canary_wait(reinterpret_cast<const llword_t*>(fresh), seq, p.ll_nowait != 0);
+    }
+    // Plain mode: weights never depend on the previous kernel, but what is requested before the dependency wait competes
+    // with the previous kernel's last, latency-bound stages; `pre_stages` of the ring are requested now, the others right
+    // after the wait (they still land during this kernel's prologue).
+    const int pre = LL ? DEPTH : min(p.pre_stages, DEPTH);
+    if (lane == 0)
+        for (int s = 0; s < pre && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
+    if constexpr (!LL) {
+        pdl_wait();   // upstream activations are complete and visible from here on
+        if (lane == 0)
+            for (int s = pre; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
+    }
     if constexpr (EPI == EPI_GLU_SILU) {   // expf table -> shared memory (last 256 B), by the LAST warp, after the weight prefetch was issued
-        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (PRO == PRO_NORM ? (size_t)p.n * 4 : 0));
+        uint64_t* tab = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm.xf) + (PRO == PRO_NORM ? (size_t)p.n * 4 + 128 : 0));
         if (warp == WARPS - 1) tab[lane] = kExp2fTab[lane];
         sm.exp_tab = tab;
     }
-    // Plain mode: upstream activations are complete and visible after griddepcontrol.wait (inside the prologue's real
-    // pass).  LL mode: no wait at all -- the prologue polls the activation words; the step parameters were written before
-    // the step's first (ordinary) launch.
-    // Warm-up pass (p.warm): a kernel of the chain is resident microseconds before its inputs exist, and every launch
-    // starts on a cold instruction cache (five different kernels per block evict each other; round 1 measured the exact
-    // rmsnorm chain at 5093 cycles cold against 2858 warm).  So the SAME loop body runs once on zeros first -- prologue,
-    // first ring stage, epilogue arithmetic, stores suppressed -- and the real pass finds its instructions cached.
-    const uint32_t seq = LL ? p.step->seq : 0u;
+    // LL mode: no dependency wait at all -- the prologue polls the activation words; the step parameters were written before
+    // the step's first (ordinary) launch.  (A warm-up pass that ran prologue + first stage on dummy data before the inputs arrive, to prime
+    // the instruction cache, measured no gain and was removed.)
     if (lane == 0) { ktrace(p.trace_slot, 1); ktrace_c(p.trace_slot, 1, c0); }
-    uint32_t pos = 0u;
-#pragma unroll 1
-    for (int pass = (p.warm && PRO != PRO_RAW) ? 0 : 1; pass < 2; pass++) {
-        const bool real = pass == 1;
-        gemv_prologue<QT, WARPS, PRO, LL>(p, sm, seq, real);
-        if (real && lane == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 2, c0); }
-        if (real && EPI == EPI_QKV && !LL) pos = p.step->pos;
-        Consumer<QT> cs;
-        consumer_begin<QT>(cs, w, sm);
-        const int nst = real ? w.nst : min(w.nst, 1);
-        for (int s = 0; s < nst; s++) {
-            const int d = s % DEPTH;
-            mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
-            consume_stage<QT, EPI, LL>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, cs, pos, seq, !real);
-            __syncwarp();
-            if (real && lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
-        }
-        if (!real) __syncthreads();   // nobody re-stages the activation while a warp still reads the dummy one
+    gemv_prologue<QT, WARPS, PRO, LL>(p, sm, seq);
+    if (lane == 0) { ktrace(p.trace_slot, 2); ktrace_c(p.trace_slot, 2, c0); }
+    const uint32_t pos = (EPI == EPI_QKV && !LL) ? p.step->pos : 0u;
+    Consumer<QT> cs;
+    consumer_begin<QT>(cs, w, sm);
+    for (int s = 0; s < w.nst; s++) {
+        const int d = s % DEPTH;
+        mbar_wait(&bars[d], (uint32_t)((s / DEPTH) & 1));
+        consume_stage<QT, EPI, LL>(p, w, s, ring + (size_t)(warp * DEPTH + d) * STAGE, sm, cs, pos, seq);
+        __syncwarp();
+        if (lane == 0 && s + DEPTH < w.nst) issue_stage<QT>(w, s + DEPTH, ring + (size_t)(warp * DEPTH + d) * STAGE, &bars[d], pol);
     }
     if (lane == 0) { ktrace(p.trace_slot, 3); ktrace_c(p.trace_slot, 3, c0); }
 }

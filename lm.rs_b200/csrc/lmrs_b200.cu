@@ -20,6 +20,7 @@
 #include "gemm.cuh"
 #include "gemv.cuh"
 #include "misc.cuh"
+#include "prefill_attn.cuh"
 #include "f32_ops.cuh"
 #include "shard.h"
 
@@ -91,6 +92,7 @@ struct lmrs_b200 {
     uint8_t* pf_xq = nullptr;
     float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr, *pf_scores = nullptr;
     bool use_gemm = true;
+    bool use_pf_attn = true;   // batched-rows attention as throughput kernels (prefill_attn.cuh); 0: the per-row decode kernel
     size_t rows_cap = 0;
     StepParams* d_step = nullptr;
     StepParams* h_step_ring = nullptr;  // pinned
@@ -107,8 +109,9 @@ struct lmrs_b200 {
     llword_t* d_ll = nullptr;
     size_t ll_words = 0;
     bool use_ll = true;
-    bool use_warm = true;   // instruction-cache warm-up pass in the chain's kernels (gemv.cuh)
     uint32_t step_seq = 0;
+    cudaEvent_t ev_pf0 = nullptr, ev_pf1 = nullptr;   // device time of the last fill_kv_cache (kernels only, copies excluded)
+    float last_prefill_ms = -1.0f;
     float* d_fin_scratch = nullptr;
     std::map<const void*, size_t> smem_optin;   // per handle (= per device): kernels whose >48 KB opt-in has been set
     // one CUDA graph per attention variant: 0..5 = cluster attention variants (setup_attn_cluster), 7 = single-CTA kernel
@@ -169,8 +172,8 @@ static cudaError_t smem_optin(lmrs_b200* m, const void* fn, size_t smem) {
 // ---- GEMV dispatch ----------------------------------------------------------------------------------------
 // ring geometries (warps, stages per warp); 8 warps x <= 128 registers: two CTAs (consecutive kernels of the chain) per SM
 struct GemvCfg { int warps, depth; };
-static const GemvCfg kGemvCfgs[] = {{8, 2}, {8, 3}};
-constexpr int N_GEMV_CFG = 2;
+static const GemvCfg kGemvCfgs[] = {{8, 2}, {8, 3}, {8, 4}, {16, 2}, {16, 3}};
+constexpr int N_GEMV_CFG = 5;
 typedef void (*gemv_fn)(const GemvParams);
 template <int QT, int W, int D, bool LL> static gemv_fn gemv_kernel_pe(int pro, int epi) {
     if (pro == PRO_RAW) return LL ? nullptr : (gemv_fn)lmrs_q_matvec_kernel<QT, W, D, PRO_RAW, EPI_STORE, false>;
@@ -185,10 +188,19 @@ template <int QT, int W, int D, bool LL> static gemv_fn gemv_kernel_pe(int pro, 
 }
 template <int QT> static gemv_fn gemv_kernel_for(int cfg, int pro, int epi, bool ll) {
     if (cfg == 1) return ll ? gemv_kernel_pe<QT, 8, 3, true>(pro, epi) : gemv_kernel_pe<QT, 8, 3, false>(pro, epi);
+    if (cfg == 2) return ll ? gemv_kernel_pe<QT, 8, 4, true>(pro, epi) : gemv_kernel_pe<QT, 8, 4, false>(pro, epi);
+    if (cfg == 3) return ll ? gemv_kernel_pe<QT, 16, 2, true>(pro, epi) : gemv_kernel_pe<QT, 16, 2, false>(pro, epi);
+    if (cfg == 4) return ll ? gemv_kernel_pe<QT, 16, 3, true>(pro, epi) : gemv_kernel_pe<QT, 16, 3, false>(pro, epi);
     return ll ? gemv_kernel_pe<QT, 8, 2, true>(pro, epi) : gemv_kernel_pe<QT, 8, 2, false>(pro, epi);
 }
 template <int QT> static size_t gemv_smem_for(int cfg, int n, bool norm) {
-    return cfg == 1 ? gemv_smem_bytes<QT, 8, 3>(n, norm) : gemv_smem_bytes<QT, 8, 2>(n, norm);
+    switch (cfg) {
+        case 1: return gemv_smem_bytes<QT, 8, 3>(n, norm);
+        case 2: return gemv_smem_bytes<QT, 8, 4>(n, norm);
+        case 3: return gemv_smem_bytes<QT, 16, 2>(n, norm);
+        case 4: return gemv_smem_bytes<QT, 16, 3>(n, norm);
+        default: return gemv_smem_bytes<QT, 8, 2>(n, norm);
+    }
 }
 // stream boundaries must fall on BP16 block boundaries: row0 * G must be a multiple of 16 groups
 static int gran_for(int n) {
@@ -209,11 +221,16 @@ static cudaError_t repack_bp16(int q_type, uint8_t* dst, const uint8_t* src_q, c
 }
 
 static cudaError_t launch_gemv(lmrs_b200* m, int q_type, GemvParams p) {
-    const int cfg = m->gemv_cfg;
+    static const int cfg_long = env_int("LMRS_B200_GEMV_CFG_LONG", -1);   // developer knob: geometry of the down projection
+    const int cfg = (cfg_long >= 0 && cfg_long < N_GEMV_CFG && p.pro == PRO_QUANT && p.n >= 4096) ? cfg_long : m->gemv_cfg;
     const GemvCfg c = kGemvCfgs[cfg];
     gemv_fn fn = q_type == 1 ? gemv_kernel_for<1>(cfg, p.pro, p.epi, p.ll != 0) : gemv_kernel_for<2>(cfg, p.pro, p.epi, p.ll != 0);
     if (!fn) return cudaErrorInvalidValue;
     size_t smem = q_type == 1 ? gemv_smem_for<1>(cfg, p.n, p.pro == PRO_NORM) : gemv_smem_for<2>(cfg, p.n, p.pro == PRO_NORM);
+    static const int pre_stages = env_int("LMRS_B200_PRE", 99);   // developer knob: ring stages requested before the dependency wait
+    p.pre_stages = pre_stages;
+    static const int pad_kb = env_int("LMRS_B200_GEMV_PAD_KB", 0);   // developer knob: unused shared memory (limits co-residency)
+    smem += (size_t)pad_kb * 1024;
     cudaError_t se = smem_optin(m, (const void*)fn, smem);
     if (se != cudaSuccess) return se;
     int grid = m->sms * m->gemv_ctas_per_sm;
@@ -712,7 +729,6 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
         P.g = gemv_base(A, B);
         P.g.step = m->d_step;
         P.g.ll = ll;
-        P.g.warm = m->use_warm;
         return P;
     };
     for (size_t l = 0; l < L; l++) {
@@ -908,6 +924,31 @@ static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
     return 0;
 }
 
+// batched-rows attention (prefill_attn.cuh): scores + softmax per (token, head) thread, then a*v per (token, head, 8 dims) thread
+template <int HS> static int launch_prefill_attn_t(lmrs_b200* m, const PrefillAttnParams& p, int n_kv_heads) {
+    const int TB = PFA_THREADS / p.kv_mul;
+    CK(smem_optin(m, (const void*)prefill_scores_kernel<HS>, prefill_scores_smem<HS>()));
+    prefill_scores_kernel<HS><<<dim3((unsigned)((p.n + TB - 1) / TB), (unsigned)n_kv_heads), PFA_THREADS, prefill_scores_smem<HS>(), m->stream>>>(p);
+    m->launches++;
+    CK(cudaGetLastError());
+    const int TBV = prefill_av_tokens(HS, p.kv_mul), pairs = TBV * p.kv_mul;
+    const int threads = (pairs * (HS / 8) + 31) / 32 * 32;
+    CK(smem_optin(m, (const void*)prefill_av_kernel<HS>, prefill_av_smem<HS>(pairs)));
+    prefill_av_kernel<HS><<<dim3((unsigned)((p.n + TBV - 1) / TBV), (unsigned)n_kv_heads), threads, prefill_av_smem<HS>(pairs), m->stream>>>(p, TBV);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+static int launch_prefill_attn(lmrs_b200* m, const PrefillAttnParams& p, int n_kv_heads) {
+    switch (m->args.head_size) {
+        case 64: return launch_prefill_attn_t<64>(m, p, n_kv_heads);
+        case 96: return launch_prefill_attn_t<96>(m, p, n_kv_heads);
+        case 128: return launch_prefill_attn_t<128>(m, p, n_kv_heads);
+        case 256: return launch_prefill_attn_t<256>(m, p, n_kv_heads);
+        default: return fail("unsupported head_size");
+    }
+}
+
 static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
     if (!m->use_gemm || n < 8 || pos + n > (size_t)ATT_SC_CAP) return false;
     for (const Layer& Y : m->layers)
@@ -918,7 +959,7 @@ static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
 
 static int launch_rows_prologue(lmrs_b200* m, GemvParams p, int T) {
     const int n = p.n, G = n / GS;
-    size_t smem = (size_t)((n + 127) / 128) * 128 + (size_t)((G * 8 + 127) / 128) * 128 + 64 * 4 + (p.pro == PRO_NORM ? (size_t)n * 4 : 0) + 128;
+    size_t smem = (size_t)((n + 127) / 128) * 128 + (size_t)((G * 8 + 127) / 128) * 128 + 64 * 4 + (p.pro == PRO_NORM ? (size_t)n * 4 + 128 : 0) + 128;
     static thread_local size_t set_for = 0;
     if (smem > set_for) { CK(cudaFuncSetAttribute(rows_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_for = smem; }
     rows_prologue_kernel<<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
@@ -969,7 +1010,13 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
         rope_rows_kernel<<<T, 256, 0, m->stream>>>(m->pf_q, kc, m->d_rope_cos, m->d_rope_sin, m->l_heads, m->l_kv_heads, a.head_size, (int)pos);
         m->launches++;
         CK(cudaGetLastError());
-        {
+        if (m->use_pf_attn) {
+            PrefillAttnParams p{};
+            p.q = m->pf_q; p.kcache = kc; p.vcache = vc; p.probs = m->pf_scores; p.out = m->pf_att;
+            p.n = T; p.pos = (int)pos; p.t_cap = (int)sc_stride; p.att_dim = att; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads;
+            p.gemma = gemma; p.mask_base = pos; p.sqrt_hs = sqrtf((float)a.head_size);
+            if (launch_prefill_attn(m, p, m->l_kv_heads)) return 1;
+        } else {
             AttnParams p{};
             p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
             p.out = m->pf_att; p.scores = m->pf_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
@@ -1041,12 +1088,18 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     m->rank = rank; m->world = world;
     m->use_graph = env_int("LMRS_B200_GRAPH", 1) != 0;
     m->use_pdl = env_int("LMRS_B200_PDL", 1) != 0;
-    m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 0);
+    // ring geometry: 16 warps x 2 stages measured best for the decode chain (profiles/r2_decode_experiments.md): the exact-
+    // order prologues and the per-stage scans are latency chains that want warps, deeper rings measured slower
+    m->gemv_cfg = env_int("LMRS_B200_GEMV_CFG", 3);
     if (m->gemv_cfg < 0 || m->gemv_cfg >= N_GEMV_CFG) m->gemv_cfg = 0;
     m->gemv_ctas_per_sm = env_int("LMRS_B200_GEMV_CTAS", 1);
-    // LL hand-over between the kernels of a step (common.cuh); the NCCL-sharded mode keeps kernel-boundary hand-overs
-    m->use_ll = env_int("LMRS_B200_LL", 1) != 0 && world == 1;
-    m->use_warm = env_int("LMRS_B200_WARM", 1) != 0;
+    // Hand-over between the kernels of a step.  Default: kernel boundaries (programmatic dependent launch +
+    // griddepcontrol.wait), one matrix-vector CTA per SM.  LMRS_B200_LL=1: fence-free LL exchange between co-resident
+    // kernels (common.cuh) -- bit-identical and covered by the tests, but measured SLOWER on B200 (an L2 round trip costs
+    // 0.3-0.6 us, a hand-over needs two or three of them, and co-resident waiting kernels slow the running one; see
+    // profiles/r2_decode_experiments.md), so it is opt-in.
+    m->use_ll = env_int("LMRS_B200_LL", 0) != 0 && world == 1;
+    m->use_pf_attn = env_int("LMRS_B200_PF_ATTN", 1) != 0;
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
     if ((int)m->args.dim > NORM_MAX_DIM) {
         lmrs_b200_destroy(m);
@@ -1090,6 +1143,8 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ll); cudaFree(m->d_fin_scratch);
     cudaFree(m->d_amax); cudaFree(m->d_aidx); cudaFree(m->d_ticket); cudaFree(m->d_next); cudaFree(m->d_gen);
     if (m->h_gen) cudaFreeHost(m->h_gen);
+    if (m->ev_pf0) cudaEventDestroy(m->ev_pf0);
+    if (m->ev_pf1) cudaEventDestroy(m->ev_pf1);
     if (m->h_step_ring) cudaFreeHost(m->h_step_ring);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->own_stream) cudaStreamDestroy(m->own_stream);
@@ -1277,11 +1332,21 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
             if (m->g_prefill[v]) { cudaGraphExecDestroy(m->g_prefill[v]); m->g_prefill[v] = nullptr; }
         m->ph_prefill = make_phases(m, true);   // the phase table embeds the staging buffer's address
     }
+    if (!m->ev_pf0) { CK(cudaEventCreate(&m->ev_pf0)); CK(cudaEventCreate(&m->ev_pf1)); }
     CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaEventRecord(m->ev_pf0, m->stream));
     if (prefill_batched(m, n, pos)) return 1;
+    CK(cudaEventRecord(m->ev_pf1, m->stream));
     CK(cudaMemcpyAsync(emb, m->d_rows, n * dim * 4, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
+    if (cudaEventElapsedTime(&m->last_prefill_ms, m->ev_pf0, m->ev_pf1) != cudaSuccess) m->last_prefill_ms = -1.0f;
     *new_pos = pos + (uint32_t)n;
+    return 0;
+}
+
+extern "C" int lmrs_b200_last_prefill_device_ms(const lmrs_b200_t* m, float* ms) {
+    if (!m || !ms) return fail("null argument");
+    *ms = m->last_prefill_ms;
     return 0;
 }
 

@@ -67,8 +67,8 @@ __global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_
     if (p.x_out) p.x_out = reinterpret_cast<float*>(p.x_out) + row * n;
     if (p.act_in) p.act_in = reinterpret_cast<const float*>(p.act_in) + row * n;
     p.xout_all = 1;
-    if (p.pro == PRO_NORM) gemv_prologue<1, 8, PRO_NORM, false>(p, sm, 0u, true);
-    else gemv_prologue<1, 8, PRO_QUANT, false>(p, sm, 0u, true);
+    if (p.pro == PRO_NORM) gemv_prologue<1, 8, PRO_NORM, false>(p, sm, 0u);
+    else gemv_prologue<1, 8, PRO_QUANT, false>(p, sm, 0u);
     for (int i = threadIdx.x; i < n / 16; i += 256) reinterpret_cast<int4*>(xq_out + row * n)[i] = reinterpret_cast<const int4*>(sm.xq)[i];
     for (int g = threadIdx.x; g < G; g += 256) xs_out[row * G + g] = sm.xs[g];
 }

@@ -13,7 +13,7 @@ ABI_SYMBOLS = [
     "lmrs_b200_create", "lmrs_b200_create_sharded", "lmrs_b200_nccl_unique_id", "lmrs_b200_destroy",
     "lmrs_b200_args", "lmrs_b200_forward", "lmrs_b200_get_embeddings", "lmrs_b200_fill_kv_cache",
     "lmrs_b200_forward_argmax", "lmrs_b200_generate_greedy", "lmrs_b200_forward_device", "lmrs_b200_logits_device", "lmrs_b200_set_stream", "lmrs_b200_synchronize",
-    "lmrs_b200_kernel_launches", "lmrs_b200_bench_gemv_pass", "lmrs_b200_bench_attn_pass", "lmrs_b200_read_kv", "lmrs_b200_debug_buffer", "lmrs_b200_matmul_q8", "lmrs_b200_matmul_q4", "lmrs_b200_matmul_f32", "lmrs_b200_matmul_rest",
+    "lmrs_b200_kernel_launches", "lmrs_b200_bench_gemv_pass", "lmrs_b200_bench_attn_pass", "lmrs_b200_last_prefill_device_ms", "lmrs_b200_read_kv", "lmrs_b200_debug_buffer", "lmrs_b200_matmul_q8", "lmrs_b200_matmul_q4", "lmrs_b200_matmul_f32", "lmrs_b200_matmul_rest",
     "lmrs_b200_quantize_q8", "lmrs_b200_quantize_q4", "lmrs_b200_rmsnorm", "lmrs_b200_softmax",
     "lmrs_b200_last_error", "lmrs_b200_version",
 ]
@@ -68,6 +68,7 @@ def lib():
     L.lmrs_b200_kernel_launches.argtypes = [vp, C.POINTER(C.c_uint64)]
     L.lmrs_b200_bench_gemv_pass.argtypes = [vp, u32, C.POINTER(i)]
     L.lmrs_b200_bench_attn_pass.argtypes = [vp, u32, C.POINTER(i)]
+    L.lmrs_b200_last_prefill_device_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.lmrs_b200_read_kv.argtypes = [vp, u32, u32, u32, vp, vp]
     L.lmrs_b200_debug_buffer.argtypes = [vp, C.c_char_p, vp, C.POINTER(sz)]
     L.lmrs_b200_matmul_q8.argtypes = [vp] * 5 + [i] * 4

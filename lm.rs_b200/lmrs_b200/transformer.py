@@ -122,6 +122,11 @@ class Transformer:
         check(lib().lmrs_b200_bench_attn_pass(self._h, pos, C.byref(n)))
         return n.value
 
+    def last_prefill_device_ms(self) -> float:
+        ms = C.c_float()
+        check(lib().lmrs_b200_last_prefill_device_ms(self._h, C.byref(ms)))
+        return ms.value
+
     def read_kv(self, layer: int, pos0: int, n: int):
         kvd = self.args.head_size * self.args.n_kv_heads // self._world   # a sharded handle holds its own KV heads only
         k, v = np.zeros((n, kvd), np.float32), np.zeros((n, kvd), np.float32)

@@ -191,12 +191,13 @@ def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
     assert np.array_equal(gpu.forward(3, 20), cpu.forward(3, 20))
 
 
-@pytest.mark.parametrize("env", [{"LMRS_B200_LL": "0"}, {"LMRS_B200_LL": "0", "LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"},
-                                 {"LMRS_B200_GRAPH": "0"}, {"LMRS_B200_GEMM": "0"}, {"LMRS_B200_GEMV_CFG": "1"},
+@pytest.mark.parametrize("env", [{"LMRS_B200_LL": "1"}, {"LMRS_B200_LL": "1", "LMRS_B200_GEMV_CFG": "0"}, {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"},
+                                 {"LMRS_B200_GRAPH": "0"}, {"LMRS_B200_GEMM": "0"}, {"LMRS_B200_GEMV_CFG": "1"}, {"LMRS_B200_GEMV_CFG": "4"},
                                  {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "4"}, {"LMRS_B200_ATT_GROUPS": "1"}])
 def test_alternative_execution_modes_stay_bit_exact(env):
-    """kernel-boundary hand-overs instead of the LL exchange (+ GPU-wide score kernel) / no graph, no PDL / no graph /
-    serial prefill / three-stage rings / single-CTA attention / clusters of 4 / ungrouped heads: same bits as the default path."""
+    """fence-free LL exchange between co-resident kernels instead of kernel-boundary hand-overs (16- and 8-warp rings) /
+    GPU-wide score kernel / no graph, no PDL / no graph / serial prefill / other ring geometries / single-CTA attention /
+    clusters of 4 / ungrouped heads: same bits as the default path."""
     import subprocess
     import sys
     code = r'''
