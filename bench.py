@@ -79,12 +79,13 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_reference_run(buf, a, pos0, steps, warmup, prompt, keep_logits=0):
+def cpu_reference_run(buf, a, pos0, steps, warmup, prompt, keep_logits=0, kshards=1):
     """The reference arm / cpu_baseline: oracle/ (C restatement of the reference's CPU path) on the host cores.
     keep_logits: also return the prefill residual stream and the logits of the first `keep_logits` greedy steps from
     (prompt[pos0], pos0) -- the parity reference for the GPU arm."""
     import lmrs_ref
     lmrs_ref.build()
+    lmrs_ref.set_kshards(kshards)   # N-GPU parity leg: the rank-ordered partial sums of the peer exchange (oracle/lmrs_ref.h)
     m = lmrs_ref.RefTransformer(buf)
     # "all the host threads it can use": probe a few team sizes on one decode step each and keep the fastest
     # (nproc can exceed the container's CPU quota, where more threads only add spin-wait contention)
@@ -158,7 +159,10 @@ def main():
                           f"{args.steps} tokens from pos {args.pos} after a {args.pos}-embedding fill_kv_cache",
               "model_file_bytes": lf.file_size(a), "first_pos": args.pos, "batch": 1,
               "l2": "inputs larger than L2 (whole weight set streamed every step); no flush needed",
-              "parallelism": "single GPU" if args.gpus == 1 else f"row-sharded x{args.gpus} (2 all-reduces per block)"}
+              "parallelism": "single GPU" if args.gpus == 1 else
+                             f"row-sharded x{args.gpus}: partial Wo/W2 results pushed between the GPUs by the kernels (NVLink peer stores, "
+                             f"rank-ordered sum in the next prologue), no collective in the decode chain"
+                             if os.environ.get("LMRS_B200_PEER", "1") != "0" else f"row-sharded x{args.gpus} (2 NCCL all-reduces per block)"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -278,7 +282,8 @@ def main():
         return dt
     # (a) forward() -> host logits -> numpy argmax: vocab*4 bytes device->host per step
     e2e_logits_s = timed_loop(lambda tok, pos: int(np.argmax(m.forward(tok, pos))) % a.vocab_size)
-    if world == 1:
+    peer = os.environ.get("LMRS_B200_PEER", "1") != "0"
+    if world == 1 or peer:
         # (b) headline: forward_argmax() -- the greedy pick happens on the device, 4 bytes come back
         e2e_s = timed_loop(lambda tok, pos: m.forward_argmax(tok, pos))
         # (c) the whole loop in one call, token fed back on the device
@@ -319,7 +324,8 @@ def main():
     parity = None
     if (args.gpus == 1 and args.cpu_steps > 0) or args.parity_steps > 0:
         cpu_steps = args.cpu_steps if args.gpus == 1 else 0
-        r = cpu_reference_run(buf, a, args.pos, max(cpu_steps, 1), 2 if cpu_steps else 0, prompt, keep_logits=args.parity_steps)
+        r = cpu_reference_run(buf, a, args.pos, max(cpu_steps, 1), 2 if cpu_steps else 0, prompt, keep_logits=args.parity_steps,
+                              kshards=args.gpus if (args.gpus > 1 and peer) else 1)
         if cpu_steps:
             cpu = {"value": r["decode_tok_s"], "unit": "tok/s", "cores": r["cores"], "kind": "port",
                    "sample": f"{args.cpu_steps} greedy decode steps at pos {args.pos}+ after a {args.pos}-token batched prefill",
@@ -327,7 +333,8 @@ def main():
         if args.parity_steps > 0:
             d_stream = float(np.abs(emb - r["prefill_stream"]).max())
             d_logits = [float(np.abs(g - c).max()) for g, c in zip(gpu_logits, r["logits"])]
-            parity = {"reference": "oracle/ (C restatement of the reference's CPU path; the Rust binary cannot be built here: parity unpinned)",
+            parity = {"reference": "oracle/ (C restatement of the reference's CPU path; the Rust binary cannot be built here: parity unpinned)"
+                                   + (f"; N-GPU: Wo/W2 partial sums added in rank order (oracle k-shard mode, {args.gpus} shards)" if args.gpus > 1 and peer else ""),
                       "prefill_residual_stream": {"rows": args.pos, "max_abs": d_stream, "bit_exact": bool(np.array_equal(emb, r["prefill_stream"]))},
                       "decode_logits": {"positions": [args.pos + i for i in range(len(d_logits))], "max_abs": max(d_logits) if d_logits else None,
                                         "bit_exact": bool(all(np.array_equal(g, c) for g, c in zip(gpu_logits, r["logits"]))),
@@ -338,9 +345,9 @@ def main():
         "metric": metric, "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "int8 x int8 -> int32 groups, f32 accumulate", "data": "synthetic", "config": config,
-        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4 if world == 1 else a.vocab_size * 4,
+        "e2e": {"value": e2e, "unit": "tok/s", "h2d_bytes_per_step": 16, "d2h_bytes_per_step": 4 if (world == 1 or peer) else a.vocab_size * 4,
                 "ms_per_step": e2e_s / args.steps * 1e3,
-                "api": "forward_argmax(token, pos) -> next token (greedy pick fused on the device)" if world == 1 else "forward(token, pos) -> host logits",
+                "api": "forward_argmax(token, pos) -> next token (greedy pick fused on the device)" if (world == 1 or peer) else "forward(token, pos) -> host logits",
                 "logits_to_host": {"value": args.steps / e2e_logits_s, "ms_per_step": e2e_logits_s / args.steps * 1e3,
                                    "d2h_bytes_per_step": a.vocab_size * 4, "api": "forward(token, pos) -> host logits + host argmax"},
                 "generate_greedy": None if gen_s is None else {"value": args.steps / gen_s, "ms_per_step": gen_s / args.steps * 1e3,

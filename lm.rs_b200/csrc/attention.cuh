@@ -45,6 +45,9 @@ struct AttnParams {
     int trace_slot;        // LMRS_TRACE builds: timeline slot of this launch (-1: none)
     int dev_skip;          // -DLMRS_DEV_PROBES builds only: phases to leave out when timing (results are then wrong)
     const StepParams* step;
+    // L2 prefetch of the weights the NEXT kernels of the step will stream (decode chain): the attention phase is a latency
+    // chain that leaves HBM idle, so its CTAs ask the L2 to fetch [l2pf_ptr, +l2pf_bytes) meanwhile (cp.async.bulk.prefetch.L2)
+    const uint8_t* l2pf_ptr; unsigned long long l2pf_bytes; int l2pf_chunk;
 };
 
 template <int HS, bool BIG = false> __host__ __device__ constexpr int att_tile_rows() { return (BIG ? 128 : 64) / (HS <= 64 ? 1 : (HS <= 128 ? 2 : 4)); }
@@ -581,6 +584,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_cluster_kernel(const AttnPar
     if (warp == NWARP - 1) exp_tab[lane] = kExp2fTab[lane];
     if (blockIdx.x == 0 && tid == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
+    if (p.l2pf_bytes && tid == 32 * (NWARP - 2)) l2_prefetch_slice(p.l2pf_ptr, p.l2pf_bytes, p.l2pf_chunk);   // after this CTA's own K/V requests
     const bool ll = p.ll != 0, nowait = p.ll_nowait != 0;
     const uint32_t seq = ll ? p.step->seq : 0u;
     if (!ll) pdl_wait();

@@ -61,6 +61,28 @@ LMRS_DEVINL void bulk_g2s_hint(void* dst_smem, const void* src_gmem, uint32_t by
         : "memory");
 }
 
+// fire-and-forget request to bring [src, src + bytes) into L2 (no shared-memory destination, no completion to wait for)
+LMRS_DEVINL void bulk_prefetch_l2(const void* src_gmem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
+}
+LMRS_DEVINL void bulk_prefetch_l2_hint(const void* src_gmem, uint32_t bytes, uint64_t pol) {
+    asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(src_gmem), "r"(bytes), "l"(pol) : "memory");
+}
+// one thread per CTA: this CTA's 1/gridDim.x slice of the range, in `chunk`-byte requests (everything 16-byte aligned)
+// evict_first (chunk < 0 selects it): the lines are read exactly once, soon; they must not push the KV cache out of L2
+LMRS_DEVINL void l2_prefetch_slice(const uint8_t* base, unsigned long long bytes, int chunk) {
+    const bool ef = chunk < 0;
+    if (ef) chunk = -chunk;
+    const uint64_t pol = ef ? l2_policy_evict_first() : 0ull;
+    const unsigned long long per = ((bytes / gridDim.x) + 4095ull) & ~4095ull;
+    const unsigned long long lo = (unsigned long long)blockIdx.x * per;
+    const unsigned long long hi = lo + per < bytes ? lo + per : bytes;
+    for (unsigned long long o = lo; o < hi; o += (unsigned long long)chunk) {
+        const uint32_t nb = (uint32_t)((hi - o < (unsigned long long)chunk ? hi - o : (unsigned long long)chunk) & ~15ull);
+        if (ef) bulk_prefetch_l2_hint(base + o, nb, pol); else bulk_prefetch_l2(base + o, nb);
+    }
+}
+
 // ---- programmatic dependent launch ---------------------------------------------------------------------
 // pdl_wait(): block until every kernel this launch depends on has completed and flushed (no-op when the
 // kernel was launched without the PDL attribute).  pdl_launch_dependents(): allow the next kernel in the
@@ -123,6 +145,45 @@ LMRS_DEVINL float4 ll_wait4(const llword_t* p, uint32_t seq, bool nowait) {
     if (!ll_try4(p, seq, nowait, v)) { const LLSpin sp = ll_spin_begin(); do { __nanosleep(20); ll_spin_check(sp); } while (!ll_try4(p, seq, nowait, v)); }
     return v;
 }
+
+// ---- the same words BETWEEN GPUs (row-sharded N-GPU mode): every GPU pushes its partial result vector straight into the
+// exchange buffers of all its peers over NVLink (peer-mapped pointers), one 8-byte (value, sequence) word per element --
+// the protocol NCCL's LL path uses, but issued from the epilogue of the producing kernel, so no collective sits in the chain.
+// System scope: the consumer polls its OWN memory, which the peers write through this GPU's L2.
+LMRS_DEVINL void ll_store_sys(llword_t* p, float v, uint32_t seq) {
+    asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(p), "l"(((unsigned long long)seq << 32) | (unsigned long long)__float_as_uint(v)) : "memory");
+}
+LMRS_DEVINL llword_t ll_ld1_sys(const llword_t* p) {
+    llword_t a;
+    asm volatile("ld.relaxed.sys.global.b64 %0, [%1];" : "=l"(a) : "l"(p) : "memory");
+    return a;
+}
+LMRS_DEVINL bool ll_try4_sys(const llword_t* p, uint32_t seq, bool nowait, float4& out) {
+    llword_t a, b, c, d;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(c), "=l"(d) : "l"(p + 2) : "memory");
+    if (!nowait && !(ll_ok(a, seq) && ll_ok(b, seq) && ll_ok(c, seq) && ll_ok(d, seq))) return false;
+    out = make_float4(ll_val(a), ll_val(b), ll_val(c), ll_val(d));
+    return true;
+}
+// a peer may be a whole host-side launch behind (graph instantiation, a slow rank): wait longer before giving up
+LMRS_DEVINL void px_spin_check(const LLSpin& s) { if (clock64() - s.t0 > 40000000000LL) __trap(); }
+LMRS_DEVINL float px_wait1(const llword_t* p, uint32_t seq, bool nowait) {
+    llword_t w = ll_ld1_sys(p);
+    if (!nowait && !ll_ok(w, seq)) { const LLSpin sp = ll_spin_begin(); do { __nanosleep(40); px_spin_check(sp); w = ll_ld1_sys(p); } while (!ll_ok(w, seq)); }
+    return ll_val(w);
+}
+// whole CTA: one thread per source GPU parks on the first word of that GPU's slot (stride n words), everybody else sits
+// in the barrier -- 148 CTAs polling with every thread would flood the L2 the peers' stores have to get through
+LMRS_DEVINL void px_canary_wait(const llword_t* base, int world, int n, uint32_t seq, bool nowait) {
+    if (!nowait && (int)threadIdx.x < world) {
+        const llword_t* p = base + (size_t)threadIdx.x * n;
+        const LLSpin sp = ll_spin_begin();
+        while (!ll_ok(ll_ld1_sys(p), seq)) { __nanosleep(40); px_spin_check(sp); }
+    }
+    __syncthreads();
+}
+constexpr int PX_MAX_WORLD = 8;
 
 // ---- integer dot products ------------------------------------------------------------------------------
 LMRS_DEVINL int dp4a_ss(int a, int b, int c) { return __dp4a(a, b, c); }

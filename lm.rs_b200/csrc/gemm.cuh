@@ -12,28 +12,38 @@
 //   warps 2..9  epilogue       tcgen05.ld 32x32b (thread = token row x 64 columns), s32 -> f32, * ws[col][g] * xs[row][g], added
 //                              into 64 f32 register accumulators in the reference's order -> results are bit-identical
 //                              to the CPU path; double-buffered TMEM lets group g+1's MMAs run under group g's epilogue.
-// The CUDA-core mini-epilogue (4 instructions per element per group) is about twice the MMA time of a tile: the
-// honest int8 tensor-core roofline fraction of this formulation is bounded by it (hard part 1).
+// The CUDA-core mini-epilogue runs after EVERY group (the scale is rank-1 per K group), so it bounds the kernel: it is written
+// with packed f32x2 arithmetic and an exact integer->float conversion without I2F (2.5 issue slots per element per group
+// instead of ~5 with a quarter-rate I2F; 3 per element), the tile's weight scales are staged once for all groups, and tiles come in three
+// shapes so that every matrix fills the GPU: 128 x 128, 128 x 64 (Wo / W2: 2048 output rows), and the fused gate/up tile.
 #pragma once
 #include <cuda.h>
 
 #include "common.cuh"
+#include "gemv.cuh"   // glu_act
 
 namespace lmrs {
 
-constexpr int GEMM_M = 128, GEMM_N = 128, GEMM_K = 128, GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant, 64 columns each)
-constexpr int GEMM_TILE_BYTES = GEMM_M * GEMM_K;   // 16 KB per operand tile
-constexpr size_t GEMM_SMEM = 1024 + (size_t)GEMM_STAGES * 2 * GEMM_TILE_BYTES + 2 * GEMM_N * 4 + 256;
+constexpr int GEMM_M = 128, GEMM_K = 128, GEMM_STAGES = 4;
+constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+constexpr int GEMM_TILE_BYTES = GEMM_M * GEMM_K;   // 16 KB A tile (128 token rows x one quantization group)
+// BNM = accumulator columns of one MMA (output rows of w per CTA tile): 128 or 64.  Shared memory: operand ring, the tile's
+// weight scales for ALL groups transposed to [group][column], barriers.
+template <int BNM> inline size_t gemm_smem_bytes(int n) {
+    return 1024 + (size_t)GEMM_STAGES * (GEMM_TILE_BYTES + BNM * GEMM_K) + (size_t)(n / GEMM_K) * BNM * 4 + 256;
+}
 
 struct GemmParams {
     int T, n, o;          // rows of x, input features, output rows of w
     const float* ws;      // dense [o][n/128] weight scales (file layout)
+    const float* ws2;     // GLU: scales of the second matrix (w3)
     const float* xs;      // [T][n/128] activation scales
     // output: columns [0,c1) -> out0, [c1,c2) -> out1, [c2,o) -> out2 (segment boundaries are multiples of 128)
     float* out0; int ld0; int c1;
     float* out1; int ld1; int c2;
     float* out2; int ld2;
+    int glu_epi;          // GLU: EPI_GLU_SILU / EPI_GLU_GELU (gemv.cuh)
+    float neg_zero;       // -0.0f, passed at run time (see f2_mul_sep)
 };
 
 LMRS_DEVINL void tma_load_2d(void* dst, const CUtensorMap* map, int x, int y, uint64_t* bar) {
@@ -56,9 +66,9 @@ LMRS_DEVINL uint64_t umma_desc_sw128(const void* smem_tile) {
     d |= (uint64_t)2 << 61;                          // SWIZZLE_128B
     return d;
 }
-// instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = 128, dense, no saturate
-__host__ __device__ constexpr uint32_t umma_idesc_i8_m128_n128() {
-    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(GEMM_N >> 3) << 17) | ((uint32_t)(GEMM_M >> 4) << 24);
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, M = 128, N = BNM, dense, no saturate
+template <int BNM> __host__ __device__ constexpr uint32_t umma_idesc_i8_m128() {
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BNM >> 3) << 17) | ((uint32_t)(GEMM_M >> 4) << 24);
 }
 LMRS_DEVINL void umma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -84,29 +94,72 @@ LMRS_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+// ---- packed f32x2 arithmetic (Blackwell FADD2 / FMUL2: two IEEE round-to-nearest results per issue slot) ----------------
+LMRS_DEVINL uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+LMRS_DEVINL void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+LMRS_DEVINL uint64_t f2_mul(uint64_t a, uint64_t b) { uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+LMRS_DEVINL uint64_t f2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+// A product that must stay a SEPARATELY ROUNDED product when an add consumes it.  ptxas (12.9) contracts mul.rn.f32x2
+// followed by add.rn.f32x2 into one FFMA2 -- a single rounding -- although both carry an explicit rounding modifier (it
+// does not do that to the scalar forms).  Written as fma(a, b, -0.0) with the -0.0 taken from a kernel PARAMETER the
+// product is exact (a*b + -0.0 rounds like a*b and keeps the sign of a zero product), costs the same FFMA2 issue slot,
+// and cannot be contracted any further: the following add stays an FADD2.
+LMRS_DEVINL uint64_t f2_mul_sep(uint64_t a, uint64_t b, uint64_t neg_zero2) {
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(neg_zero2)); return r;
+}
+// (ival as f32) for |ival| < 2^22 without I2F (a quarter-rate conversion that bounded the first build's epilogue): the
+// integer is added into the mantissa of 1.5 * 2^23 and the constant subtracted again -- both steps exact.
+// |ival| <= 128 * 127 * 127 = 2,064,512 for one quantization group.
+constexpr int GEMM_MAGIC_I = 0x4B400000;
+constexpr float GEMM_MAGIC_F = 12582912.0f;
+
+// acc[0..15] (pairs) += ((v as f32) * ws) * xs for 32 consecutive accumulator columns: src/functional.rs:207's term and the
+// ascending-group f32 accumulation, two columns per instruction
+LMRS_DEVINL void gemm_epi_chunk(uint64_t* acc, const uint32_t (&v)[32], const float* ws32, uint64_t xs2, uint64_t neg_magic2, uint64_t nz2) {
+    const float4* w4 = reinterpret_cast<const float4*>(ws32);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const float4 w = w4[j];   // the same address for every lane: one broadcast LDS.128
+        const uint64_t f0 = f2_add(f2_pack(__int_as_float((int)v[4 * j] + GEMM_MAGIC_I), __int_as_float((int)v[4 * j + 1] + GEMM_MAGIC_I)), neg_magic2);
+        const uint64_t f1 = f2_add(f2_pack(__int_as_float((int)v[4 * j + 2] + GEMM_MAGIC_I), __int_as_float((int)v[4 * j + 3] + GEMM_MAGIC_I)), neg_magic2);
+        acc[2 * j] = f2_add(acc[2 * j], f2_mul_sep(f2_mul(f0, f2_pack(w.x, w.y)), xs2, nz2));
+        acc[2 * j + 1] = f2_add(acc[2 * j + 1], f2_mul_sep(f2_mul(f1, f2_pack(w.z, w.w)), xs2, nz2));
+    }
+}
+
+// BNM: accumulator columns per CTA tile (128 or 64).  GLU (BNM = 128): accumulator columns 0..63 are rows n0h..n0h+63 of
+// w1 (gate), columns 64..127 the same rows of w3 (up); the epilogue writes act(gate) * up (src/transformer.rs:607-624)
+// for 64 hidden columns, so gate/up never travel through HBM.
+template <int BNM, bool GLU>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const GemmParams p) {
+gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2,
+               const GemmParams p) {
+    static_assert(BNM == 128 || BNM == 64, "tile width");
+    static_assert(!GLU || BNM == 128, "GLU tiles pair 64 gate with 64 up columns");
+    constexpr int B_TILE_BYTES = BNM * GEMM_K;
+    constexpr int STAGE_BYTES = GEMM_TILE_BYTES + B_TILE_BYTES;
+    constexpr int OUT_COLS = GLU ? 64 : BNM;                              // output columns (rows of w) per CTA
     extern __shared__ uint8_t gsm_raw[];
     uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
-    uint8_t* tiles = gsm;                                                   // [STAGES][A 16 KB | B 16 KB]
-    float* ws_s = reinterpret_cast<float*>(tiles + (size_t)GEMM_STAGES * 2 * GEMM_TILE_BYTES);   // [2][128]
-    uint64_t* full = reinterpret_cast<uint64_t*>(ws_s + 2 * GEMM_N);        // [STAGES]
+    const int G = p.n / GEMM_K;
+    uint8_t* tiles = gsm;                                                   // [STAGES][A 16 KB | B]
+    float* ws_t = reinterpret_cast<float*>(tiles + (size_t)GEMM_STAGES * STAGE_BYTES);   // [G][BNM]
+    uint64_t* full = reinterpret_cast<uint64_t*>(ws_t + (size_t)G * BNM);   // [STAGES]
     uint64_t* empty = full + GEMM_STAGES;                                   // [STAGES]
     uint64_t* tfull = empty + GEMM_STAGES;                                  // [2]
     uint64_t* tempty = tfull + 2;                                           // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.y * GEMM_M, n0 = blockIdx.x * GEMM_N;
-    const int G = p.n / GEMM_K;
+    const int m0 = blockIdx.y * GEMM_M, n0 = blockIdx.x * OUT_COLS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
         fence_barrier_init();
     }
-    if (warp == 1) {   // TMEM: 256 columns = two 128-column s32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(tmem_slot)) : "memory");
+    if (warp == 1) {   // TMEM: two BNM-column s32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * BNM) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -119,77 +172,109 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             for (int g = 0; g < G; g++) {
                 const int s = g % GEMM_STAGES;
                 mbar_wait(&empty[s], ((g / GEMM_STAGES) & 1) ^ 1);
-                uint8_t* a_t = tiles + (size_t)s * 2 * GEMM_TILE_BYTES;
-                mbar_expect_tx(&full[s], 2 * GEMM_TILE_BYTES);
+                uint8_t* a_t = tiles + (size_t)s * STAGE_BYTES;
+                mbar_expect_tx(&full[s], STAGE_BYTES);
                 tma_load_2d(a_t, &tm_a, g * GEMM_K, m0, &full[s]);
-                tma_load_2d(a_t + GEMM_TILE_BYTES, &tm_b, g * GEMM_K, n0, &full[s]);
+                if (GLU) {
+                    tma_load_2d(a_t + GEMM_TILE_BYTES, &tm_b, g * GEMM_K, n0, &full[s]);
+                    tma_load_2d(a_t + GEMM_TILE_BYTES + 64 * GEMM_K, &tm_b2, g * GEMM_K, n0, &full[s]);
+                } else {
+                    tma_load_2d(a_t + GEMM_TILE_BYTES, &tm_b, g * GEMM_K, n0, &full[s]);
+                }
             }
         }
     } else if (warp == 1) {
         if (lane == 0) {   // ---- MMA issuer ----
-            const uint32_t idesc = umma_idesc_i8_m128_n128();
+            const uint32_t idesc = umma_idesc_i8_m128<BNM>();
             for (int g = 0; g < G; g++) {
                 const int s = g % GEMM_STAGES, b = g & 1;
                 mbar_wait(&tempty[b], ((g >> 1) & 1) ^ 1);          // epilogue has drained this accumulator
                 mbar_wait(&full[s], (g / GEMM_STAGES) & 1);         // operands have landed
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint8_t* a_t = tiles + (size_t)s * 2 * GEMM_TILE_BYTES;
+                const uint8_t* a_t = tiles + (size_t)s * STAGE_BYTES;
                 const uint64_t da = umma_desc_sw128(a_t), db = umma_desc_sw128(a_t + GEMM_TILE_BYTES);
 #pragma unroll
                 for (int k = 0; k < GEMM_K / 32; k++)   // advance 32 bytes along K inside the swizzle atom
-                    umma_i8(tmem_base + b * GEMM_N, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k > 0);
+                    umma_i8(tmem_base + b * BNM, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, k > 0);
                 umma_commit(&empty[s]);                              // smem stage reusable once these MMAs finished
                 umma_commit(&tfull[b]);                              // accumulator complete
             }
         }
-    } else {   // ---- epilogue: warps 2..9, TMEM lane quadrant = warp % 4, thread = one token row x 64 columns ----
-        constexpr int EC = GEMM_N / 2;                               // columns per epilogue thread
+    } else {   // ---- epilogue: warps 2..9, TMEM lane quadrant = warp % 4, thread = one token row x EC columns ----
+        constexpr int EC = GLU ? 64 : BNM / 2;                       // accumulator columns per epilogue thread
+        constexpr int NCH = EC / 32;                                 // 32-column TMEM loads per group
         const int quad = warp & 3;
-        const int chalf = (warp - 2) >> 2;                           // 0: columns 0..63, 1: columns 64..127
+        const int chalf = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
         const int et = threadIdx.x - 64;                             // 0..255 among the epilogue threads
         const bool row_ok = m0 + row < p.T;
-        float acc[EC];
+        // chunk c of this thread covers accumulator columns col_of(c) .. +31
+        //   plain: the thread's half of the tile; GLU: 32 gate columns (c = 0) and the matching 32 up columns (c = 1)
+        auto col_of = [&](int c) { return GLU ? c * 64 + chalf * 32 : chalf * EC + c * 32; };
+        // the tile's weight scales for every group, transposed to [g][column] (file layout is [row of w][g])
+        for (int e = et; e < G * BNM; e += 256) {
+            const int c = e / G, g = e - c * G;
+            float v;
+            if (GLU) v = c < 64 ? p.ws[(size_t)(n0 + c) * G + g] : p.ws2[(size_t)(n0 + c - 64) * G + g];
+            else v = (n0 + c < p.o) ? p.ws[(size_t)(n0 + c) * G + g] : 0.0f;
+            ws_t[g * BNM + c] = v;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint64_t acc[EC / 2];
 #pragma unroll
-        for (int j = 0; j < EC; j++) acc[j] = 0.0f;
+        for (int j = 0; j < EC / 2; j++) acc[j] = 0ull;               // (+0.0f, +0.0f)
+        const uint64_t neg_magic2 = f2_pack(-GEMM_MAGIC_F, -GEMM_MAGIC_F), nz2 = f2_pack(p.neg_zero, p.neg_zero);
+        const float* xs_row = p.xs + (size_t)(row_ok ? m0 + row : 0) * G;
+        float xs_next = row_ok ? xs_row[0] : 0.0f;
         for (int g = 0; g < G; g++) {
             const int b = g & 1;
-            // stage this group's 128 column scales (file layout [o][G]) and fetch my row's activation scale
-            if (et < GEMM_N) ws_s[b * GEMM_N + et] = (n0 + et < p.o) ? p.ws[(size_t)(n0 + et) * G + g] : 0.0f;
-            const float xsc = row_ok ? p.xs[(size_t)(m0 + row) * G + g] : 0.0f;
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            const float xsc = xs_next;
+            if (g + 1 < G) xs_next = row_ok ? xs_row[g + 1] : 0.0f;   // in flight under this group's arithmetic
+            const uint64_t xs2 = f2_pack(xsc, xsc);
             mbar_wait(&tfull[b], (g >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-            for (int c = 0; c < EC / 32; c++) {
+            for (int c = 0; c < NCH; c++) {
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * GEMM_N + chalf * EC + c * 32), v);
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * BNM + col_of(c)), v);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const float t = __fmul_rn(__fmul_rn((float)(int)v[j], ws_s[b * GEMM_N + chalf * EC + c * 32 + j]), xsc);
-                    acc[c * 32 + j] = __fadd_rn(acc[c * 32 + j], t);
-                }
+                gemm_epi_chunk(acc + c * 16, v, ws_t + g * BNM + col_of(c), xs2, neg_magic2, nz2);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
         }
         if (row_ok) {
-            float* dst; int ld, cbase;
-            if (n0 < p.c1) { dst = p.out0; ld = p.ld0; cbase = 0; }
-            else if (n0 < p.c2) { dst = p.out1; ld = p.ld1; cbase = p.c1; }
-            else { dst = p.out2; ld = p.ld2; cbase = p.c2; }
-            float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase) + chalf * EC);
+            if constexpr (GLU) {
+                float4* o4 = reinterpret_cast<float4*>(p.out0 + (size_t)(m0 + row) * p.ld0 + n0 + chalf * 32);
 #pragma unroll
-            for (int j = 0; j < EC / 4; j++) o4[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+                for (int j = 0; j < 8; j++) {
+                    float g0, g1, g2, g3, u0, u1, u2, u3;
+                    f2_unpack(acc[2 * j], g0, g1); f2_unpack(acc[2 * j + 1], g2, g3);
+                    f2_unpack(acc[16 + 2 * j], u0, u1); f2_unpack(acc[16 + 2 * j + 1], u2, u3);
+                    o4[j] = make_float4(__fmul_rn(glu_act(p.glu_epi, g0), u0), __fmul_rn(glu_act(p.glu_epi, g1), u1),
+                                        __fmul_rn(glu_act(p.glu_epi, g2), u2), __fmul_rn(glu_act(p.glu_epi, g3), u3));
+                }
+            } else {
+                float* dst; int ld, cbase;
+                if (n0 < p.c1) { dst = p.out0; ld = p.ld0; cbase = 0; }
+                else if (n0 < p.c2) { dst = p.out1; ld = p.ld1; cbase = p.c1; }
+                else { dst = p.out2; ld = p.ld2; cbase = p.c2; }
+                float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase) + chalf * EC);
+#pragma unroll
+                for (int j = 0; j < EC / 4; j++) {
+                    float a0, a1, a2, a3;
+                    f2_unpack(acc[2 * j], a0, a1); f2_unpack(acc[2 * j + 1], a2, a3);
+                    o4[j] = make_float4(a0, a1, a2, a3);
+                }
+            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * BNM) : "memory");
     }
 }
 

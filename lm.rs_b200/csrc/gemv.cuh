@@ -72,6 +72,14 @@ struct GemvParams {
     const StepParams* step;
     int softcap_rows;
     int trace_slot;    // LMRS_TRACE builds: timeline slot of this launch (-1: none)
+    // L2 prefetch of weights LATER kernels of the step will stream, requested while this kernel's CTAs sit in the dependency
+    // wait (common.cuh l2_prefetch_slice; chunk < 0: evict_first)
+    const uint8_t* l2pf_ptr; unsigned long long l2pf_bytes; int l2pf_chunk;
+    // row-sharded N-GPU mode, peer exchange (common.cuh): px_world > 1
+    int px_world;
+    const llword_t* px_in;               // PRO_NORM: this GPU's exchange vector [px_world][n]; delta = slot 0 + slot 1 + ... in rank order
+    llword_t* px_out[PX_MAX_WORLD];      // EPI_STORE: this rank's slot in EVERY GPU's exchange vector (peer-mapped), indexed by row
+    float* px_logits[PX_MAX_WORLD];      // EPI_LOGITS: every GPU's logits buffer + this rank's vocabulary offset
 };
 
 template <int QT> struct QTraits;
@@ -369,6 +377,46 @@ LMRS_DEVINL void ll_gather2(const llword_t* base_a, const llword_t* base_b, int 
         ll_spin_check(sp);
     }
 }
+// peer exchange: this thread's chunks of the N partial vectors the GPUs pushed into this GPU's exchange buffer, added in
+// ascending rank order starting from rank 0's (the order the oracle's k-shard mode restates).  Up to four slots are
+// requested together (one L2 round trip per batch), only incomplete chunks are polled again.
+template <int NC, int THREADS>
+LMRS_DEVINL void px_gather_sum(const llword_t* base, int world, int n, int nchunks, uint32_t seq, bool nowait, float4 (&dv)[NC]) {
+    constexpr int PXB = NC <= 2 ? 4 : 2;   // slots requested together (bounded by the registers of the wide-CTA builds)
+    const int tid = threadIdx.x;
+    for (int r0 = 0; r0 < world; r0 += PXB) {
+        float4 t[PXB][NC];
+        bool done[PXB][NC];
+#pragma unroll
+        for (int b = 0; b < PXB; b++)
+#pragma unroll
+            for (int k = 0; k < NC; k++) { done[b][k] = !(r0 + b < world && tid + k * THREADS < nchunks); t[b][k] = make_float4(0.f, 0.f, 0.f, 0.f); }
+        const LLSpin sp = ll_spin_begin();
+        for (;;) {
+            bool all = true;
+#pragma unroll
+            for (int b = 0; b < PXB; b++)
+#pragma unroll
+                for (int k = 0; k < NC; k++)
+                    if (!done[b][k]) {
+                        if (ll_try4_sys(base + (size_t)(r0 + b) * n + 4 * (size_t)(tid + k * THREADS), seq, nowait, t[b][k])) done[b][k] = true;
+                        else all = false;
+                    }
+            if (all) break;
+            __nanosleep(40);
+            px_spin_check(sp);
+        }
+#pragma unroll
+        for (int b = 0; b < PXB; b++)
+            if (r0 + b < world) {
+#pragma unroll
+                for (int k = 0; k < NC; k++) {
+                    if (r0 + b == 0) dv[k] = t[b][k];
+                    else { dv[k].x = __fadd_rn(dv[k].x, t[b][k].x); dv[k].y = __fadd_rn(dv[k].y, t[b][k].y); dv[k].z = __fadd_rn(dv[k].z, t[b][k].z); dv[k].w = __fadd_rn(dv[k].w, t[b][k].w); }
+                }
+            }
+    }
+}
 LMRS_DEVINL void ll_store4(llword_t* p, float4 v, uint32_t seq) {
     const unsigned long long hi = (unsigned long long)seq << 32;
     asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(hi | __float_as_uint(v.x)), "l"(hi | __float_as_uint(v.y)) : "memory");
@@ -386,7 +434,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
     constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
-    const bool nowait = LL && p.ll_nowait;
+    const bool nowait = (LL || p.px_world > 1) && p.ll_nowait;
     const long long cP = ktrace_c0();
     trace_event(100 + PRO);
     if constexpr (PRO == PRO_NORM) {
@@ -436,6 +484,9 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
                     ll_gather2<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.x_in), reinterpret_cast<const llword_t*>(p.delta), nchunks, seq, nowait, v, dv);
                 else
                     ll_gather<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.delta), nchunks, seq, nowait, dv);
+            } else if (p.px_world > 1) {   // N-GPU mode: the contribution is the rank-ordered sum of the partials every GPU pushed here
+                px_canary_wait(p.px_in, p.px_world, n, seq, nowait);
+                px_gather_sum<NORM_MAXC, THREADS>(p.px_in, p.px_world, n, nchunks, seq, nowait, dv);
             } else {
                 const float4* din = reinterpret_cast<const float4*>(p.delta);
 #pragma unroll
@@ -612,9 +663,17 @@ LMRS_DEVINL void store_row(const GemvParams& p, int row, float v, uint32_t pos, 
             t = (float)tanh((double)t);
             v = __fmul_rn(t, 30.0f);
         }
-        reinterpret_cast<float*>(p.out)[row] = v;   // logits leave the step: plain f32
+        if (p.px_world > 1) {   // N-GPU mode: this rank's vocabulary rows go straight into every GPU's logits buffer
+            for (int r = 0; r < p.px_world; r++) p.px_logits[r][row] = v;
+        } else {
+            reinterpret_cast<float*>(p.out)[row] = v;   // logits leave the step: plain f32
+        }
     } else {
-        act_store<LL>(p.out, row, v, seq);
+        if (!LL && p.px_world > 1) {   // N-GPU mode: push the partial into this rank's slot on every GPU (NVLink stores)
+            for (int r = 0; r < p.px_world; r++) ll_store_sys(p.px_out[r] + row, v, seq);
+        } else {
+            act_store<LL>(p.out, row, v, seq);
+        }
     }
 }
 template <int QT, int EPI, bool LL>
@@ -746,7 +805,7 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? LMRS_GEMV_MINB : 1) l
     const long long c0 = ktrace_c0();
     if (blockIdx.x == 0 && threadIdx.x == 0) ktrace(p.trace_slot, 0);
     pdl_launch_dependents();
-    const uint32_t seq = LL ? p.step->seq : 0u;
+    const uint32_t seq = (LL || p.px_world > 1) ? p.step->seq : 0u;
     // LL mode: the kernel is resident long before its inputs exist.  It parks on ONE word of its freshest input (the pending
     // residual contribution / the activation to quantize) and only then starts streaming: a weight prefetch issued at CTA
     // start lands in the middle of the PREVIOUS kernel's latency-bound stream and delays it by more than it saves here
@@ -763,6 +822,9 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? LMRS_GEMV_MINB : 1) l
     if (lane == 0)
         for (int s = 0; s < pre && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     if constexpr (!LL) {
+        // this kernel's CTAs were launched early and now idle until the previous kernel completes: one otherwise unused
+        // thread asks the L2 to fetch weights that later kernels of the step will stream (after this CTA's own requests)
+        if (p.l2pf_bytes && threadIdx.x == (WARPS - 1) * 32 + 1) l2_prefetch_slice(p.l2pf_ptr, p.l2pf_bytes, p.l2pf_chunk);
         pdl_wait();   // upstream activations are complete and visible from here on
         if (lane == 0)
             for (int s = pre; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);

@@ -30,13 +30,14 @@ using namespace lmrs;
 
 // one phase of a step (src/transformer.rs:316-384 + :388-657): a quantized matrix-vector product with its fused glue,
 // the attention of a block, or the pending-residual write-back of a serial fill_kv_cache step
-enum { PH_GEMV = 0, PH_ATTN = 1, PH_FINALIZE = 2 };
+enum { PH_GEMV = 0, PH_ATTN = 1, PH_FINALIZE = 2, PH_PEERFLAG = 3 };
 struct Phase {
     int kind;
     int comm;     // row-sharded (NCCL) mode: 1 = all-reduce the output, 2 = all-gather the logits
     GemvParams g;
     AttnParams a;
     ResidualParams r;
+    PeerFlagParams f;
 };
 
 static thread_local std::string g_err;
@@ -64,7 +65,7 @@ struct Mat {
     int o = 0, n = 0, gran = 1;
     const uint8_t* dq = nullptr;    // dense file-layout copy [o][n] int8 + [o][n/128] f32 (prefill GEMM operand; Q8 only)
     const float* ds = nullptr;
-    CUtensorMap tmap;               // TMA descriptor of dq as a [o][n] byte matrix, 128x128 box, 128B swizzle
+    CUtensorMap tmap, tmap64;       // TMA descriptors of dq as a [o][n] byte matrix, 128 B x 128 / 64 rows box, 128B swizzle
     bool has_tmap = false;
 };
 struct Layer {
@@ -88,11 +89,11 @@ struct lmrs_b200 {
     float *d_h = nullptr, *d_down_out = nullptr, *d_logits = nullptr, *d_scores = nullptr, *d_rows = nullptr;
     uint8_t* d_dense = nullptr;           // file-layout weights kept for the tcgen05 prefill GEMM (Q8 models)
     // batched prefill activations, capacity pf_cap rows
-    size_t pf_cap = 0;
+    size_t pf_cap = 0, pf_sc_bytes = 0;
     uint8_t* pf_xq = nullptr;
     float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr, *pf_scores = nullptr;
     bool use_gemm = true;
-    bool use_pf_attn = true;   // batched-rows attention as throughput kernels (prefill_attn.cuh); 0: the per-row decode kernel
+    int use_pf_attn = 1;       // batched-rows attention: 1 = fused throughput kernel (prefill_attn.cuh), 2 = its two-kernel form, 0 = the per-row decode kernel
     size_t rows_cap = 0;
     StepParams* d_step = nullptr;
     StepParams* h_step_ring = nullptr;  // pinned
@@ -126,8 +127,19 @@ struct lmrs_b200 {
     int att_chunks = 1;
     bool use_graph = true, use_pdl = true;
     int gemv_cfg = 0, gemv_ctas_per_sm = 1;
-    Shard shard;  // multi-GPU exchange (shard.h); inert when world == 1
+    int l2pf = 0, l2pf_cls_mb = 24, l2pf_chunk = 32768, l2pf_ef = 1;   // L2 prefetch of upcoming weights during the attention phase (make_phases)
+    Shard shard;  // multi-GPU bootstrap / NCCL fallback (shard.h); inert when world == 1
+    // peer exchange (common.cuh, N-GPU mode): ONE cudaMalloc'ed block per GPU, mapped into every peer through CUDA IPC:
+    //   [n_layers][2][world][dim] LL words (slot r of a vector = rank r's partial) | flags[world] | logits[vocab]
+    bool use_peer = false;
+    uint8_t* d_xchg = nullptr;
+    uint8_t* xchg_peer[PX_MAX_WORLD] = {};   // the same block on every GPU (entry `rank` = d_xchg)
+    size_t xchg_flags_off = 0, xchg_logits_off = 0;
 };
+
+static llword_t* px_vec(const lmrs_b200* m, int gpu, size_t layer, int which) {   // exchange vector (layer, 0: after Wo / 1: after W2) on GPU `gpu`
+    return reinterpret_cast<llword_t*>(m->xchg_peer[gpu]) + ((layer * 2 + (size_t)which) * m->world) * (size_t)m->args.dim;
+}
 
 static cudaError_t smem_optin(lmrs_b200* m, const void* fn, size_t smem);
 
@@ -389,12 +401,12 @@ static EncodeTiledFn encode_tiled_fn() {
     return fn;
 }
 // [rows][row_bytes] byte matrix, box 128 bytes x 128 rows, 128B swizzle (the K-major UMMA operand layout)
-static int make_tmap_2d(CUtensorMap* map, const void* base, size_t row_bytes, size_t rows) {
+static int make_tmap_2d(CUtensorMap* map, const void* base, size_t row_bytes, size_t rows, int box_rows = 128) {
     EncodeTiledFn enc = encode_tiled_fn();
     if (!enc) return fail("cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t gdim[2] = {(cuuint64_t)row_bytes, (cuuint64_t)rows};
     cuuint64_t gstride[1] = {(cuuint64_t)row_bytes};
-    cuuint32_t box[2] = {128, 128};
+    cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -403,14 +415,37 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, size_t row_bytes, si
     return 0;
 }
 static bool gemm_shape_ok(int n, int o) { return n % 128 == 0 && o % 128 == 0; }
-// out[t][i] for t < T: tcgen05 int8 GEMM of xq [T][n] (with xs [T][n/128]) against the dense copy of w
+// out[t][i] for t < T: tcgen05 int8 GEMM of xq [T][n] (with xs [T][n/128]) against the dense copy of w.  Tile shape: 128
+// output rows of w per CTA, or 64 when that is what it takes to give every SM a tile (Wo / W2 of the 1B..3B models).
 static int launch_gemm(lmrs_b200* m, const Mat& w, const uint8_t* xq, const float* xs, int T, GemmParams gp) {
     CUtensorMap ta;
     if (make_tmap_2d(&ta, xq, (size_t)w.n, (size_t)T)) return 1;
-    CK(smem_optin(m, (const void*)gemm_q8_kernel, GEMM_SMEM));
-    gp.T = T; gp.n = w.n; gp.o = w.o; gp.ws = w.ds; gp.xs = xs;
-    dim3 grid(w.o / GEMM_N, (T + GEMM_M - 1) / GEMM_M);
-    gemm_q8_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, m->stream>>>(ta, w.tmap, gp);
+    gp.T = T; gp.n = w.n; gp.o = w.o; gp.ws = w.ds; gp.xs = xs; gp.neg_zero = -0.0f;
+    const int mt = (T + GEMM_M - 1) / GEMM_M;
+    static const int force_bn = env_int("LMRS_B200_GEMM_BN", 0);   // developer knob
+    const bool narrow = force_bn ? force_bn == 64 : (w.o / 128) * mt < m->sms;
+    if (narrow) {
+        const size_t smem = gemm_smem_bytes<64>(w.n);
+        CK(smem_optin(m, (const void*)gemm_q8_kernel<64, false>, smem));
+        gemm_q8_kernel<64, false><<<dim3(w.o / 64, mt), GEMM_THREADS, smem, m->stream>>>(ta, w.tmap64, w.tmap64, gp);
+    } else {
+        const size_t smem = gemm_smem_bytes<128>(w.n);
+        CK(smem_optin(m, (const void*)gemm_q8_kernel<128, false>, smem));
+        gemm_q8_kernel<128, false><<<dim3(w.o / 128, mt), GEMM_THREADS, smem, m->stream>>>(ta, w.tmap, w.tmap, gp);
+    }
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+// h[t][i] = act(w1[i] . x[t]) * (w3[i] . x[t]): gate and up in ONE launch, each CTA tile = 64 rows of w1 + the same 64 rows of w3
+static int launch_gemm_glu(lmrs_b200* m, const Mat& w1, const Mat& w3, const uint8_t* xq, const float* xs, int T, float* h, int ld, int epi) {
+    CUtensorMap ta;
+    if (make_tmap_2d(&ta, xq, (size_t)w1.n, (size_t)T)) return 1;
+    GemmParams gp{};
+    gp.T = T; gp.n = w1.n; gp.o = w1.o; gp.ws = w1.ds; gp.ws2 = w3.ds; gp.xs = xs; gp.out0 = h; gp.ld0 = ld; gp.glu_epi = epi; gp.neg_zero = -0.0f;
+    const size_t smem = gemm_smem_bytes<128>(w1.n);
+    CK(smem_optin(m, (const void*)gemm_q8_kernel<128, true>, smem));
+    gemm_q8_kernel<128, true><<<dim3(w1.o / 64, (T + GEMM_M - 1) / GEMM_M), GEMM_THREADS, smem, m->stream>>>(ta, w1.tmap64, w3.tmap64, gp);
     m->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -637,7 +672,10 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     auto mkd = [&](Mat& x, const MatPlan& pl) {   // dense views + TMA descriptor
         if (!m->use_gemm) return;
         x.dq = m->d_dense + pl.q; x.ds = (const float*)(m->d_dense + pl.s);
-        if (gemm_shape_ok(pl.n, pl.o)) { if (make_tmap_2d(&x.tmap, x.dq, (size_t)pl.n, (size_t)pl.o)) tmap_err = 1; else x.has_tmap = true; }
+        if (gemm_shape_ok(pl.n, pl.o)) {
+            if (make_tmap_2d(&x.tmap, x.dq, (size_t)pl.n, (size_t)pl.o) || make_tmap_2d(&x.tmap64, x.dq, (size_t)pl.n, (size_t)pl.o, 64)) tmap_err = 1;
+            else x.has_tmap = true;
+        }
     };
     auto mk = [&](size_t off, int o, int n) { Mat x; x.q = m->d_arena + off; x.s = nullptr; x.o = o; x.n = n; x.gran = gran_for(n); return x; };
     auto fp = [&](size_t o) { return (const float*)(m->d_arena + o); };
@@ -687,7 +725,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     CK(cudaMalloc(&m->d_wo_out, dim * 4));
     CK(cudaMalloc(&m->d_h, lh * 4));
     CK(cudaMalloc(&m->d_down_out, dim * 4));
-    CK(cudaMalloc(&m->d_logits, (size_t)a.vocab_size * 4));
+    if (!m->use_peer) CK(cudaMalloc(&m->d_logits, (size_t)a.vocab_size * 4));   // peer mode: lives in the exchange block (setup_peer_exchange)
     CK(cudaMalloc(&m->d_scores, (size_t)m->l_heads * align_up(a.seq_len, 4) * 4));
     {
         const LLLayout Y0 = ll_layout(m);
@@ -731,6 +769,30 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
         P.g.ll = ll;
         return P;
     };
+    // L2 prefetch (LMRS_B200_L2PF): while a block's latency-bound middle runs, HBM is idle; the rest of the block's weights
+    // (through the next block's [Wq;Wk;Wv]; after the last block: the first part of a tied classifier) form ONE contiguous
+    // arena range (pack order of build_model) that idle CTAs ask the L2 to fetch.  1: the attention kernel's CTAs request
+    // from Wo on; 2: the Wo kernel's CTAs (parked in their dependency wait while the attention runs) request from W1 on.
+    auto l2pf_range = [&](size_t l, const uint8_t* lo, const uint8_t*& ptr, unsigned long long& bytes, int& chunk) {
+        const Layer& Y = m->layers[l];
+        const uint8_t* hi;
+        if (l + 1 < L) hi = m->layers[l + 1].qkv.q + bp16_bytes(a.q_type, m->layers[l + 1].qkv.o, m->layers[l + 1].qkv.n);
+        else {
+            const size_t extra = (m->cls.q == m->emb.q && m->world == 1) ? ((size_t)m->l2pf_cls_mb << 20) : (size_t)65536;
+            hi = std::min<const uint8_t*>(m->d_arena + m->arena_bytes, Y.w2.q + bp16_bytes(a.q_type, Y.w2.o, Y.w2.n) + extra);
+        }
+        if (hi > lo) { ptr = lo; bytes = ((unsigned long long)(hi - lo)) & ~15ull; chunk = m->l2pf_ef ? -m->l2pf_chunk : m->l2pf_chunk; }
+    };
+    const bool peer = m->use_peer;
+    const llword_t* px_pending = nullptr;   // peer mode: the pending contribution lives in this GPU's exchange vector
+    auto px_push = [&](GemvParams& g, size_t layer, int which) {   // the producer writes its slot on every GPU
+        g.px_world = m->world;
+        for (int r = 0; r < m->world; r++) g.px_out[r] = px_vec(m, r, layer, which) + (size_t)m->rank * a.dim;
+    };
+    auto px_take = [&](GemvParams& g) {                             // the consumer sums the slots in rank order
+        if (!px_pending) return;
+        g.px_world = m->world; g.px_in = px_pending; g.delta = px_pending;
+    };
     for (size_t l = 0; l < L; l++) {
         const Layer& Y = m->layers[l];
         float* kc = m->d_kcache + l * (size_t)a.seq_len * m->l_kv_dim;
@@ -759,6 +821,7 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
             }
             p.epi = EPI_QKV; p.out = b_q; p.out_k = b_knew; p.out_v = b_vnew;
             p.att_dim = m->l_att_dim; p.kv_dim = m->l_kv_dim;
+            if (peer) px_take(p);
             ph.push_back(P);
         }
         {   // RoPE + attention (:443-544)
@@ -771,12 +834,15 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
             p.kv_dim = m->l_kv_dim; p.kv_mul = a.n_heads / a.n_kv_heads;
             p.chunks = m->att_chunks; p.gemma = gemma; p.seq_len = (int)align_up(a.seq_len, 4);
             p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step; p.ll = ll;
+            if (m->l2pf == 1 && !serial_prefill) l2pf_range(l, Y.wo.q, p.l2pf_ptr, p.l2pf_bytes, p.l2pf_chunk);   // requested by the attention CTAs
             ph.push_back(P);
         }
         {   // quantize(att) -> Wo (:546-560)
             Phase P = gemv_phase(Y.wo, nullptr);
             P.g.pro = PRO_QUANT; P.g.act_in = b_att; P.g.epi = EPI_STORE; P.g.out = b_wo;
-            P.comm = 1;   // row-sharded mode: all-reduce the output
+            if (m->l2pf == 2 && !serial_prefill && !ll) l2pf_range(l, Y.w1.q, P.g.l2pf_ptr, P.g.l2pf_bytes, P.g.l2pf_chunk);
+            P.comm = peer ? 0 : 1;   // row-sharded mode: push the partial to every GPU / NCCL all-reduce of the output
+            if (peer) { px_push(P.g, l, 0); px_pending = px_vec(m, m->rank, l, 0); }
             ph.push_back(P);
         }
         {   // x += wo_out (Gemma: normed) -> rmsnorm -> quantize -> gate/up -> act*up (:562-624)
@@ -785,12 +851,14 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
             p.pro = PRO_NORM; p.x_in = b_xo1; p.delta = b_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
             p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = b_xo0; p.eps = a.rms_norm_eps;
             p.unit_offset = gemma; p.epi = gemma ? EPI_GLU_GELU : EPI_GLU_SILU; p.out = b_h;
+            if (peer) px_take(p);
             ph.push_back(P);
         }
         {   // quantize(hidden) -> W2 (:626-640)
             Phase P = gemv_phase(Y.w2, nullptr);
             P.g.pro = PRO_QUANT; P.g.act_in = b_h; P.g.epi = EPI_STORE; P.g.out = b_down;
-            P.comm = 1;
+            P.comm = peer ? 0 : 1;
+            if (peer) { px_push(P.g, l, 1); px_pending = px_vec(m, m->rank, l, 1); }
             ph.push_back(P);
         }
         x_cur = b_xo0;
@@ -805,14 +873,29 @@ static std::vector<Phase> make_phases(lmrs_b200* m, bool serial_prefill) {
         p.epi = EPI_LOGITS; p.out = m->d_logits + m->vocab_off;
         int cap = gemma ? (int)a.dim - m->vocab_off : 0;
         p.softcap_rows = cap < 0 ? 0 : (cap > m->l_vocab ? m->l_vocab : cap);
-        P.comm = 2;   // row-sharded mode: all-gather logits
+        P.comm = peer ? 0 : 2;   // row-sharded mode: rows written into every GPU's logits buffer / NCCL all-gather
+        if (peer) {
+            px_take(p);
+            p.px_world = m->world;
+            for (int r = 0; r < m->world; r++) p.px_logits[r] = reinterpret_cast<float*>(m->xchg_peer[r] + m->xchg_logits_off) + m->vocab_off;
+        }
         ph.push_back(P);
+        if (peer) {   // "my rows have landed everywhere" / wait for everybody else's
+            Phase F;
+            memset(&F, 0, sizeof F);
+            F.kind = PH_PEERFLAG;
+            for (int r = 0; r < m->world; r++) F.f.flag_peer[r] = reinterpret_cast<uint32_t*>(m->xchg_peer[r] + m->xchg_flags_off);
+            F.f.flag_local = reinterpret_cast<const uint32_t*>(m->d_xchg + m->xchg_flags_off);
+            F.f.world = m->world; F.f.rank = m->rank; F.f.step = m->d_step;
+            ph.push_back(F);
+        }
     } else {                 // fill_kv_cache returns the residual stream: apply the pending add (:642-656)
         Phase P;
         memset(&P, 0, sizeof P);
         P.kind = PH_FINALIZE;
         P.r.x_in = x_cur; P.r.delta = delta; P.r.w_post = w_post; P.r.n = a.dim; P.r.eps = a.rms_norm_eps;
         P.r.rows = m->d_rows; P.r.step = m->d_step; P.r.ll = ll; P.r.scratch = m->d_fin_scratch;
+        if (peer && px_pending) { P.r.px_world = m->world; P.r.px_in = px_pending; }
         ph.push_back(P);
     }
     return ph;
@@ -833,7 +916,7 @@ static int enqueue_step(lmrs_b200* m, bool decode, bool nowait = false, int only
         if (m->d_trace && P.kind == PH_ATTN) P.a.trace_slot = slot;
         slot++;
         if (only_kind >= 0 && P.kind != only_kind) continue;
-        P.g.ll_nowait = P.a.ll_nowait = P.r.ll_nowait = nowait;
+        P.g.ll_nowait = P.a.ll_nowait = P.r.ll_nowait = P.f.nowait = nowait;
         // the first kernel of a step is an ordinary launch: it starts after EVERYTHING earlier in the stream has
         // completed, which is what lets later kernels of the step touch older KV rows (and reuse the LL buffers of the
         // previous step) without any further synchronisation
@@ -848,6 +931,8 @@ static int enqueue_step(lmrs_b200* m, bool decode, bool nowait = false, int only
         } else if (P.kind == PH_ATTN) {
             if (m->att_variant != ATT_LEGACY) e = launch_attn_cluster(m, P.a, m->l_kv_heads, m->att_var[m->att_variant].cap, m->att_var[m->att_variant].g);
             else e = launch_attn(m, P.a, m->l_kv_heads);
+        } else if (P.kind == PH_PEERFLAG) {
+            e = launch(m, peer_flag_kernel, dim3(1), dim3(32), 0, P.f);
         } else {
             e = launch(m, residual_finalize_kernel, dim3(1), dim3(256), 0, P.r);
         }
@@ -926,6 +1011,18 @@ static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
 
 // batched-rows attention (prefill_attn.cuh): scores + softmax per (token, head) thread, then a*v per (token, head, 8 dims) thread
 template <int HS> static int launch_prefill_attn_t(lmrs_b200* m, const PrefillAttnParams& p, int n_kv_heads) {
+    if (m->use_pf_attn == 1) {   // fused form: score rows in shared memory
+        const int scs = prefill_fused_scs(p.pos + p.n);
+        const int tb = prefill_fused_tb(HS, p.kv_mul, p.pos + p.n);
+        const size_t smem = prefill_fused_smem(HS, tb * p.kv_mul, scs);
+        if (tb > 0) {
+            CK(smem_optin(m, (const void*)prefill_attn_fused_kernel<HS>, smem));
+            prefill_attn_fused_kernel<HS><<<dim3((unsigned)((p.n + tb - 1) / tb), (unsigned)n_kv_heads), PFF_THREADS, smem, m->stream>>>(p, tb, scs);
+            m->launches++;
+            CK(cudaGetLastError());
+            return 0;
+        }
+    }
     const int TB = PFA_THREADS / p.kv_mul;
     CK(smem_optin(m, (const void*)prefill_scores_kernel<HS>, prefill_scores_smem<HS>()));
     prefill_scores_kernel<HS><<<dim3((unsigned)((p.n + TB - 1) / TB), (unsigned)n_kv_heads), PFA_THREADS, prefill_scores_smem<HS>(), m->stream>>>(p);
@@ -950,7 +1047,11 @@ static int launch_prefill_attn(lmrs_b200* m, const PrefillAttnParams& p, int n_k
 }
 
 static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
-    if (!m->use_gemm || n < 8 || pos + n > (size_t)ATT_SC_CAP) return false;
+    if (!m->use_gemm || n < 8) return false;
+    // attention of the batch: the fused kernel keeps whole score rows in shared memory (any context the KV cache holds for
+    // the shipped shapes); the older forms stop at ATT_SC_CAP positions
+    const bool fused = m->use_pf_attn == 1 && prefill_fused_tb((int)m->args.head_size, (int)(m->args.n_heads / m->args.n_kv_heads), (int)(pos + n)) > 0;
+    if (!fused && pos + n > (size_t)ATT_SC_CAP) return false;
     for (const Layer& Y : m->layers)
         for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
             if (!x->has_tmap) return false;
@@ -976,18 +1077,23 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
     const lmrs_args_t& a = m->args;
     const int T = (int)n, dim = a.dim, att = m->l_att_dim, kvd = m->l_kv_dim, hid = m->l_hidden;
     const bool gemma = a.model_type == 0;
-    const size_t sc_stride = align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // batched rows: pos + n <= ATT_SC_CAP
+    const bool fused_attn = m->use_pf_attn == 1 && prefill_fused_tb((int)a.head_size, (int)(a.n_heads / a.n_kv_heads), (int)(pos + n)) > 0;
+    const size_t sc_stride = fused_attn ? 4 : align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // score scratch of the unfused forms (pos + n <= ATT_SC_CAP)
     if (m->pf_cap < n) {
-        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down, (void*)m->pf_scores}) cudaFree(p);
-        m->pf_xq = nullptr; m->pf_xs = m->pf_q = m->pf_att = m->pf_wo = m->pf_g = m->pf_u = m->pf_h = m->pf_down = m->pf_scores = nullptr;
+        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
+        m->pf_xq = nullptr; m->pf_xs = m->pf_q = m->pf_att = m->pf_wo = m->pf_g = m->pf_u = m->pf_h = m->pf_down = nullptr;
         m->pf_cap = 0;   // a failed allocation below must not leave a capacity behind
         const size_t nmax = std::max<size_t>(std::max<size_t>(dim, att), hid);
         CK(cudaMalloc(&m->pf_xq, n * nmax)); CK(cudaMalloc(&m->pf_xs, n * (nmax / GS) * 4));
         CK(cudaMalloc(&m->pf_q, n * att * 4)); CK(cudaMalloc(&m->pf_att, n * att * 4)); CK(cudaMalloc(&m->pf_wo, n * dim * 4));
-        CK(cudaMalloc(&m->pf_g, n * hid * 4)); CK(cudaMalloc(&m->pf_u, n * hid * 4)); CK(cudaMalloc(&m->pf_h, n * hid * 4));
+        CK(cudaMalloc(&m->pf_h, n * hid * 4));   // (pf_g / pf_u: unused since gate/up are fused)
         CK(cudaMalloc(&m->pf_down, n * dim * 4));
-        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * sc_stride * 4));
         m->pf_cap = n;
+    }
+    if (!fused_attn && m->pf_sc_bytes < n * (size_t)m->l_heads * sc_stride * 4) {   // score scratch of the unfused attention forms
+        cudaFree(m->pf_scores); m->pf_scores = nullptr; m->pf_sc_bytes = 0;
+        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * sc_stride * 4));
+        m->pf_sc_bytes = n * (size_t)m->l_heads * sc_stride * 4;
     }
     if (push_step(m, 0, pos, pos)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
     const float* delta = nullptr;
@@ -1014,7 +1120,7 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
             PrefillAttnParams p{};
             p.q = m->pf_q; p.kcache = kc; p.vcache = vc; p.probs = m->pf_scores; p.out = m->pf_att;
             p.n = T; p.pos = (int)pos; p.t_cap = (int)sc_stride; p.att_dim = att; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads;
-            p.gemma = gemma; p.mask_base = pos; p.sqrt_hs = sqrtf((float)a.head_size);
+            p.gemma = gemma; p.mask_base = pos; p.sqrt_hs = sqrtf((float)a.head_size); p.neg_zero = -0.0f;
             if (launch_prefill_attn(m, p, m->l_kv_heads)) return 1;
         } else {
             AttnParams p{};
@@ -1038,12 +1144,8 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
             p.n = dim; p.pro = PRO_NORM; p.x_in = m->d_rows; p.delta = m->pf_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
             p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
             if (launch_rows_prologue(m, p, T)) return 1;
-            if (launch_gemm(m, Y.w1, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_g, hid, hid))) return 1;
-            if (launch_gemm(m, Y.w3, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_u, hid, hid))) return 1;
-            const size_t cnt = (size_t)T * hid;
-            glu_rows_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, m->stream>>>(m->pf_h, m->pf_g, m->pf_u, cnt, gemma ? EPI_GLU_GELU : EPI_GLU_SILU);
-            m->launches++;
-            CK(cudaGetLastError());
+            // gate and up in one launch with act(gate) * up in its epilogue (:607-624): g and u never travel through HBM
+            if (launch_gemm_glu(m, Y.w1, Y.w3, m->pf_xq, m->pf_xs, T, m->pf_h, hid, gemma ? EPI_GLU_GELU : EPI_GLU_SILU)) return 1;
         }
         {
             GemvParams p{};
@@ -1066,6 +1168,39 @@ static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
 static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
     if (gemm_prefill_ok(m, n, pos)) return prefill_gemm(m, n, pos);
     return prefill_serial(m, n, pos);
+}
+
+// N-GPU mode: allocate this GPU's exchange block and map every peer's (CUDA IPC; handles travel through one NCCL all-gather)
+static int setup_peer_exchange(lmrs_b200* m) {
+    const size_t W = (size_t)m->world, dim = m->args.dim, L = m->args.n_layers;
+    if (W > (size_t)PX_MAX_WORLD) return fail("peer exchange supports up to 8 GPUs");
+    const size_t px_bytes = L * 2 * W * dim * sizeof(llword_t);
+    m->xchg_flags_off = align_up(px_bytes, 256);
+    m->xchg_logits_off = m->xchg_flags_off + 256;
+    const size_t total = m->xchg_logits_off + (size_t)m->args.vocab_size * 4;
+    CK(cudaMalloc(&m->d_xchg, total));
+    CK(cudaMemset(m->d_xchg, 0, total));   // sequence number 0 = "never written"
+    CK(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mine;
+    CK(cudaIpcGetMemHandle(&mine, m->d_xchg));
+    uint8_t* d_h = nullptr;
+    CK(cudaMalloc(&d_h, (W + 1) * sizeof(mine)));
+    CK(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    if (shard_allgather_bytes(m->shard, d_h, d_h + sizeof(mine), sizeof(mine), m->stream)) { cudaFree(d_h); return fail(shard_error()); }
+    CK(cudaStreamSynchronize(m->stream));
+    std::vector<cudaIpcMemHandle_t> all(W);
+    CK(cudaMemcpy(all.data(), d_h + sizeof(mine), W * sizeof(mine), cudaMemcpyDeviceToHost));
+    cudaFree(d_h);
+    for (size_t r = 0; r < W; r++) {
+        if ((int)r == m->rank) { m->xchg_peer[r] = m->d_xchg; continue; }
+        void* ptr = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess)
+            return fail(std::string("cudaIpcOpenMemHandle (peer exchange between GPUs; LMRS_B200_PEER=0 selects the NCCL data path): ") + cudaGetErrorString(e));
+        m->xchg_peer[r] = (uint8_t*)ptr;
+    }
+    m->d_logits = reinterpret_cast<float*>(m->d_xchg + m->xchg_logits_off);
+    return 0;
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------------
@@ -1099,13 +1234,21 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     // 0.3-0.6 us, a hand-over needs two or three of them, and co-resident waiting kernels slow the running one; see
     // profiles/r2_decode_experiments.md), so it is opt-in.
     m->use_ll = env_int("LMRS_B200_LL", 0) != 0 && world == 1;
-    m->use_pf_attn = env_int("LMRS_B200_PF_ATTN", 1) != 0;
+    m->use_pf_attn = env_int("LMRS_B200_PF_ATTN", 1);
+    m->l2pf = env_int("LMRS_B200_L2PF", 0);
+    m->l2pf_ef = env_int("LMRS_B200_L2PF_EF", 1);
+    m->l2pf_cls_mb = env_int("LMRS_B200_L2PF_CLS_MB", 24);
+    m->l2pf_chunk = std::max(1024, env_int("LMRS_B200_L2PF_CHUNK", 32768)) & ~15;
+    // N-GPU data path: partial vectors pushed between the GPUs by the kernels themselves (default), or NCCL collectives
+    // between the kernels (LMRS_B200_PEER=0)
+    m->use_peer = world > 1 && env_int("LMRS_B200_PEER", 1) != 0;
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
     if ((int)m->args.dim > NORM_MAX_DIM) {
         lmrs_b200_destroy(m);
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
+    if (m->use_peer && setup_peer_exchange(m)) { lmrs_b200_destroy(m); return 1; }
     setup_attn_cluster(m);
     if (setup_trace(m)) { lmrs_b200_destroy(m); return 1; }
     m->ph_decode = make_phases(m, false);
@@ -1135,11 +1278,14 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
         if (m->g_decode[v]) cudaGraphExecDestroy(m->g_decode[v]);
         if (m->g_prefill[v]) cudaGraphExecDestroy(m->g_prefill[v]);
     }
+    for (int r = 0; r < m->world && r < PX_MAX_WORLD; r++)
+        if (m->xchg_peer[r] && m->xchg_peer[r] != m->d_xchg) cudaIpcCloseMemHandle(m->xchg_peer[r]);
+    cudaFree(m->d_xchg);
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
     cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->pf_scores); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);
     cudaFree(m->d_x[0]); cudaFree(m->d_x[1]); cudaFree(m->d_q); cudaFree(m->d_knew); cudaFree(m->d_att);
-    cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); cudaFree(m->d_logits); cudaFree(m->d_scores);
+    cudaFree(m->d_wo_out); cudaFree(m->d_h); cudaFree(m->d_down_out); if (!m->d_xchg) cudaFree(m->d_logits); cudaFree(m->d_scores);
     cudaFree(m->d_step); cudaFree(m->d_rows); cudaFree(m->d_ll); cudaFree(m->d_fin_scratch);
     cudaFree(m->d_amax); cudaFree(m->d_aidx); cudaFree(m->d_ticket); cudaFree(m->d_next); cudaFree(m->d_gen);
     if (m->h_gen) cudaFreeHost(m->h_gen);
@@ -1199,7 +1345,7 @@ static int launch_argmax(lmrs_b200* m, uint32_t* d_out, bool advance) {
 }
 extern "C" int lmrs_b200_forward_argmax(lmrs_b200_t* m, uint32_t token, uint32_t pos, uint32_t* next_token) {
     if (!next_token) return fail("null argument");
-    if (m && m->world > 1) return fail("forward_argmax: single-GPU handles only");
+    if (m && m->world > 1 && !m->use_peer) return fail("forward_argmax: not with the NCCL data path (LMRS_B200_PEER=0)");   // peer mode: every GPU holds all logits rows
     if (lmrs_b200_forward_device(m, token, pos)) return 1;
     if (ensure_gen(m, 64)) return 1;
     if (launch_argmax(m, m->d_next, false)) return 1;
@@ -1215,7 +1361,7 @@ extern "C" int lmrs_b200_forward_argmax(lmrs_b200_t* m, uint32_t token, uint32_t
 extern "C" int lmrs_b200_generate_greedy(lmrs_b200_t* m, uint32_t first_token, uint32_t pos, uint32_t max_new, int32_t eos,
                                          uint32_t* out_tokens, uint32_t* n_out) {
     if (!m || !out_tokens || !n_out) return fail("null argument");
-    if (m->world > 1) return fail("generate_greedy: single-GPU handles only");
+    if (m->world > 1 && !m->use_peer) return fail("generate_greedy: not with the NCCL data path (LMRS_B200_PEER=0)");
     if (first_token >= m->args.vocab_size) return fail("token out of range");
     if ((size_t)pos + max_new > m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
     CK(cudaSetDevice(m->device));

@@ -17,7 +17,9 @@ struct ResidualParams {
     const StepParams* step;
     int row_from_block;        // batched prefill: row = blockIdx.x and x_in/delta are row-strided too
     int ll, ll_nowait;         // serial prefill inside the LL decode chain (never with row_from_block)
-    float* scratch;            // ll: [n] f32 scratch for the Gemma post-norm chain
+    float* scratch;            // ll / px: [n] f32 scratch for the unpacked contribution
+    int px_world;              // N-GPU peer exchange: delta = rank-ordered sum of the px_world slots of px_in ([px_world][n] words)
+    const llword_t* px_in;
 };
 LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
     const size_t row = p.row_from_block ? (size_t)blockIdx.x : (size_t)p.step->token;
@@ -25,7 +27,17 @@ LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
     const float* x_in = reinterpret_cast<const float*>(p.x_in) + (p.row_from_block ? row * p.n : 0);
     const float* delta = reinterpret_cast<const float*>(p.delta) + (p.row_from_block ? row * p.n : 0);
     const uint32_t seq = p.ll ? p.step->seq : 0u;
-    if (p.ll) {   // unpack delta once (the exact chain below wants a plain array)
+    if (p.px_world > 1) {   // N-GPU mode: sum the partials the GPUs pushed here, in rank order (see gemv.cuh px_gather_sum)
+        const uint32_t pseq = p.step->seq;
+        px_canary_wait(p.px_in, p.px_world, p.n, pseq, p.ll_nowait != 0);
+        for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
+            float d = px_wait1(p.px_in + i, pseq, p.ll_nowait != 0);
+            for (int r = 1; r < p.px_world; r++) d = __fadd_rn(d, px_wait1(p.px_in + (size_t)r * p.n + i, pseq, p.ll_nowait != 0));
+            p.scratch[i] = d;
+        }
+        __syncthreads();
+        delta = p.scratch;
+    } else if (p.ll) {   // unpack delta once (the exact chain below wants a plain array)
         ll_canary_wait(reinterpret_cast<const llword_t*>(p.delta), seq, p.ll_nowait != 0);
         for (int i = threadIdx.x; i < p.n; i += blockDim.x)
             p.scratch[i] = ll_wait1(reinterpret_cast<const llword_t*>(p.delta) + i, seq, p.ll_nowait != 0);
@@ -35,7 +47,7 @@ LMRS_DEVINL void residual_finalize_body(const ResidualParams& p, float* red) {
     float r = 1.0f;
     if (p.w_post) r = exact_rnorm(delta, p.n, p.eps, red);   // chains read global memory directly
     for (int i = threadIdx.x; i < p.n; i += blockDim.x) {
-        float d = p.ll ? delta[i] : __ldcg(delta + i);
+        float d = (p.ll || p.px_world > 1) ? delta[i] : __ldcg(delta + i);
         if (p.w_post) d = __fmul_rn(__fadd_rn(1.0f, p.w_post[i]), __fmul_rn(r, d));
         const float xv = p.ll ? ll_wait1(reinterpret_cast<const llword_t*>(p.x_in) + i, seq, p.ll_nowait != 0) : __ldcg(x_in + i);
         out[i] = __fadd_rn(xv, d);
@@ -46,6 +58,35 @@ __global__ void __launch_bounds__(256) residual_finalize_kernel(const ResidualPa
     pdl_launch_dependents();
     if (!p.ll) pdl_wait();
     residual_finalize_body(p, red);
+}
+
+// ---- N-GPU mode: "my logits rows have landed everywhere" ------------------------------------------------------------------
+// Runs after the classifier (griddepcontrol.wait: all its stores, including the ones into the peers' logits buffers, are
+// performed).  Thread r tells GPU r so (release at system scope) and waits until GPU r has told this GPU the same: when the
+// kernel ends, this GPU's logits buffer holds every rank's rows of the step.
+struct PeerFlagParams {
+    uint32_t* flag_peer[PX_MAX_WORLD];   // GPU r's flag array (peer-mapped); this rank writes element `rank`
+    const uint32_t* flag_local;          // this GPU's flag array; element r is written by GPU r
+    int world, rank, nowait;
+    const StepParams* step;
+};
+__global__ void __launch_bounds__(32) peer_flag_kernel(const PeerFlagParams p) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int r = threadIdx.x;
+    if (r >= p.world) return;
+    const uint32_t seq = p.step->seq;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_peer[r] + p.rank), "r"(seq) : "memory");
+    if (p.nowait) return;
+    const LLSpin sp = ll_spin_begin();
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flag_local + r) : "memory");
+        if (v == seq) break;
+        __nanosleep(100);
+        px_spin_check(sp);
+    }
 }
 
 // ---- batched prefill row kernels (fill_kv_cache, src/transformer.rs:672-684 -> forward_layer with sl = N) ----------

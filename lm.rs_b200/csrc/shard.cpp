@@ -11,7 +11,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { ncclFloat = 7, ncclSum = 0 };
+enum { ncclUint8 = 1, ncclFloat = 7, ncclSum = 0 };
 struct Api {
     void* h = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
@@ -68,6 +68,10 @@ int shard_allreduce(Shard& s, float* buf, size_t count, cudaStream_t stream) {
 int shard_allgather_logits(Shard& s, float* logits, size_t per_rank, cudaStream_t stream) {
     return ck(api.AllGather(logits + (size_t)s.rank * per_rank, logits, per_rank, ncclFloat, (ncclComm_t)s.comm, stream),
               "ncclAllGather");
+}
+// `bytes` from every rank, in rank order (device buffers): carries the IPC handles of the peer-exchange buffers at load time
+int shard_allgather_bytes(Shard& s, const void* d_in, void* d_out, size_t bytes, cudaStream_t stream) {
+    return ck(api.AllGather(d_in, d_out, bytes, ncclUint8, (ncclComm_t)s.comm, stream), "ncclAllGather");
 }
 void shard_destroy(Shard& s) {
     if (s.comm && api.CommDestroy) api.CommDestroy((ncclComm_t)s.comm);

@@ -143,8 +143,18 @@ void lmrs_ref_matmul_rest(float* xout, const float* x, const float* w, int rows,
 /* src/functional.rs:173-214.  Integer part exact (order-free); f32 part: per group, ascending,
  * xout += ((ival as f32) * ws) * xs, starting from 0.  Outputs beyond o/4*4 are not written
  * (par_chunks_exact_mut(4), :179). */
+static void matmul_q8_kshards(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                              int rows, int n, int o, int gs, int shards);
 void lmrs_ref_matmul_q8(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
                         int rows, int n, int o, int gs) {
+    matmul_q8_kshards(xout, xq, xs, wq, ws, rows, n, o, gs, 1);
+}
+/* `shards` > 1 is NOT a reference feature: it restates the summation order of lmrs_b200's row-sharded N-GPU mode
+ *  so that N-GPU runs can be checked bit for bit: the K groups are split into `shards` equal
+ * contiguous ranges, each range is accumulated from 0.0 in ascending order (one GPU's partial), and the partials are
+ * added in ascending rank order starting from rank 0's. */
+static void matmul_q8_kshards(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                              int rows, int n, int o, int gs, int shards) {
     int o4 = o / 4 * 4;
     int ng = n / gs; /* (0..=(n-gs)).step_by(gs) */
 #pragma omp parallel for collapse(2) schedule(static)
@@ -154,17 +164,21 @@ void lmrs_ref_matmul_q8(float* xout, const int8_t* xq, const float* xs, const in
             for (int u = 0; u < 4; u++) {
                 int i = i4 + u;
                 const int8_t* wr = wq + (size_t)i * n;
-                float acc = 0.0f;
-                for (int g = 0; g < ng; g++) {
-                    int32_t ival = 0;
-                    const int8_t* xa = xr + g * gs;
-                    const int8_t* wa = wr + g * gs;
-                    for (int k = 0; k < gs / 8 * 8; k++) ival += (int32_t)xa[k] * (int32_t)wa[k];
-                    float t = (float)ival * ws[((size_t)i * n + (size_t)g * gs) / gs];
-                    t = t * xs[((size_t)r * n + (size_t)g * gs) / gs];
-                    acc += t;
+                float total = 0.0f;
+                for (int sh = 0; sh < shards; sh++) {
+                    float acc = 0.0f;
+                    for (int g = sh * (ng / shards); g < (sh + 1 == shards ? ng : (sh + 1) * (ng / shards)); g++) {
+                        int32_t ival = 0;
+                        const int8_t* xa = xr + g * gs;
+                        const int8_t* wa = wr + g * gs;
+                        for (int k = 0; k < gs / 8 * 8; k++) ival += (int32_t)xa[k] * (int32_t)wa[k];
+                        float t = (float)ival * ws[((size_t)i * n + (size_t)g * gs) / gs];
+                        t = t * xs[((size_t)r * n + (size_t)g * gs) / gs];
+                        acc += t;
+                    }
+                    total = sh == 0 ? acc : total + acc;
                 }
-                xout[(size_t)r * o + i] = acc;
+                xout[(size_t)r * o + i] = total;
             }
         }
     }
@@ -174,8 +188,14 @@ void lmrs_ref_matmul_q8(float* xout, const int8_t* xq, const float* xs, const in
  * even element.  Reference bug (:224 `xi = j*n` although packed rows are n/2 bytes) makes rows>0
  * undefined in the reference; here rows>0 index x row-wise (xq + r*n/2, xs + r*n/gs), i.e. the
  * result every row would get if it were passed alone as row 0. */
+static void matmul_q4_kshards(float* xout, const uint8_t* xq, const float* xs, const uint8_t* wq, const float* ws,
+                              int rows, int n, int o, int gs, int shards);
 void lmrs_ref_matmul_q4(float* xout, const uint8_t* xq, const float* xs, const uint8_t* wq, const float* ws,
                         int rows, int n, int o, int gs) {
+    matmul_q4_kshards(xout, xq, xs, wq, ws, rows, n, o, gs, 1);
+}
+static void matmul_q4_kshards(float* xout, const uint8_t* xq, const float* xs, const uint8_t* wq, const float* ws,
+                              int rows, int n, int o, int gs, int shards) {
     int gb = gs / 2;     /* bytes per group */
     int ng = (n / 2) / gb;
 #pragma omp parallel for collapse(2) schedule(static)
@@ -184,19 +204,23 @@ void lmrs_ref_matmul_q4(float* xout, const uint8_t* xq, const float* xs, const u
             const uint8_t* xr = xq + (size_t)r * (n / 2);
             const float* xsr = xs + (size_t)r * (n / gs);
             const uint8_t* wr = wq + (size_t)i * (n / 2);
-            float acc = 0.0f; /* Iterator::sum::<f32>() */
-            for (int g = 0; g < ng; g++) {
-                int32_t ival = 0;
-                for (int k = 0; k < gb / 8 * 8; k++) {
-                    int xb = xr[g * gb + k], wb = wr[g * gb + k];
-                    ival += ((xb & 0x0F) - 8) * ((wb & 0x0F) - 8);
-                    ival += (((xb & 0xF0) >> 4) - 8) * (((wb & 0xF0) >> 4) - 8);
+            float total = 0.0f;
+            for (int sh = 0; sh < shards; sh++) {
+                float acc = 0.0f; /* Iterator::sum::<f32>() */
+                for (int g = sh * (ng / shards); g < (sh + 1 == shards ? ng : (sh + 1) * (ng / shards)); g++) {
+                    int32_t ival = 0;
+                    for (int k = 0; k < gb / 8 * 8; k++) {
+                        int xb = xr[g * gb + k], wb = wr[g * gb + k];
+                        ival += ((xb & 0x0F) - 8) * ((wb & 0x0F) - 8);
+                        ival += (((xb & 0xF0) >> 4) - 8) * (((wb & 0xF0) >> 4) - 8);
+                    }
+                    float t = (float)ival * ws[((size_t)i * (n / 2) + (size_t)g * gb) / gb];
+                    t = t * xsr[g];
+                    acc += t;
                 }
-                float t = (float)ival * ws[((size_t)i * (n / 2) + (size_t)g * gb) / gb];
-                t = t * xsr[g];
-                acc += t;
+                total = sh == 0 ? acc : total + acc;
             }
-            xout[(size_t)r * o + i] = acc;
+            xout[(size_t)r * o + i] = total;
         }
     }
 }
@@ -452,19 +476,25 @@ void lmrs_ref_rope_freq(int model_type, float rope_theta, int head_size, int j, 
 }
 
 /* quantize + matmul dispatch used 4x per layer (src/transformer.rs:424-438,550-558,593-603,630-638) */
+static int g_kshards = 1;   /* see matmul_q8_kshards: models lmrs_b200's N-GPU partial-sum order for Wo / W2 (not a reference feature) */
+void lmrs_ref_set_kshards(int n) { g_kshards = n < 1 ? 1 : n; }
+static void qmatmul_sh(const lmrs_ref_t* m, float* out, const float* in, const qt_t* w, int rows, int n, int o, int shards);
 static void qmatmul(const lmrs_ref_t* m, float* out, const float* in, const qt_t* w, int rows, int n, int o) {
+    qmatmul_sh(m, out, in, w, rows, n, o, 1);
+}
+static void qmatmul_sh(const lmrs_ref_t* m, float* out, const float* in, const qt_t* w, int rows, int n, int o, int shards) {
     int gs = m->args.group_size;
     if (m->args.q_type == 1) {
         int8_t* q = (int8_t*)malloc((size_t)rows * n);
         float* s = (float*)malloc((size_t)rows * n / gs * 4);
         lmrs_ref_quantize_q8(q, s, in, rows * n, gs);
-        lmrs_ref_matmul_q8(out, q, s, (const int8_t*)w->q, w->s, rows, n, o, gs);
+        matmul_q8_kshards(out, q, s, (const int8_t*)w->q, w->s, rows, n, o, gs, shards);
         free(q); free(s);
     } else {
         uint8_t* q = (uint8_t*)malloc((size_t)rows * n / 2);
         float* s = (float*)malloc((size_t)rows * n / gs * 4);
         lmrs_ref_quantize_q4(q, s, in, rows * n, gs);
-        lmrs_ref_matmul_q4(out, q, s, (const uint8_t*)w->q, w->s, rows, n, o, gs);
+        matmul_q4_kshards(out, q, s, (const uint8_t*)w->q, w->s, rows, n, o, gs, shards);
         free(q); free(s);
     }
 }
@@ -587,7 +617,7 @@ static int forward_layer(lmrs_ref_t* m, float* x, uint32_t sl, uint32_t l, uint3
     if (!m->quantized)
         lmrs_ref_matmul_f32(temp_embeddings, embeddings, m->wo_f + (size_t)l * dim * att_dim, sl, att_dim, dim);
     else
-        qmatmul(m, temp_embeddings, embeddings, &m->wo_q[l], sl, att_dim, dim);
+        qmatmul_sh(m, temp_embeddings, embeddings, &m->wo_q[l], sl, att_dim, dim, g_kshards);
 
     /* residual + norm :562-580 (rows of `embeddings` are re-used as dim-strided scratch) */
 #pragma omp parallel for schedule(static)
@@ -645,7 +675,7 @@ static int forward_layer(lmrs_ref_t* m, float* x, uint32_t sl, uint32_t l, uint3
     if (!m->quantized)
         lmrs_ref_matmul_f32(embeddings, hidden, m->w2_f + (size_t)l * dim * hidden_dim, sl, hidden_dim, dim);
     else
-        qmatmul(m, embeddings, hidden, &m->w2_q[l], sl, hidden_dim, dim);
+        qmatmul_sh(m, embeddings, hidden, &m->w2_q[l], sl, hidden_dim, dim, g_kshards);
 
     /* final residual :642-656 */
 #pragma omp parallel for schedule(static)

@@ -70,6 +70,10 @@ void lmrs_ref_dequantize(float* x, const void* q, const float* s, int n, int gs,
 /* RoPE frequency for pair index j (src/transformer.rs:445-478); writes freq and magnitude scale. */
 void lmrs_ref_rope_freq(int model_type, float rope_theta, int head_size, int j, float* freq, float* mscale);
 
+/* NOT a reference feature: Wo / W2 accumulate `n` contiguous K ranges separately and add the partials in ascending
+ * order -- the summation order of lmrs_b200's N-GPU row-sharded mode, so that N-GPU runs can be checked bit for bit. */
+void lmrs_ref_set_kshards(int n);
+
 int lmrs_ref_num_threads(void);
 void lmrs_ref_set_num_threads(int n);
 

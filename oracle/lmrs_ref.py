@@ -35,6 +35,12 @@ def set_threads(n):
     lib().lmrs_ref_set_num_threads(int(n))
 
 
+def set_kshards(n):
+    """NOT a reference feature: Wo / W2 accumulate n contiguous K ranges separately and add the partials in ascending
+    order -- the summation order of lmrs_b200's N-GPU row-sharded mode (checked bit for bit by the multi-GPU tests)."""
+    lib().lmrs_ref_set_kshards(int(n))
+
+
 def build(force=False):
     if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(os.path.join(_HERE, "lmrs_ref.c")):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
@@ -65,6 +71,8 @@ def lib():
             # shared hosts: nproc may far exceed the cgroup's CPU quota, and oversubscribed OpenMP spin-waits are
             # catastrophic (measured 11 s/token at 128 threads); default to the quota, capped at 32
             L.lmrs_ref_set_num_threads(min(32, usable_cores()))
+        L.lmrs_ref_set_kshards.argtypes = [C.c_int]
+        L.lmrs_ref_set_kshards.restype = None
         L.lmrs_ref_last_error.restype = C.c_char_p
         L.lmrs_ref_create.argtypes = [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
         L.lmrs_ref_destroy.argtypes = [C.c_void_p]

@@ -179,6 +179,31 @@ def test_decode_attention_position_buckets(gpu_lib, ref, lf, name):
         assert float(np.abs(lg - le).max()) <= TOL, f"{name} pos {pos}"
 
 
+@pytest.mark.parametrize("name", ["tiny-llama", "tiny-gemma", "tiny-phi", "small-llama"])
+def test_batched_prefill_ragged_multi_tile(gpu_lib, ref, lf, name):
+    """fill_kv_cache over several token tiles of the fused attention kernel, a ragged second batch at pos > 0 whose tiles
+    straddle the 32-position K/V tiles, then decode: residual stream, KV rows and logits against the oracle."""
+    a = lf.model_args(name, 1, seq_len=4096)
+    buf = lf.write_synthetic(a)
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    toks = prompt_tokens(a.vocab_size, 300 + 77 + 2, seed=11)
+    exact = a.model_type != 0
+    pos = 0
+    for n in (300, 77):
+        eg, ec = gpu.get_embeddings(toks[pos:pos + n]), cpu.get_embeddings(toks[pos:pos + n])
+        assert gpu.fill_kv_cache(eg, pos) == cpu.fill_kv_cache(ec, pos) == pos + n
+        assert np.array_equal(eg, ec) if exact else float(np.abs(eg - ec).max()) <= TOL, f"{name}: residual stream after {pos}+{n}"
+        pos += n
+    kg, vg = gpu.read_kv(a.n_layers - 1, 0, pos)
+    kc, vc = cpu.kv_cache()
+    if exact:
+        assert np.array_equal(kg, kc[a.n_layers - 1, :pos]) and np.array_equal(vg, vc[a.n_layers - 1, :pos])
+    for i in range(2):
+        lg, le = gpu.forward(int(toks[pos + i]), pos + i), cpu.forward(int(toks[pos + i]), pos + i)
+        assert np.array_equal(lg, le) if exact else float(np.abs(lg - le).max()) <= TOL, f"{name}: logits at {pos + i}"
+
+
 def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
     """matmul_q4 with sl > 1 is undefined in the reference (src/functional.rs:224): row-wise semantics, no GEMM path."""
     buf = synth("tiny-llama", 2)
@@ -193,11 +218,14 @@ def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
 
 @pytest.mark.parametrize("env", [{"LMRS_B200_LL": "1"}, {"LMRS_B200_LL": "1", "LMRS_B200_GEMV_CFG": "0"}, {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"},
                                  {"LMRS_B200_GRAPH": "0"}, {"LMRS_B200_GEMM": "0"}, {"LMRS_B200_GEMV_CFG": "1"}, {"LMRS_B200_GEMV_CFG": "4"},
-                                 {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "4"}, {"LMRS_B200_ATT_GROUPS": "1"}])
+                                 {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "4"}, {"LMRS_B200_ATT_GROUPS": "1"},
+                                 {"LMRS_B200_PF_ATTN": "2"}, {"LMRS_B200_PF_ATTN": "0"}, {"LMRS_B200_L2PF": "1"}, {"LMRS_B200_L2PF": "2"}, {"LMRS_B200_GEMM_BN": "128"},
+                                 {"LMRS_B200_GEMM_BN": "64"}])
 def test_alternative_execution_modes_stay_bit_exact(env):
     """fence-free LL exchange between co-resident kernels instead of kernel-boundary hand-overs (16- and 8-warp rings) /
     GPU-wide score kernel / no graph, no PDL / no graph / serial prefill / other ring geometries / single-CTA attention /
-    clusters of 4 / ungrouped heads: same bits as the default path."""
+    clusters of 4 / ungrouped heads / two-kernel and per-row prefill attention / L2 prefetch modes / forced GEMM tile widths:
+    same bits as the default path."""
     import subprocess
     import sys
     code = r'''

@@ -1,5 +1,9 @@
-"""Row-sharded forward on 2 GPUs (one process per GPU, NCCL all-reduce of the residual contribution twice per block)
-against the unsharded CPU oracle.  Partial sums re-associate the f32 accumulation -> tolerance 1e-3, not bit-equality."""
+"""Row-sharded forward on 2 (4, 8) GPUs, one process per GPU.
+
+Default data path: the peer exchange fused into the kernels (every GPU pushes its partial Wo / W2 result into all peers'
+exchange buffers over NVLink, the next prologue adds the partials in rank order).  That order is deterministic, and the
+oracle's k-shard mode (lmrs_ref.set_kshards) restates it, so LLAMA logits are checked BIT FOR BIT -- also on a deeper
+model.  The NCCL fallback (LMRS_B200_PEER=0) re-associates the sum inside the collective: tolerance 1e-3 on tiny models."""
 import os
 import socket
 import sys
@@ -15,9 +19,10 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, out_dir, name, expect_error=None):
+def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True):
     for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
+    os.environ["LMRS_B200_PEER"] = "1" if peer else "0"
     import torch
     import torch.distributed as dist
     import lmrs_b200
@@ -38,20 +43,27 @@ def _worker(rank, world, port, out_dir, name, expect_error=None):
     m, _ = lmrs_b200.Transformer.new_sharded(buf, rank, rank, world, bytes(idt.cpu().numpy().tobytes()))
     toks = np.random.default_rng(1).integers(0, m.args.vocab_size, 10)
     worst = 0.0
+    exact = True
     if rank == 0:
         import lmrs_ref
+        if peer:
+            lmrs_ref.set_kshards(world)   # the partial-sum order of the peer exchange
         cpu = lmrs_ref.RefTransformer(buf)
     emb = m.get_embeddings(toks[:4])
     assert m.fill_kv_cache(emb, 0) == 4
     if rank == 0:
         ec = cpu.get_embeddings(toks[:4]); cpu.fill_kv_cache(ec, 0)
         worst = max(worst, float(np.abs(emb - ec).max()))
+        exact = exact and np.array_equal(emb, ec)
     for i, t in enumerate(toks[4:]):
         lg = m.forward(int(t), 4 + i)
         if rank == 0:
-            worst = max(worst, float(np.abs(lg - cpu.forward(int(t), 4 + i)).max()))
+            le = cpu.forward(int(t), 4 + i)
+            worst = max(worst, float(np.abs(lg - le).max()))
+            exact = exact and np.array_equal(lg, le)
     if rank == 0:
         open(os.path.join(out_dir, "worst.txt"), "w").write(repr(worst))
+        open(os.path.join(out_dir, "exact.txt"), "w").write("1" if exact else "0")
     dist.barrier()
     dist.destroy_process_group()
 
@@ -59,12 +71,26 @@ def _worker(rank, world, port, out_dir, name, expect_error=None):
 # tiny models only: on deeper random-weight models any f32 re-association flips activation-quantization codes and the
 # deviation is amplified far beyond 1e-3, which is exactly what the partial sums of N > 1 do
 def test_two_gpu_sharded_forward_matches_oracle(tmp_path):
+    """NCCL fallback data path (collectives between the kernels)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "tiny-llama"), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "tiny-llama", None, False), nprocs=2, join=True)
     assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
+
+
+@pytest.mark.parametrize("world,name", [(2, "tiny-llama"), (2, "small-llama"), (4, "small-llama")])
+def test_peer_exchange_is_bit_exact_against_the_kshard_oracle(tmp_path, world, name):
+    """Default N-GPU data path: partials pushed between the GPUs by the kernels, added in rank order -> same bits as the
+    oracle in k-shard mode (fill_kv_cache residual stream and decode logits), tiny and 4-block models."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), name), nprocs=world, join=True)
+    assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
+    assert open(tmp_path / "exact.txt").read() == "1"
 
 
 def test_two_gpu_rejects_shapes_that_split_a_quantization_group(tmp_path):

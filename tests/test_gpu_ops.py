@@ -32,7 +32,7 @@ def test_matmul_q8_bit_exact(gpu_lib, ref, n, o, rows):
     assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
 
 
-@pytest.mark.parametrize("n,o,rows", [(128, 128, 8), (256, 128, 130), (2048, 2048, 128), (2048, 3072, 512), (8192, 2048, 200),
+@pytest.mark.parametrize("n,o,rows", [(128, 128, 8), (256, 128, 130), (2048, 2048, 128), (2048, 3072, 512), (2048, 8192, 300), (8192, 2048, 200),
                                       (3584, 256, 64), (384, 1152, 17)])
 def test_matmul_q8_batched_tcgen05_gemm_bit_exact(gpu_lib, ref, n, o, rows):
     """rows >= 8 and 128-aligned shapes run the tcgen05/TMEM int8 GEMM (the fill_kv_cache kernel): same bits as the CPU path."""
