@@ -57,6 +57,13 @@ int lmrs_b200_nccl_unique_id(void* out128);
 /* impl Drop for Transformer                                      src/transformer.rs:688-711 */
 void lmrs_b200_destroy(lmrs_b200_t* m);
 
+/* Transformer::new on `n_gpus` GPUs of THIS process (devices 0 .. n_gpus-1), the form SURVEY.md section 8b proposes: one
+ * handle per GPU behind the returned one, weights row-sharded like create_sharded, the GPUs mapped into one another with
+ * cudaDeviceEnablePeerAccess and exchanging their partial results from inside the kernels (no NCCL, no second process, no
+ * host synchronisation between the GPUs).  Every entry point below accepts the returned handle and drives all GPUs from
+ * the caller's thread; logits / token ids / the residual stream come back from GPU 0.  n_gpus <= 1: same as lmrs_b200_create. */
+int lmrs_b200_create_multi(const uint8_t* file, size_t len, int n_gpus, lmrs_b200_t** out, size_t* end_offset);
+
 /* pub args: TransformerArgs (vocab_size, model_type, multimodal are the pub fields the bins read:
  * src/bin/chat.rs:85,135,158); seq_len is returned clamped to 8192 as at src/transformer.rs:158-160. */
 int lmrs_b200_args(const lmrs_b200_t* m, lmrs_args_t* out);
@@ -132,6 +139,19 @@ int lmrs_b200_quantize_q8(int8_t* q, float* s, const float* x, int n, int gs);
 int lmrs_b200_quantize_q4(uint8_t* q, float* s, const float* x, int n, int gs);
 int lmrs_b200_rmsnorm(float* o, const float* x, const float* w, int size, float eps, int add_unit_offset);
 int lmrs_b200_softmax(float* x, int n);
+/* layernorm   src/functional.rs:80-114     `rows` independent rows of `size` elements (src/vision.rs normalises every token
+ *                                          row); the size % 8 tail of o is left as the caller passed it, like the reference */
+int lmrs_b200_layernorm(float* o, const float* x, const float* w, const float* b, int rows, int size, float eps);
+
+/* ---- quantized weights resident in HBM: QuantizedTensor views that src/vision.rs / src/processor.rs build once with
+ * init_param_quant (src/transformer.rs:24-48) and then apply to every token row.  upload copies the matrix (q: i8[o*n]
+ * for Q8_0, u8[o*n/2] for Q4_0; s: f32[o*n/gs]) to the current device once; matmul_w is matmul_q8 / matmul_q4
+ * (src/functional.rs:173-250) of `rows` quantized activation rows against it -- only the rows and the result cross PCIe.
+ * rows >= 8 of a Q8_0 matrix with 128-aligned shapes run on the tcgen05 GEMM, everything else on the matrix-vector kernel. */
+typedef struct lmrs_b200_weights lmrs_b200_weights_t;
+int  lmrs_b200_weights_upload(int q_type, const void* wq, const float* ws, int n, int o, int gs, lmrs_b200_weights_t** out);
+int  lmrs_b200_matmul_w(float* xout, const void* xq, const float* xs, const lmrs_b200_weights_t* w, int rows);
+void lmrs_b200_weights_free(lmrs_b200_weights_t* w);
 
 const char* lmrs_b200_last_error(void);
 /* "lmrs_b200 <version> sm_100a" */

@@ -465,6 +465,10 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
             // gathered together with delta below (one round trip); a vector without a pending contribution is read alone
             if (!p.delta) ll_gather<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.x_in), nchunks, seq, nowait, v);
         } else {
+            // N-GPU consumer: this kernel did NOT wait for its predecessor (see the kernel body).  The first words of every
+            // GPU's partial prove that the predecessor is past ITS dependency wait, i.e. the kernel that wrote x_in has
+            // completed and flushed; only then is x_in read (through L2).
+            if (!LL && p.px_world > 1 && p.px_in) px_canary_wait(p.px_in, p.px_world, n, seq, nowait);
             const float4* xin = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.x_in) + (size_t)(p.x_in_stride ? p.step->token : 0u) * p.x_in_stride);
 #pragma unroll
             for (int k = 0; k < NORM_MAXC; k++) {
@@ -485,7 +489,7 @@ LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const ui
                 else
                     ll_gather<NORM_MAXC, THREADS>(reinterpret_cast<const llword_t*>(p.delta), nchunks, seq, nowait, dv);
             } else if (p.px_world > 1) {   // N-GPU mode: the contribution is the rank-ordered sum of the partials every GPU pushed here
-                px_canary_wait(p.px_in, p.px_world, n, seq, nowait);
+                if (p.emb_q) px_canary_wait(p.px_in, p.px_world, n, seq, nowait);   // (otherwise parked on the canaries before x_in was read)
                 px_gather_sum<NORM_MAXC, THREADS>(p.px_in, p.px_world, n, nchunks, seq, nowait, dv);
             } else {
                 const float4* din = reinterpret_cast<const float4*>(p.delta);
@@ -825,7 +829,11 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? LMRS_GEMV_MINB : 1) l
         // this kernel's CTAs were launched early and now idle until the previous kernel completes: one otherwise unused
         // thread asks the L2 to fetch weights that later kernels of the step will stream (after this CTA's own requests)
         if (p.l2pf_bytes && threadIdx.x == (WARPS - 1) * 32 + 1) l2_prefetch_slice(p.l2pf_ptr, p.l2pf_bytes, p.l2pf_chunk);
-        pdl_wait();   // upstream activations are complete and visible from here on
+        // N-GPU mode, consumer of an exchanged vector: everything this kernel reads from its predecessor arrives as
+        // (value, sequence) words it polls anyway, so it does not wait for the predecessor's COMPLETION (which includes the
+        // NVLink round trip of that kernel's stores into the peers) -- only for the words themselves (gemv_prologue)
+        if (!(PRO == PRO_NORM && p.px_world > 1 && p.px_in != nullptr))
+            pdl_wait();   // upstream activations are complete and visible from here on
         if (lane == 0)
             for (int s = pre; s < DEPTH && s < w.nst; s++) issue_stage<QT>(w, s, ring + (size_t)(warp * DEPTH + s) * STAGE, &bars[s], pol);
     }

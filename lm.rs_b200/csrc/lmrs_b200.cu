@@ -130,11 +130,18 @@ struct lmrs_b200 {
     int l2pf = 0, l2pf_cls_mb = 24, l2pf_chunk = 32768, l2pf_ef = 1;   // L2 prefetch of upcoming weights during the attention phase (make_phases)
     Shard shard;  // multi-GPU bootstrap / NCCL fallback (shard.h); inert when world == 1
     // peer exchange (common.cuh, N-GPU mode): ONE cudaMalloc'ed block per GPU, mapped into every peer through CUDA IPC:
-    //   [n_layers][2][world][dim] LL words (slot r of a vector = rank r's partial) | flags[world] | logits[vocab]
+    //   [n_layers][2][world][dim] LL words (slot r of a vector = rank r's partial) | flags | logits[vocab] |
+    //   batched prefill: [2][world][pf_xchg_rows][dim] f32 partial rows
     bool use_peer = false;
+    // in-process N-GPU mode (lmrs_b200_create_multi): the rank-0 handle leads a group of one handle per GPU, all driven
+    // by the caller's thread; `group` is empty for ordinary handles and lists every member (itself first) on the leader
+    std::vector<lmrs_b200*> group;
+    bool in_process_group = false;   // member of such a group: peers are mapped with cudaDeviceEnablePeerAccess, not CUDA IPC
     uint8_t* d_xchg = nullptr;
     uint8_t* xchg_peer[PX_MAX_WORLD] = {};   // the same block on every GPU (entry `rank` = d_xchg)
-    size_t xchg_flags_off = 0, xchg_logits_off = 0;
+    size_t xchg_flags_off = 0, xchg_logits_off = 0, xchg_pf_off = 0;
+    int pf_xchg_rows = 512;          // rows per batched-prefill pass in N-GPU mode (capacity of the exchange buffers)
+    uint32_t pf_xchg_count = 0;      // exchanges so far (same on every GPU): flag value and buffer parity
 };
 
 static llword_t* px_vec(const lmrs_b200* m, int gpu, size_t layer, int which) {   // exchange vector (layer, 0: after Wo / 1: after W2) on GPU `gpu`
@@ -525,6 +532,8 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     if (a.q_type != 1 && a.q_type != 2)
         return fail("lmrs_b200: only Q8_0 / Q4_0 models are supported on the B200 path (q_type=" + std::to_string(a.q_type) + ")");
     if (a.model_type > 2) return fail("unknown model_type");
+    if (!a.dim || !a.hidden_dim || !a.n_layers || !a.n_heads || !a.n_kv_heads || !a.head_size || !a.vocab_size || !a.seq_len)
+        return fail("malformed header: zero-sized model dimension");
     if (a.group_size != GS) return fail("lmrs_b200: group_size must be 128 (the exporter always quantizes with 128, utils/io.py:21)");
     const size_t dim = a.dim, hd = a.hidden_dim, L = a.n_layers, hs = a.head_size;
     const size_t att_dim = (size_t)a.n_heads * hs, kv_dim = (size_t)a.n_kv_heads * hs;
@@ -665,7 +674,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
         CK(repack_bp16(a.q_type, m->d_arena + j.dst, d_stage + j.src.q, (const float*)(d_stage + j.src.s), j.src.o, j.src.n, 0));
     for (const VecJob& j : vjobs) CK(cudaMemcpy(m->d_arena + j.dst, d_stage + j.src, dim * 4, cudaMemcpyDeviceToDevice));
     CK(cudaDeviceSynchronize());
-    m->use_gemm = a.q_type == 1 && env_int("LMRS_B200_GEMM", 1) != 0 && W == 1;
+    m->use_gemm = a.q_type == 1 && env_int("LMRS_B200_GEMM", 1) != 0 && (W == 1 || m->use_peer);   // N-GPU: needs the peer exchange
     if (m->use_gemm) m->d_dense = d_stage;   // the file-layout copy doubles as the GEMM's B operand
     else cudaFree(d_stage);
     int tmap_err = 0;
@@ -1073,95 +1082,155 @@ static int launch_rows_prologue(lmrs_b200* m, GemvParams p, int T) {
 //   rows prologue (residual, exact rmsnorm, quantize) -> tcgen05 GEMM [Wq;Wk;Wv] (K/V straight into the cache) -> RoPE rows
 //   -> exact attention per (token, kv head) -> quantize -> GEMM Wo -> rows prologue -> GEMM W1, W3 -> act*up -> quantize
 //   -> GEMM W2; the block-closing residual is folded into the next prologue, the last one is materialised at the end.
-static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
+// fill_kv_cache, batched form, in three parts so that an in-process group can walk its GPUs block by block:
+//   pf_begin  buffers + step parameters;  pf_layer  one transformer block of T rows;  pf_end  the pending residual
+struct PfCtx { int T; uint32_t pos; float* rows; const float* delta; const float* w_post; bool fused_attn; size_t sc_stride; };
+
+// N-GPU mode: `part` holds this GPU's partial [T][dim] product (K-sharded Wo / W2); on return it holds the sum over the
+// GPUs in rank order.  Two alternating exchange buffers per GPU: a peer can be at most one exchange ahead of this GPU's
+// reads (it needs this GPU's flag of exchange e to get past e).
+static int pf_exchange(lmrs_b200* m, float* part, int T) {
+    if (m->world == 1) return 0;
+    const uint32_t e = m->pf_xchg_count++;
+    const size_t dim = m->args.dim, slot = (size_t)m->pf_xchg_rows * dim;   // floats per slot
+    PxRowsParams p{};
+    p.src = part; p.world = m->world; p.count4 = (size_t)T * dim / 4; p.slot_stride = slot;
+    for (int r = 0; r < m->world; r++)
+        p.dst[r] = reinterpret_cast<float*>(m->xchg_peer[r] + m->xchg_pf_off) + ((size_t)(e & 1) * m->world + m->rank) * slot;
+    p.slots = reinterpret_cast<const float*>(m->d_xchg + m->xchg_pf_off) + (size_t)(e & 1) * m->world * slot;
+    p.out = part;
+    const unsigned grid = (unsigned)((p.count4 + 255) / 256);
+    px_rows_push_kernel<<<grid, 256, 0, m->stream>>>(p);
+    m->launches++;
+    CK(cudaGetLastError());
+    PeerFlagParams f{};
+    for (int r = 0; r < m->world; r++) f.flag_peer[r] = reinterpret_cast<uint32_t*>(m->xchg_peer[r] + m->xchg_flags_off + 128);
+    f.flag_local = reinterpret_cast<const uint32_t*>(m->d_xchg + m->xchg_flags_off + 128);
+    f.world = m->world; f.rank = m->rank; f.step = m->d_step; f.value = e + 1; f.use_value = 1;
+    peer_flag_kernel<<<1, 32, 0, m->stream>>>(f);
+    m->launches++;
+    CK(cudaGetLastError());
+    px_rows_sum_kernel<<<grid, 256, 0, m->stream>>>(p);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+static int pf_begin(lmrs_b200* m, size_t n, uint32_t pos, float* rows, PfCtx& c) {
     const lmrs_args_t& a = m->args;
-    const int T = (int)n, dim = a.dim, att = m->l_att_dim, kvd = m->l_kv_dim, hid = m->l_hidden;
-    const bool gemma = a.model_type == 0;
-    const bool fused_attn = m->use_pf_attn == 1 && prefill_fused_tb((int)a.head_size, (int)(a.n_heads / a.n_kv_heads), (int)(pos + n)) > 0;
-    const size_t sc_stride = fused_attn ? 4 : align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // score scratch of the unfused forms (pos + n <= ATT_SC_CAP)
+    const int dim = a.dim, att = m->l_att_dim, hid = m->l_hidden;
+    c.T = (int)n; c.pos = pos; c.rows = rows; c.delta = nullptr; c.w_post = nullptr;
+    c.fused_attn = m->use_pf_attn == 1 && prefill_fused_tb((int)a.head_size, (int)(a.n_heads / a.n_kv_heads), (int)(pos + n)) > 0;
+    c.sc_stride = c.fused_attn ? 4 : align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // score scratch of the unfused forms (pos + n <= ATT_SC_CAP)
     if (m->pf_cap < n) {
-        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_g, (void*)m->pf_u, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
-        m->pf_xq = nullptr; m->pf_xs = m->pf_q = m->pf_att = m->pf_wo = m->pf_g = m->pf_u = m->pf_h = m->pf_down = nullptr;
+        for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
+        m->pf_xq = nullptr; m->pf_xs = m->pf_q = m->pf_att = m->pf_wo = m->pf_h = m->pf_down = nullptr;
         m->pf_cap = 0;   // a failed allocation below must not leave a capacity behind
         const size_t nmax = std::max<size_t>(std::max<size_t>(dim, att), hid);
         CK(cudaMalloc(&m->pf_xq, n * nmax)); CK(cudaMalloc(&m->pf_xs, n * (nmax / GS) * 4));
         CK(cudaMalloc(&m->pf_q, n * att * 4)); CK(cudaMalloc(&m->pf_att, n * att * 4)); CK(cudaMalloc(&m->pf_wo, n * dim * 4));
-        CK(cudaMalloc(&m->pf_h, n * hid * 4));   // (pf_g / pf_u: unused since gate/up are fused)
+        CK(cudaMalloc(&m->pf_h, n * hid * 4));   // (gate and up never leave the fused GEMM)
         CK(cudaMalloc(&m->pf_down, n * dim * 4));
         m->pf_cap = n;
     }
-    if (!fused_attn && m->pf_sc_bytes < n * (size_t)m->l_heads * sc_stride * 4) {   // score scratch of the unfused attention forms
+    if (!c.fused_attn && m->pf_sc_bytes < n * (size_t)m->l_heads * c.sc_stride * 4) {   // score scratch of the unfused attention forms
         cudaFree(m->pf_scores); m->pf_scores = nullptr; m->pf_sc_bytes = 0;
-        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * sc_stride * 4));
-        m->pf_sc_bytes = n * (size_t)m->l_heads * sc_stride * 4;
+        CK(cudaMalloc(&m->pf_scores, n * (size_t)m->l_heads * c.sc_stride * 4));
+        m->pf_sc_bytes = n * (size_t)m->l_heads * c.sc_stride * 4;
     }
-    if (push_step(m, 0, pos, pos)) return 1;   // attention: pos = step->pos + token index, mask_base = batch start
-    const float* delta = nullptr;
-    const float* w_post = nullptr;
-    for (size_t l = 0; l < a.n_layers; l++) {
-        const Layer& Y = m->layers[l];
-        float* kc = m->d_kcache + l * (size_t)a.seq_len * kvd;
-        float* vc = m->d_vcache + l * (size_t)a.seq_len * kvd;
-        {
-            GemvParams p{};
-            p.n = dim; p.pro = PRO_NORM; p.x_in = m->d_rows; p.delta = delta; p.w_post = w_post; p.w_norm = Y.rms_att;
-            p.x_out = m->d_rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
-            if (launch_rows_prologue(m, p, T)) return 1;
-            GemmParams g{};
-            g.out0 = m->pf_q; g.ld0 = att; g.c1 = att;
-            g.out1 = kc + (size_t)pos * kvd; g.ld1 = kvd; g.c2 = att + kvd;
-            g.out2 = vc + (size_t)pos * kvd; g.ld2 = kvd;
-            if (launch_gemm(m, Y.qkv, m->pf_xq, m->pf_xs, T, g)) return 1;
-        }
-        rope_rows_kernel<<<T, 256, 0, m->stream>>>(m->pf_q, kc, m->d_rope_cos, m->d_rope_sin, m->l_heads, m->l_kv_heads, a.head_size, (int)pos);
-        m->launches++;
-        CK(cudaGetLastError());
-        if (m->use_pf_attn) {
-            PrefillAttnParams p{};
-            p.q = m->pf_q; p.kcache = kc; p.vcache = vc; p.probs = m->pf_scores; p.out = m->pf_att;
-            p.n = T; p.pos = (int)pos; p.t_cap = (int)sc_stride; p.att_dim = att; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads;
-            p.gemma = gemma; p.mask_base = pos; p.sqrt_hs = sqrtf((float)a.head_size); p.neg_zero = -0.0f;
-            if (launch_prefill_attn(m, p, m->l_kv_heads)) return 1;
-        } else {
-            AttnParams p{};
-            p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
-            p.out = m->pf_att; p.scores = m->pf_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
-            p.gemma = gemma; p.seq_len = (int)sc_stride; p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
-            p.batch = 1; p.q_stride = att;
-            bool pdl = m->use_pdl; m->use_pdl = false;
-            cudaError_t e = launch_attn_grid(m, p, m->l_kv_heads, T);
-            m->use_pdl = pdl;
-            CK(e);
-        }
-        {
-            GemvParams p{};
-            p.n = att; p.pro = PRO_QUANT; p.act_in = m->pf_att; p.step = m->d_step;
-            if (launch_rows_prologue(m, p, T)) return 1;
-            if (launch_gemm(m, Y.wo, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_wo, dim, dim))) return 1;
-        }
-        {
-            GemvParams p{};
-            p.n = dim; p.pro = PRO_NORM; p.x_in = m->d_rows; p.delta = m->pf_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
-            p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = m->d_rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
-            if (launch_rows_prologue(m, p, T)) return 1;
-            // gate and up in one launch with act(gate) * up in its epilogue (:607-624): g and u never travel through HBM
-            if (launch_gemm_glu(m, Y.w1, Y.w3, m->pf_xq, m->pf_xs, T, m->pf_h, hid, gemma ? EPI_GLU_GELU : EPI_GLU_SILU)) return 1;
-        }
-        {
-            GemvParams p{};
-            p.n = hid; p.pro = PRO_QUANT; p.act_in = m->pf_h; p.step = m->d_step;
-            if (launch_rows_prologue(m, p, T)) return 1;
-            if (launch_gemm(m, Y.w2, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_down, dim, dim))) return 1;
-        }
-        delta = m->pf_down;
-        w_post = gemma ? Y.rms_post_ffn : nullptr;
+    return push_step(m, 0, pos, pos);   // attention: pos = step->pos + token index, mask_base = batch start
+}
+
+static int pf_layer(lmrs_b200* m, size_t l, PfCtx& c) {
+    const lmrs_args_t& a = m->args;
+    const int T = c.T, dim = a.dim, att = m->l_att_dim, kvd = m->l_kv_dim, hid = m->l_hidden;
+    const uint32_t pos = c.pos;
+    const bool gemma = a.model_type == 0;
+    const Layer& Y = m->layers[l];
+    float* kc = m->d_kcache + l * (size_t)a.seq_len * kvd;
+    float* vc = m->d_vcache + l * (size_t)a.seq_len * kvd;
+    {
+        GemvParams p{};
+        p.n = dim; p.pro = PRO_NORM; p.x_in = c.rows; p.delta = c.delta; p.w_post = c.w_post; p.w_norm = Y.rms_att;
+        p.x_out = c.rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
+        if (launch_rows_prologue(m, p, T)) return 1;
+        GemmParams g{};
+        g.out0 = m->pf_q; g.ld0 = att; g.c1 = att;
+        g.out1 = kc + (size_t)pos * kvd; g.ld1 = kvd; g.c2 = att + kvd;
+        g.out2 = vc + (size_t)pos * kvd; g.ld2 = kvd;
+        if (launch_gemm(m, Y.qkv, m->pf_xq, m->pf_xs, T, g)) return 1;
     }
-    ResidualParams r{};
-    r.x_in = m->d_rows; r.delta = delta; r.w_post = w_post; r.n = dim; r.eps = a.rms_norm_eps; r.rows = m->d_rows; r.step = m->d_step;
-    r.row_from_block = 1;
-    residual_finalize_kernel<<<T, 256, 0, m->stream>>>(r);
+    rope_rows_kernel<<<T, 256, 0, m->stream>>>(m->pf_q, kc, m->d_rope_cos, m->d_rope_sin, m->l_heads, m->l_kv_heads, a.head_size, (int)pos);
     m->launches++;
     CK(cudaGetLastError());
+    if (m->use_pf_attn) {
+        PrefillAttnParams p{};
+        p.q = m->pf_q; p.kcache = kc; p.vcache = vc; p.probs = m->pf_scores; p.out = m->pf_att;
+        p.n = T; p.pos = (int)pos; p.t_cap = (int)c.sc_stride; p.att_dim = att; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads;
+        p.gemma = gemma; p.mask_base = pos; p.sqrt_hs = sqrtf((float)a.head_size); p.neg_zero = -0.0f;
+        if (launch_prefill_attn(m, p, m->l_kv_heads)) return 1;
+    } else {
+        AttnParams p{};
+        p.q = m->pf_q; p.k_new = nullptr; p.kcache = kc; p.vcache = vc; p.rope_cos = m->d_rope_cos; p.rope_sin = m->d_rope_sin;
+        p.out = m->pf_att; p.scores = m->pf_scores; p.kv_dim = kvd; p.kv_mul = a.n_heads / a.n_kv_heads; p.chunks = m->att_chunks;
+        p.gemma = gemma; p.seq_len = (int)c.sc_stride; p.sqrt_hs = sqrtf((float)a.head_size); p.step = m->d_step;
+        p.batch = 1; p.q_stride = att;
+        bool pdl = m->use_pdl; m->use_pdl = false;
+        cudaError_t e = launch_attn_grid(m, p, m->l_kv_heads, T);
+        m->use_pdl = pdl;
+        CK(e);
+    }
+    {
+        GemvParams p{};
+        p.n = att; p.pro = PRO_QUANT; p.act_in = m->pf_att; p.step = m->d_step;
+        if (launch_rows_prologue(m, p, T)) return 1;
+        if (launch_gemm(m, Y.wo, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_wo, dim, dim))) return 1;
+        if (pf_exchange(m, m->pf_wo, T)) return 1;
+    }
+    {
+        GemvParams p{};
+        p.n = dim; p.pro = PRO_NORM; p.x_in = c.rows; p.delta = m->pf_wo; p.w_post = gemma ? Y.rms_post_att : nullptr;
+        p.w_norm = gemma ? Y.rms_pre_ffn : Y.rms_post_att; p.x_out = c.rows; p.eps = a.rms_norm_eps; p.unit_offset = gemma; p.step = m->d_step;
+        if (launch_rows_prologue(m, p, T)) return 1;
+        // gate and up in one launch with act(gate) * up in its epilogue (:607-624): g and u never travel through HBM
+        if (launch_gemm_glu(m, Y.w1, Y.w3, m->pf_xq, m->pf_xs, T, m->pf_h, hid, gemma ? EPI_GLU_GELU : EPI_GLU_SILU)) return 1;
+    }
+    {
+        GemvParams p{};
+        p.n = hid; p.pro = PRO_QUANT; p.act_in = m->pf_h; p.step = m->d_step;
+        if (launch_rows_prologue(m, p, T)) return 1;
+        if (launch_gemm(m, Y.w2, m->pf_xq, m->pf_xs, T, gemm_out1(m->pf_down, dim, dim))) return 1;
+        if (pf_exchange(m, m->pf_down, T)) return 1;
+    }
+    c.delta = m->pf_down;
+    c.w_post = gemma ? Y.rms_post_ffn : nullptr;
+    return 0;
+}
+
+static int pf_end(lmrs_b200* m, PfCtx& c) {
+    ResidualParams r{};
+    r.x_in = c.rows; r.delta = c.delta; r.w_post = c.w_post; r.n = m->args.dim; r.eps = m->args.rms_norm_eps; r.rows = c.rows; r.step = m->d_step;
+    r.row_from_block = 1;
+    residual_finalize_kernel<<<c.T, 256, 0, m->stream>>>(r);
+    m->launches++;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// rows per pass: everything at once on one GPU; N-GPU mode walks the batch in chunks the exchange buffers hold (a later
+// chunk attends to the earlier ones through the KV cache: same results as one pass)
+static size_t pf_chunk_rows(const lmrs_b200* m, size_t n) { return m->world > 1 ? std::min<size_t>(n, (size_t)m->pf_xchg_rows) : n; }
+
+static int prefill_gemm(lmrs_b200* m, size_t n, uint32_t pos) {
+    for (size_t r0 = 0; r0 < n;) {
+        const size_t cn = pf_chunk_rows(m, n - r0);
+        PfCtx c;
+        if (pf_begin(m, cn, pos + (uint32_t)r0, m->d_rows + r0 * m->args.dim, c)) return 1;
+        for (size_t l = 0; l < m->args.n_layers; l++)
+            if (pf_layer(m, l, c)) return 1;
+        if (pf_end(m, c)) return 1;
+        r0 += cn;
+    }
     return 0;
 }
 
@@ -1171,16 +1240,25 @@ static int prefill_batched(lmrs_b200* m, size_t n, uint32_t pos) {
 }
 
 // N-GPU mode: allocate this GPU's exchange block and map every peer's (CUDA IPC; handles travel through one NCCL all-gather)
-static int setup_peer_exchange(lmrs_b200* m) {
+static int alloc_peer_exchange(lmrs_b200* m) {
     const size_t W = (size_t)m->world, dim = m->args.dim, L = m->args.n_layers;
     if (W > (size_t)PX_MAX_WORLD) return fail("peer exchange supports up to 8 GPUs");
     const size_t px_bytes = L * 2 * W * dim * sizeof(llword_t);
     m->xchg_flags_off = align_up(px_bytes, 256);
     m->xchg_logits_off = m->xchg_flags_off + 256;
-    const size_t total = m->xchg_logits_off + (size_t)m->args.vocab_size * 4;
+    m->pf_xchg_rows = std::max(8, env_int("LMRS_B200_PF_ROWS", 512));
+    m->xchg_pf_off = align_up(m->xchg_logits_off + (size_t)m->args.vocab_size * 4, 256);
+    const size_t total = m->xchg_pf_off + (m->use_gemm ? (size_t)2 * W * m->pf_xchg_rows * dim * 4 : 0);
     CK(cudaMalloc(&m->d_xchg, total));
     CK(cudaMemset(m->d_xchg, 0, total));   // sequence number 0 = "never written"
     CK(cudaDeviceSynchronize());
+    m->xchg_peer[m->rank] = m->d_xchg;
+    m->d_logits = reinterpret_cast<float*>(m->d_xchg + m->xchg_logits_off);
+    return 0;
+}
+static int setup_peer_exchange(lmrs_b200* m) {
+    const size_t W = (size_t)m->world;
+    if (alloc_peer_exchange(m)) return 1;
     cudaIpcMemHandle_t mine;
     CK(cudaIpcGetMemHandle(&mine, m->d_xchg));
     uint8_t* d_h = nullptr;
@@ -1199,13 +1277,15 @@ static int setup_peer_exchange(lmrs_b200* m) {
             return fail(std::string("cudaIpcOpenMemHandle (peer exchange between GPUs; LMRS_B200_PEER=0 selects the NCCL data path): ") + cudaGetErrorString(e));
         m->xchg_peer[r] = (uint8_t*)ptr;
     }
-    m->d_logits = reinterpret_cast<float*>(m->d_xchg + m->xchg_logits_off);
     return 0;
 }
 
 // ---- C ABI -----------------------------------------------------------------------------------------------
+static int alloc_peer_exchange(lmrs_b200* m);
+// phase 1 of a handle: device checks, knobs, weights and state.  `inproc`: a member of an in-process group (no NCCL, the
+// peer mapping and the phase tables follow once every member exists: finish_create)
 static int create_common(const uint8_t* file, size_t len, int device, int rank, int world, const void* nccl_id,
-                         lmrs_b200_t** out, size_t* end_offset) {
+                         lmrs_b200_t** out, size_t* end_offset, bool inproc = false) {
     if (!file || !out) return fail("null argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -1241,11 +1321,17 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     m->l2pf_chunk = std::max(1024, env_int("LMRS_B200_L2PF_CHUNK", 32768)) & ~15;
     // N-GPU data path: partial vectors pushed between the GPUs by the kernels themselves (default), or NCCL collectives
     // between the kernels (LMRS_B200_PEER=0)
-    m->use_peer = world > 1 && env_int("LMRS_B200_PEER", 1) != 0;
+    m->use_peer = world > 1 && (inproc || env_int("LMRS_B200_PEER", 1) != 0);
+    m->in_process_group = inproc;
     if (build_model(m, file, len, end_offset)) { lmrs_b200_destroy(m); return 1; }
     if ((int)m->args.dim > NORM_MAX_DIM) {
         lmrs_b200_destroy(m);
         return fail("dim too large for the fused norm prologue of this GEMV configuration");
+    }
+    if (inproc) {   // the group wires the peers and finishes the members together
+        if (alloc_peer_exchange(m)) { lmrs_b200_destroy(m); return 1; }
+        *out = m;
+        return 0;
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
     if (m->use_peer && setup_peer_exchange(m)) { lmrs_b200_destroy(m); return 1; }
@@ -1255,6 +1341,46 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     *out = m;
     return 0;
 }
+
+// Transformer::new on n_gpus GPUs of this process (devices 0 .. n_gpus-1): one handle per GPU, row-sharded like
+// create_sharded, peers mapped with cudaDeviceEnablePeerAccess (no NCCL, no second process).  The returned handle leads
+// the group: every entry point fans out to the members from the caller's thread (the kernels of the members wait for
+// one another on the device, the host never does).
+extern "C" int lmrs_b200_create_multi(const uint8_t* file, size_t len, int n_gpus, lmrs_b200_t** out, size_t* end_offset) {
+    if (!file || !out) return fail("null argument");
+    if (n_gpus <= 1) return create_common(file, len, n_gpus == 1 ? 0 : -1, 0, 1, nullptr, out, end_offset);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < n_gpus) return fail("lmrs_b200_create_multi: fewer CUDA devices than n_gpus");
+    if (n_gpus > PX_MAX_WORLD) return fail("lmrs_b200_create_multi: at most 8 GPUs");
+    std::vector<lmrs_b200*> g((size_t)n_gpus, nullptr);
+    auto bail = [&]() { std::string e = g_err; for (lmrs_b200* x : g) if (x) { x->group.clear(); lmrs_b200_destroy(x); } g_err = e; return 1; };
+    for (int r = 0; r < n_gpus; r++)
+        if (create_common(file, len, r, r, n_gpus, nullptr, &g[r], r == 0 ? end_offset : nullptr, /*inproc=*/true)) return bail();
+    for (int a = 0; a < n_gpus; a++) {
+        if (cudaSetDevice(g[a]->device) != cudaSuccess) { fail("cudaSetDevice failed"); return bail(); }
+        for (int b = 0; b < n_gpus; b++) {
+            if (a == b) continue;
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, g[a]->device, g[b]->device);
+            if (!can) { fail("lmrs_b200_create_multi: GPUs " + std::to_string(a) + " and " + std::to_string(b) + " have no peer access"); return bail(); }
+            cudaError_t e = cudaDeviceEnablePeerAccess(g[b]->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { fail(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return bail(); }
+            cudaGetLastError();
+        }
+        for (int b = 0; b < n_gpus; b++) g[a]->xchg_peer[b] = g[b]->d_xchg;
+    }
+    for (int r = 0; r < n_gpus; r++) {
+        if (cudaSetDevice(g[r]->device) != cudaSuccess) { fail("cudaSetDevice failed"); return bail(); }
+        setup_attn_cluster(g[r]);
+        if (setup_trace(g[r])) return bail();
+        g[r]->ph_decode = make_phases(g[r], false);
+    }
+    g[0]->group = g;
+    *out = g[0];
+    return 0;
+}
+// the handles an entry point has to drive: the members of a group, or the handle itself
+static std::vector<lmrs_b200*> members(lmrs_b200* m) { return m->group.empty() ? std::vector<lmrs_b200*>{m} : m->group; }
 
 extern "C" int lmrs_b200_create(const uint8_t* file, size_t len, int device, lmrs_b200_t** out, size_t* end_offset) {
     return create_common(file, len, device, 0, 1, nullptr, out, end_offset);
@@ -1272,6 +1398,12 @@ extern "C" int lmrs_b200_nccl_unique_id(void* out128) {
 
 extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     if (!m) return;
+    if (!m->group.empty()) {   // leader of an in-process group: the members first (all idle), then itself
+        std::vector<lmrs_b200*> g = m->group;
+        for (lmrs_b200* x : g) { cudaSetDevice(x->device); if (x->own_stream) cudaStreamSynchronize(x->own_stream); }
+        m->group.clear();
+        for (size_t i = 1; i < g.size(); i++) lmrs_b200_destroy(g[i]);
+    }
     cudaSetDevice(m->device);
     if (m->own_stream) cudaStreamSynchronize(m->own_stream);
     for (int v = 0; v < 8; v++) {
@@ -1279,7 +1411,7 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
         if (m->g_prefill[v]) cudaGraphExecDestroy(m->g_prefill[v]);
     }
     for (int r = 0; r < m->world && r < PX_MAX_WORLD; r++)
-        if (m->xchg_peer[r] && m->xchg_peer[r] != m->d_xchg) cudaIpcCloseMemHandle(m->xchg_peer[r]);
+        if (!m->in_process_group && m->xchg_peer[r] && m->xchg_peer[r] != m->d_xchg) cudaIpcCloseMemHandle(m->xchg_peer[r]);
     cudaFree(m->d_xchg);
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
@@ -1303,19 +1435,26 @@ extern "C" int lmrs_b200_args(const lmrs_b200_t* m, lmrs_args_t* out) {
     return 0;
 }
 
+static int step_one(lmrs_b200* m, bool with_params, uint32_t token, uint32_t pos) {   // one decode step of ONE handle
+    CK(cudaSetDevice(m->device));
+    if (with_params) { if (push_step(m, token, pos, pos)) return 1; }
+    else next_seq(m);   // the device advanced (token, pos, seq) itself: keep the host's sequence counter in step
+    const int v = m->att_variant = attn_variant_for(m, pos);
+    return run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true);
+}
 extern "C" int lmrs_b200_forward_device(lmrs_b200_t* m, uint32_t token, uint32_t pos) {
     if (!m) return fail("null handle");
     if (token >= m->args.vocab_size) return fail("token out of range");
     if (pos >= m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
-    CK(cudaSetDevice(m->device));
-    if (push_step(m, token, pos, pos)) return 1;
-    const int v = m->att_variant = attn_variant_for(m, pos);
-    return run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true);
+    for (lmrs_b200* g : members(m))   // in-process group: every GPU's step is enqueued from this thread; they meet on the device
+        if (step_one(g, true, token, pos)) return 1;
+    return 0;
 }
 
 extern "C" int lmrs_b200_forward(lmrs_b200_t* m, uint32_t token, uint32_t pos, float** logits_host) {
     if (!logits_host) return fail("null argument");
     if (lmrs_b200_forward_device(m, token, pos)) return 1;
+    CK(cudaSetDevice(m->device));
     CK(cudaMemcpyAsync(m->h_logits, m->d_logits, (size_t)m->args.vocab_size * 4, cudaMemcpyDeviceToHost, m->stream));
     CK(cudaStreamSynchronize(m->stream));
     *logits_host = m->h_logits;
@@ -1347,6 +1486,7 @@ extern "C" int lmrs_b200_forward_argmax(lmrs_b200_t* m, uint32_t token, uint32_t
     if (!next_token) return fail("null argument");
     if (m && m->world > 1 && !m->use_peer) return fail("forward_argmax: not with the NCCL data path (LMRS_B200_PEER=0)");   // peer mode: every GPU holds all logits rows
     if (lmrs_b200_forward_device(m, token, pos)) return 1;
+    CK(cudaSetDevice(m->device));   // (a group leader holds every rank's logits rows: its own pick is the answer)
     if (ensure_gen(m, 64)) return 1;
     if (launch_argmax(m, m->d_next, false)) return 1;
     CK(cudaMemcpyAsync(m->h_gen, m->d_next, 4, cudaMemcpyDeviceToHost, m->stream));
@@ -1364,20 +1504,19 @@ extern "C" int lmrs_b200_generate_greedy(lmrs_b200_t* m, uint32_t first_token, u
     if (m->world > 1 && !m->use_peer) return fail("generate_greedy: not with the NCCL data path (LMRS_B200_PEER=0)");
     if (first_token >= m->args.vocab_size) return fail("token out of range");
     if ((size_t)pos + max_new > m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
-    CK(cudaSetDevice(m->device));
     *n_out = 0;
     if (max_new == 0) return 0;
-    if (ensure_gen(m, max_new)) return 1;
+    const std::vector<lmrs_b200*> grp = members(m);
+    for (lmrs_b200* g : grp) { CK(cudaSetDevice(g->device)); if (ensure_gen(g, max_new)) return 1; }
     const uint32_t chunk = 32;
     for (uint32_t i0 = 0; i0 < max_new; i0 += chunk) {
         const uint32_t i1 = std::min(max_new, i0 + chunk);
-        for (uint32_t i = i0; i < i1; i++) {
-            if (i == 0) { if (push_step(m, first_token, pos, pos)) return 1; }
-            else next_seq(m);   // the device advanced (token, pos, seq) itself: keep the host's sequence counter in step
-            const int v = m->att_variant = attn_variant_for(m, pos + i);
-            if (run_graph(m, &m->g_decode[v], &m->g_decode_stream[v], &m->n_decode_kernels[v], true)) return 1;
-            if (launch_argmax(m, m->d_gen + i, true)) return 1;
-        }
+        for (uint32_t i = i0; i < i1; i++)
+            for (lmrs_b200* g : grp) {   // every GPU of a group picks the same token from the same logits and advances itself
+                if (step_one(g, i == 0, first_token, pos + i)) return 1;
+                if (launch_argmax(g, g->d_gen + i, true)) return 1;
+            }
+        CK(cudaSetDevice(m->device));
         CK(cudaMemcpyAsync(m->h_gen + i0, m->d_gen + i0, (size_t)(i1 - i0) * 4, cudaMemcpyDeviceToHost, m->stream));
         CK(cudaStreamSynchronize(m->stream));
         for (uint32_t i = i0; i < i1; i++) {
@@ -1392,11 +1531,13 @@ extern "C" int lmrs_b200_generate_greedy(lmrs_b200_t* m, uint32_t first_token, u
 extern "C" int lmrs_b200_bench_gemv_pass(lmrs_b200_t* m, uint32_t pos, int* n_launches) {
     if (!m) return fail("null handle");
     if (pos >= m->args.seq_len) return fail("position out of range");
-    CK(cudaSetDevice(m->device));
-    if (push_step(m, 0, pos, pos)) return 1;
-    const uint64_t before = m->launches;
-    if (enqueue_step(m, true, /*nowait=*/true, PH_GEMV)) return 1;   // LL kernels take whatever their input buffers hold
-    if (n_launches) *n_launches = (int)(m->launches - before);
+    for (lmrs_b200* g : members(m)) {
+        CK(cudaSetDevice(g->device));
+        if (push_step(g, 0, pos, pos)) return 1;
+        const uint64_t before = g->launches;
+        if (enqueue_step(g, true, /*nowait=*/true, PH_GEMV)) return 1;   // LL / peer-exchange kernels take whatever their input buffers hold
+        if (n_launches && g == m) *n_launches = (int)(g->launches - before);
+    }
     return 0;
 }
 
@@ -1419,6 +1560,7 @@ extern "C" int lmrs_b200_logits_device(lmrs_b200_t* m, float** logits_dev) {
 }
 extern "C" int lmrs_b200_set_stream(lmrs_b200_t* m, void* s) {
     if (!m) return fail("null handle");
+    if (!m->group.empty() && s) return fail("set_stream: an in-process multi-GPU handle drives one library-owned stream per GPU");
     CK(cudaSetDevice(m->device));
     CK(cudaStreamSynchronize(m->stream));
     m->stream = s ? (cudaStream_t)s : m->own_stream;
@@ -1426,13 +1568,14 @@ extern "C" int lmrs_b200_set_stream(lmrs_b200_t* m, void* s) {
 }
 extern "C" int lmrs_b200_synchronize(lmrs_b200_t* m) {
     if (!m) return fail("null handle");
+    for (lmrs_b200* g : members(m)) { CK(cudaSetDevice(g->device)); CK(cudaStreamSynchronize(g->stream)); }
     CK(cudaSetDevice(m->device));
-    CK(cudaStreamSynchronize(m->stream));
     return 0;
 }
 extern "C" int lmrs_b200_kernel_launches(const lmrs_b200_t* m, uint64_t* count) {
     if (!m || !count) return fail("null argument");
-    *count = m->launches;
+    *count = 0;
+    for (lmrs_b200* g : members(const_cast<lmrs_b200*>(m))) *count += g->launches;   // a group counts the kernels of all its GPUs
     return 0;
 }
 
@@ -1465,26 +1608,64 @@ extern "C" int lmrs_b200_fill_kv_cache(lmrs_b200_t* m, float* emb, size_t n_floa
     const size_t dim = m->args.dim;
     const size_t n = n_floats / dim;
     if (pos + n > m->args.seq_len) return fail("position out of range (seq_len is clamped to 8192, src/transformer.rs:158)");
-    if (n > 1 && (size_t)m->args.n_heads * m->args.head_size < dim)
-        return fail("sl>1 with att_dim<dim is out of bounds in the reference (src/transformer.rs:501-503)");
+    {   // the reference walks the batch in att_dim-sized chunks of an n*dim buffer (:501-503): one chunk too many -> panic there
+        const size_t att_dim = (size_t)m->args.n_heads * m->args.head_size;
+        if (att_dim < dim && n * (dim - att_dim) >= att_dim)
+            return fail("sl*(dim-att_dim) >= att_dim is out of bounds in the reference (src/transformer.rs:501-503)");
+    }
     CK(cudaSetDevice(m->device));
     if (n == 0) { *new_pos = pos; return 0; }
-    if (m->rows_cap < n * dim) {
-        cudaFree(m->d_rows);
-        m->d_rows = nullptr;
-        CK(cudaMalloc(&m->d_rows, n * dim * 4));
-        m->rows_cap = n * dim;
-        for (int v = 0; v < 8; v++)
-            if (m->g_prefill[v]) { cudaGraphExecDestroy(m->g_prefill[v]); m->g_prefill[v] = nullptr; }
-        m->ph_prefill = make_phases(m, true);   // the phase table embeds the staging buffer's address
+    const std::vector<lmrs_b200*> grp = members(m);
+    for (lmrs_b200* g : grp) {   // every GPU of a group stages the same embedding rows
+        CK(cudaSetDevice(g->device));
+        if (g->rows_cap < n * dim) {
+            cudaFree(g->d_rows);
+            g->d_rows = nullptr; g->rows_cap = 0;
+            CK(cudaMalloc(&g->d_rows, n * dim * 4));
+            g->rows_cap = n * dim;
+            for (int v = 0; v < 8; v++)
+                if (g->g_prefill[v]) { cudaGraphExecDestroy(g->g_prefill[v]); g->g_prefill[v] = nullptr; }
+            g->ph_prefill = make_phases(g, true);   // the phase table embeds the staging buffer's address
+        }
+        if (!g->ev_pf0) { CK(cudaEventCreate(&g->ev_pf0)); CK(cudaEventCreate(&g->ev_pf1)); }
+        CK(cudaMemcpyAsync(g->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, g->stream));
+        CK(cudaEventRecord(g->ev_pf0, g->stream));
     }
-    if (!m->ev_pf0) { CK(cudaEventCreate(&m->ev_pf0)); CK(cudaEventCreate(&m->ev_pf1)); }
-    CK(cudaMemcpyAsync(m->d_rows, emb, n * dim * 4, cudaMemcpyHostToDevice, m->stream));
-    CK(cudaEventRecord(m->ev_pf0, m->stream));
-    if (prefill_batched(m, n, pos)) return 1;
-    CK(cudaEventRecord(m->ev_pf1, m->stream));
+    if (grp.size() == 1) {
+        if (prefill_batched(m, n, pos)) return 1;
+    } else if (gemm_prefill_ok(m, n, pos)) {   // in-process group, batched form: block by block across the GPUs
+        for (size_t r0 = 0; r0 < n;) {
+            const size_t cn = pf_chunk_rows(m, n - r0);
+            std::vector<PfCtx> cs(grp.size());
+            for (size_t gi = 0; gi < grp.size(); gi++) {
+                CK(cudaSetDevice(grp[gi]->device));
+                if (pf_begin(grp[gi], cn, pos + (uint32_t)r0, grp[gi]->d_rows + r0 * dim, cs[gi])) return 1;
+            }
+            for (size_t l = 0; l < m->args.n_layers; l++)
+                for (size_t gi = 0; gi < grp.size(); gi++) {
+                    CK(cudaSetDevice(grp[gi]->device));
+                    if (pf_layer(grp[gi], l, cs[gi])) return 1;
+                }
+            for (size_t gi = 0; gi < grp.size(); gi++) {
+                CK(cudaSetDevice(grp[gi]->device));
+                if (pf_end(grp[gi], cs[gi])) return 1;
+            }
+            r0 += cn;
+        }
+    } else {   // in-process group: the per-token chain, token by token across the GPUs (they meet on the device)
+        for (size_t i = 0; i < n; i++)
+            for (lmrs_b200* g : grp) {
+                CK(cudaSetDevice(g->device));
+                if (push_step(g, (uint32_t)i, pos + (uint32_t)i, pos)) return 1;
+                const int v = g->att_variant = attn_variant_for(g, pos + (uint32_t)i);
+                if (run_graph(g, &g->g_prefill[v], &g->g_prefill_stream[v], &g->n_prefill_kernels[v], false)) return 1;
+            }
+    }
+    for (lmrs_b200* g : grp) { CK(cudaSetDevice(g->device)); CK(cudaEventRecord(g->ev_pf1, g->stream)); }
+    CK(cudaSetDevice(m->device));
     CK(cudaMemcpyAsync(emb, m->d_rows, n * dim * 4, cudaMemcpyDeviceToHost, m->stream));
-    CK(cudaStreamSynchronize(m->stream));
+    for (lmrs_b200* g : grp) { CK(cudaSetDevice(g->device)); CK(cudaStreamSynchronize(g->stream)); }
+    CK(cudaSetDevice(m->device));
     if (cudaEventElapsedTime(&m->last_prefill_ms, m->ev_pf0, m->ev_pf1) != cudaSuccess) m->last_prefill_ms = -1.0f;
     *new_pos = pos + (uint32_t)n;
     return 0;
@@ -1499,11 +1680,19 @@ extern "C" int lmrs_b200_last_prefill_device_ms(const lmrs_b200_t* m, float* ms)
 extern "C" int lmrs_b200_read_kv(lmrs_b200_t* m, uint32_t layer, uint32_t pos0, uint32_t n, float* k_out, float* v_out) {
     if (!m || !k_out || !v_out) return fail("null argument");
     if (layer >= m->args.n_layers || pos0 + n > m->args.seq_len) return fail("out of range");
+    const std::vector<lmrs_b200*> grp = members(m);
+    // a group returns whole rows [n][kv_dim] (GPU r holds columns [r * l_kv_dim, (r + 1) * l_kv_dim)); a single sharded
+    // handle returns its own slice [n][l_kv_dim]
+    const size_t out_ld = grp.size() > 1 ? (size_t)m->l_kv_dim * grp.size() : (size_t)m->l_kv_dim;
+    for (size_t r = 0; r < grp.size(); r++) {
+        lmrs_b200* g = grp[r];
+        CK(cudaSetDevice(g->device));
+        CK(cudaStreamSynchronize(g->stream));
+        const size_t base = ((size_t)layer * g->args.seq_len + pos0) * g->l_kv_dim;
+        CK(cudaMemcpy2D(k_out + r * g->l_kv_dim, out_ld * 4, g->d_kcache + base, (size_t)g->l_kv_dim * 4, (size_t)g->l_kv_dim * 4, n, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(v_out + r * g->l_kv_dim, out_ld * 4, g->d_vcache + base, (size_t)g->l_kv_dim * 4, (size_t)g->l_kv_dim * 4, n, cudaMemcpyDeviceToHost));
+    }
     CK(cudaSetDevice(m->device));
-    CK(cudaStreamSynchronize(m->stream));
-    size_t base = ((size_t)layer * m->args.seq_len + pos0) * m->l_kv_dim;
-    CK(cudaMemcpy(k_out, m->d_kcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(v_out, m->d_vcache + base, (size_t)n * m->l_kv_dim * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -68,14 +68,15 @@ struct PeerFlagParams {
     uint32_t* flag_peer[PX_MAX_WORLD];   // GPU r's flag array (peer-mapped); this rank writes element `rank`
     const uint32_t* flag_local;          // this GPU's flag array; element r is written by GPU r
     int world, rank, nowait;
-    const StepParams* step;
+    const StepParams* step;              // decode: the flag value is the step's sequence number (waits for equality)
+    uint32_t value; int use_value;       // batched prefill: a counter that only grows (waits for >=, wrap-around aware)
 };
 __global__ void __launch_bounds__(32) peer_flag_kernel(const PeerFlagParams p) {
     pdl_launch_dependents();
     pdl_wait();
     const int r = threadIdx.x;
     if (r >= p.world) return;
-    const uint32_t seq = p.step->seq;
+    const uint32_t seq = p.use_value ? p.value : p.step->seq;
     __threadfence_system();
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flag_peer[r] + p.rank), "r"(seq) : "memory");
     if (p.nowait) return;
@@ -83,10 +84,37 @@ __global__ void __launch_bounds__(32) peer_flag_kernel(const PeerFlagParams p) {
     for (;;) {
         uint32_t v;
         asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flag_local + r) : "memory");
-        if (v == seq) break;
+        if (p.use_value ? (int32_t)(v - seq) >= 0 : v == seq) break;
         __nanosleep(100);
         px_spin_check(sp);
     }
+}
+
+// ---- N-GPU batched prefill: the partial [T][dim] result of a K-sharded GEMM travels to every GPU as plain f32 rows (bandwidth-
+// bound, 4-7 MB: no per-word flags), one flag exchange (peer_flag_kernel) publishes it, and the sum over the GPUs is formed
+// in ascending rank order like the decode path's (the oracle's k-shard mode restates exactly this order).
+struct PxRowsParams {
+    const float* src;                    // push: this GPU's partial [count4 * 4]
+    float* dst[PX_MAX_WORLD];            // push: slot `rank` of the exchange buffer on every GPU (peer-mapped)
+    const float* slots;                  // sum: this GPU's exchange buffer, slot r at slots + r * slot_stride
+    float* out;                          // sum: [count4 * 4]
+    int world; size_t count4, slot_stride;
+};
+__global__ void __launch_bounds__(256) px_rows_push_kernel(const PxRowsParams p) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.count4) return;
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(p.src) + i);
+    for (int r = 0; r < p.world; r++) reinterpret_cast<float4*>(p.dst[r])[i] = v;
+}
+__global__ void __launch_bounds__(256) px_rows_sum_kernel(const PxRowsParams p) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= p.count4) return;
+    float4 v = __ldcg(reinterpret_cast<const float4*>(p.slots) + i);
+    for (int r = 1; r < p.world; r++) {
+        const float4 t = __ldcg(reinterpret_cast<const float4*>(p.slots + (size_t)r * p.slot_stride) + i);
+        v.x = __fadd_rn(v.x, t.x); v.y = __fadd_rn(v.y, t.y); v.z = __fadd_rn(v.z, t.z); v.w = __fadd_rn(v.w, t.w);
+    }
+    reinterpret_cast<float4*>(p.out)[i] = v;
 }
 
 // ---- batched prefill row kernels (fill_kv_cache, src/transformer.rs:672-684 -> forward_layer with sl = N) ----------
@@ -262,6 +290,37 @@ __global__ void __launch_bounds__(256) rmsnorm_kernel(float* o, const float* x, 
         const float t = __fmul_rn(r, x[i]);
         o[i] = unit ? __fmul_rn(__fadd_rn(1.0f, w[i]), t) : __fmul_rn(w[i], t);
     }
+}
+// src/functional.rs:80-114 (the vision tower's norm): mean and variance each accumulated in eight lane partials walked
+// serially over j (x[8j+k]; then (x - mean)^2 with mul and add unfused), wide's horizontal order, /size, +eps, 1/sqrt;
+// out = ((x - mean) * inv_std) * w + b, unfused.  One CTA per row; the size % 8 tail is left untouched like the reference.
+__global__ void __launch_bounds__(256) layernorm_rows_kernel(float* o, const float* x, const float* w, const float* b, int size, float eps) {
+    __shared__ float red[2];
+    const float* xr = x + (size_t)blockIdx.x * size;
+    float* orow = o + (size_t)blockIdx.x * size;
+    const int n8 = size / 8 * 8;
+    auto lanes_reduce = [&](float s) {   // ((a0+a4)+(a2+a6))+((a1+a5)+(a3+a7)), see exact_rnorm
+        const int lane = threadIdx.x;
+        const float t = __fadd_rn(s, __shfl_sync(0xffffffffu, s, (lane + 4) & 31));
+        const float u = __fadd_rn(t, __shfl_sync(0xffffffffu, t, (lane + 2) & 31));
+        return __fadd_rn(u, __shfl_sync(0xffffffffu, u, (lane + 1) & 31));
+    };
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        float s = 0.0f;
+        if (lane < 8)
+            for (int j = 0; j < n8 / 8; j++) s = __fadd_rn(s, xr[8 * j + lane]);
+        const float mean = __fdiv_rn(__shfl_sync(0xffffffffu, lanes_reduce(s), 0), (float)size);
+        float v = 0.0f;
+        if (lane < 8)
+            for (int j = 0; j < n8 / 8; j++) { const float d = __fsub_rn(xr[8 * j + lane], mean); v = __fadd_rn(v, __fmul_rn(d, d)); }
+        const float var = __fadd_rn(__fdiv_rn(lanes_reduce(v), (float)size), eps);
+        if (lane == 0) { red[0] = mean; red[1] = __fdiv_rn(1.0f, __fsqrt_rn(var)); }
+    }
+    __syncthreads();
+    const float mean = red[0], inv_std = red[1];
+    for (int i = threadIdx.x; i < n8; i += 256)
+        orow[i] = __fadd_rn(__fmul_rn(__fmul_rn(__fsub_rn(xr[i], mean), inv_std), w[i]), b[i]);
 }
 // src/functional.rs:122-140: max, exp(x-max) with glibc's expf, SERIAL sum, divide -- bit-exact
 __global__ void __launch_bounds__(256) softmax_kernel(float* x, int n) {

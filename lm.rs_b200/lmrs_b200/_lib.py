@@ -10,11 +10,12 @@ PKG_ROOT = os.path.dirname(_HERE)
 
 # every symbol include/lmrs_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 ABI_SYMBOLS = [
-    "lmrs_b200_create", "lmrs_b200_create_sharded", "lmrs_b200_nccl_unique_id", "lmrs_b200_destroy",
+    "lmrs_b200_create", "lmrs_b200_create_multi", "lmrs_b200_create_sharded", "lmrs_b200_nccl_unique_id", "lmrs_b200_destroy",
     "lmrs_b200_args", "lmrs_b200_forward", "lmrs_b200_get_embeddings", "lmrs_b200_fill_kv_cache",
     "lmrs_b200_forward_argmax", "lmrs_b200_generate_greedy", "lmrs_b200_forward_device", "lmrs_b200_logits_device", "lmrs_b200_set_stream", "lmrs_b200_synchronize",
     "lmrs_b200_kernel_launches", "lmrs_b200_bench_gemv_pass", "lmrs_b200_bench_attn_pass", "lmrs_b200_last_prefill_device_ms", "lmrs_b200_read_kv", "lmrs_b200_debug_buffer", "lmrs_b200_matmul_q8", "lmrs_b200_matmul_q4", "lmrs_b200_matmul_f32", "lmrs_b200_matmul_rest",
-    "lmrs_b200_quantize_q8", "lmrs_b200_quantize_q4", "lmrs_b200_rmsnorm", "lmrs_b200_softmax",
+    "lmrs_b200_quantize_q8", "lmrs_b200_quantize_q4", "lmrs_b200_rmsnorm", "lmrs_b200_softmax", "lmrs_b200_layernorm",
+    "lmrs_b200_weights_upload", "lmrs_b200_matmul_w", "lmrs_b200_weights_free",
     "lmrs_b200_last_error", "lmrs_b200_version",
 ]
 
@@ -51,6 +52,7 @@ def lib():
     L.lmrs_b200_last_error.restype = C.c_char_p
     L.lmrs_b200_version.restype = C.c_char_p
     L.lmrs_b200_create.argtypes = [vp, sz, i, C.POINTER(vp), C.POINTER(sz)]
+    L.lmrs_b200_create_multi.argtypes = [vp, sz, i, C.POINTER(vp), C.POINTER(sz)]
     L.lmrs_b200_create_sharded.argtypes = [vp, sz, i, i, i, vp, C.POINTER(vp), C.POINTER(sz)]
     L.lmrs_b200_nccl_unique_id.argtypes = [vp]
     L.lmrs_b200_destroy.argtypes = [vp]
@@ -79,6 +81,11 @@ def lib():
     L.lmrs_b200_quantize_q4.argtypes = [vp] * 3 + [i] * 2
     L.lmrs_b200_rmsnorm.argtypes = [vp] * 3 + [i, C.c_float, i]
     L.lmrs_b200_softmax.argtypes = [vp, i]
+    L.lmrs_b200_layernorm.argtypes = [vp] * 4 + [i, i, C.c_float]
+    L.lmrs_b200_weights_upload.argtypes = [i, vp, vp, i, i, i, C.POINTER(vp)]
+    L.lmrs_b200_matmul_w.argtypes = [vp, vp, vp, vp, i]
+    L.lmrs_b200_weights_free.argtypes = [vp]
+    L.lmrs_b200_weights_free.restype = None
     _lib = L
     return L
 

@@ -89,6 +89,8 @@ MODEL_SHAPES = {
                        vocab_size=512, seq_len=256, rms_norm_eps=1e-6, rope_theta=10000.0, model_type=GEMMA),
     "tiny-gemma-narrow": dict(dim=384, hidden_dim=512, n_layers=2, n_heads=2, head_size=128, n_kv_heads=1,  # att_dim < dim
                               vocab_size=512, seq_len=256, rms_norm_eps=1e-6, rope_theta=10000.0, model_type=GEMMA),
+    "tiny-gemma-narrow2": dict(dim=640, hidden_dim=512, n_layers=2, n_heads=4, head_size=128, n_kv_heads=2,  # att_dim 512 < dim: batches of <= 3 rows are defined
+                               vocab_size=512, seq_len=256, rms_norm_eps=1e-6, rope_theta=10000.0, model_type=GEMMA),
     "tiny-phi": dict(dim=384, hidden_dim=512, n_layers=2, n_heads=4, head_size=96, n_kv_heads=4,
                      vocab_size=512, seq_len=256, rms_norm_eps=1e-5, rope_theta=10000.0, model_type=PHI),
     "small-llama": dict(dim=1024, hidden_dim=2048, n_layers=4, n_heads=16, head_size=64, n_kv_heads=4,

@@ -48,6 +48,16 @@ class Transformer:
         return cls(h, a), end.value
 
     @classmethod
+    def new_multi(cls, data, n_gpus: int):
+        """Transformer::new on n_gpus GPUs of this process (lmrs_b200_create_multi): one handle drives all of them."""
+        buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)
+        h, end = C.c_void_p(), C.c_size_t()
+        check(lib().lmrs_b200_create_multi(_vp(buf), buf.size, n_gpus, C.byref(h), C.byref(end)))
+        a = Args()
+        check(lib().lmrs_b200_args(h, C.byref(a)))
+        return cls(h, a), end.value   # (read_kv of a group returns whole rows: world stays 1 for the mirror)
+
+    @classmethod
     def new_sharded(cls, data, device: int, rank: int, world: int, nccl_unique_id: bytes):
         """One process per GPU, output rows sharded across `world` ranks."""
         buf = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else np.ascontiguousarray(data, np.uint8)

@@ -12,7 +12,38 @@ use std::ffi::CStr;
 use std::marker::PhantomData;
 use std::os::raw::{c_char, c_int};
 
-use crate::quantization::QuantType;
+use crate::functional::{u8_to_f32_slice, u8_to_i8_slice};
+use crate::quantization::{QuantType, QuantizedTensor};
+
+// ---- tensor views over the mapped file: `src/vision.rs:2` and `src/processor.rs:2` import these two helpers from this
+// module (reference src/transformer.rs:16-48), so the multimodal build needs them here too.  They stay host-side: the
+// vision tower still runs on the reference's CPU operators (or on the operator-level C ABI).
+
+/// The next `n * size_each` f32 values of the file; advances `offset` past them.
+pub fn init_param<'a>(data: &'a [u8], offset: &mut usize, n: u32, size_each: u32) -> &'a [f32] {
+    let start = *offset;
+    let end = start + n as usize * size_each as usize * std::mem::size_of::<f32>();
+    *offset = end;
+    u8_to_f32_slice(&data[start..end])
+}
+
+/// `n` consecutive quantized tensors of `size_each` elements: codes (one byte per element, two elements per byte for
+/// Q4_0) immediately followed by one f32 scale per `gs` elements.  The returned slice lives for the rest of the process
+/// like the reference's (it leaks the small vector of views, not the weights).
+pub fn init_param_quant<'a>(data: &'a [u8], offset: &mut usize, n: u32, size_each: u32, gs: u32, q_type: QuantType) -> &'a [QuantizedTensor<'a>] {
+    let code_bytes = if q_type == QuantType::Q4_0 { size_each as usize / 2 } else { size_each as usize };
+    let scale_bytes = (size_each / gs) as usize * std::mem::size_of::<f32>();
+    let views: Vec<QuantizedTensor<'a>> = (0..n)
+        .map(|_| {
+            let q = u8_to_i8_slice(&data[*offset..*offset + code_bytes]);
+            *offset += code_bytes;
+            let s = u8_to_f32_slice(&data[*offset..*offset + scale_bytes]);
+            *offset += scale_bytes;
+            QuantizedTensor { q, s }
+        })
+        .collect();
+    Box::leak(views.into_boxed_slice())
+}
 
 #[derive(Debug, Copy, Clone, PartialEq)]
 #[repr(u8)]
@@ -31,6 +62,7 @@ pub struct TransformerArgs {
 #[link(name = "lmrs_b200")]
 extern "C" {
     fn lmrs_b200_create(file: *const u8, len: usize, device: c_int, out: *mut *mut Handle, end_offset: *mut usize) -> c_int;
+    fn lmrs_b200_create_multi(file: *const u8, len: usize, n_gpus: c_int, out: *mut *mut Handle, end_offset: *mut usize) -> c_int;
     fn lmrs_b200_destroy(m: *mut Handle);
     fn lmrs_b200_args(m: *const Handle, out: *mut TransformerArgs) -> c_int;
     fn lmrs_b200_forward(m: *mut Handle, token: u32, pos: u32, logits_host: *mut *mut f32) -> c_int;
@@ -56,7 +88,13 @@ impl<'a> Transformer<'a> {
     pub fn new(data: &'a Mmap) -> (Transformer<'a>, usize) {
         let mut h: *mut Handle = std::ptr::null_mut();
         let mut end: usize = 0;
-        check(unsafe { lmrs_b200_create(data.as_ptr(), data.len(), -1, &mut h, &mut end) });
+        // LMRS_B200_GPUS=N: all N GPUs of this process behind the one handle (row-sharded, exchange inside the kernels)
+        let n_gpus: c_int = std::env::var("LMRS_B200_GPUS").ok().and_then(|v| v.parse().ok()).unwrap_or(1);
+        if n_gpus > 1 {
+            check(unsafe { lmrs_b200_create_multi(data.as_ptr(), data.len(), n_gpus, &mut h, &mut end) });
+        } else {
+            check(unsafe { lmrs_b200_create(data.as_ptr(), data.len(), -1, &mut h, &mut end) });
+        }
         let mut args = std::mem::MaybeUninit::<TransformerArgs>::uninit();
         check(unsafe { lmrs_b200_args(h, args.as_mut_ptr()) });
         let args = unsafe { args.assume_init() };

@@ -90,6 +90,27 @@ void lmrs_ref_rmsnorm(float* o, const float* x, const float* w, int size, float 
 }
 
 /* src/functional.rs:122-140 */
+/* src/functional.rs:80-114: mean and variance in eight lane partials each (x[8j+k] / (x[8j+k]-mean)^2 walked over j),
+ * wide's reduce_add order (see the header comment), / size, + eps, 1/sqrt; o = ((x - mean) * inv_std) * w + b with every
+ * operation rounded separately (operator overloads of wide::f32x8: no fused multiply-add).  Elements beyond size/8*8
+ * are not written. */
+void lmrs_ref_layernorm(float* o, const float* x, const float* w, const float* b, int size, float eps) {
+    int n8 = size / 8;
+    float m[8] = {0}, v[8] = {0};
+    for (int j = 0; j < n8; j++)
+        for (int k = 0; k < 8; k++) m[k] += x[8 * j + k];
+    float mean = (((m[0] + m[4]) + (m[2] + m[6])) + ((m[1] + m[5]) + (m[3] + m[7]))) / (float)size;
+    for (int j = 0; j < n8; j++)
+        for (int k = 0; k < 8; k++) { float d = x[8 * j + k] - mean; float d2 = d * d; v[k] += d2; }
+    float var = (((v[0] + v[4]) + (v[2] + v[6])) + ((v[1] + v[5]) + (v[3] + v[7]))) / (float)size + eps;
+    float inv_std = 1.0f / sqrtf(var);
+    for (int i = 0; i < n8 * 8; i++) {
+        float nrm = (x[i] - mean) * inv_std;
+        float t = nrm * w[i];
+        o[i] = t + b[i];
+    }
+}
+
 void lmrs_ref_softmax(float* x, int n) {
     float sum = 0.0f, max_val = x[0];
     for (int i = 0; i < n; i++)
@@ -507,8 +528,11 @@ static int forward_layer(lmrs_ref_t* m, float* x, uint32_t sl, uint32_t l, uint3
     const uint32_t kv_mul = p.n_heads / p.n_kv_heads, hidden_dim = p.hidden_dim;
     const int gemma = p.model_type == 0;
     if (pos + sl > p.seq_len) return fail("position out of range (seq_len is clamped to 8192)");
-    if (sl > 1 && att_dim < dim)
-        return fail("sl>1 with att_dim<dim is out of bounds in the reference (src/transformer.rs:501-503)");
+    /* :501-503 walks `embeddings` (sl*dim floats) in chunks of att_dim: floor(sl*dim/att_dim) chunks.  One chunk per token
+     * is what the code means; as soon as there is one more (sl*(dim-att_dim) >= att_dim) its `sq` slice is out of bounds
+     * and the reference panics.  Below that the batch is well defined (Gemma-2-2B: up to 7 rows). */
+    if (att_dim < dim && (size_t)sl * (dim - att_dim) >= att_dim)
+        return fail("sl*(dim-att_dim) >= att_dim is out of bounds in the reference (src/transformer.rs:501-503)");
 
     size_t total = (size_t)sl * dim, total_h = (size_t)sl * hidden_dim;
     size_t emb_len = total > (size_t)sl * att_dim ? total : (size_t)sl * att_dim; /* :497-499 */

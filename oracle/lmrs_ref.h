@@ -56,6 +56,7 @@ const float* lmrs_ref_value_cache(const lmrs_ref_t* m);
 
 /* src/functional.rs */
 void lmrs_ref_rmsnorm(float* o, const float* x, const float* w, int size, float eps, int add_unit_offset);
+void lmrs_ref_layernorm(float* o, const float* x, const float* w, const float* b, int size, float eps);
 void lmrs_ref_softmax(float* x, int n);
 void lmrs_ref_matmul_f32(float* xout, const float* x, const float* w, int rows, int n, int o);
 void lmrs_ref_matmul_rest(float* xout, const float* x, const float* w, int rows, int n, int o);

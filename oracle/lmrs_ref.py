@@ -87,6 +87,8 @@ def lib():
         L.lmrs_ref_value_cache.restype = _f32p
         L.lmrs_ref_rmsnorm.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.lmrs_ref_rmsnorm.restype = None
+        L.lmrs_ref_layernorm.argtypes = [C.c_void_p] * 4 + [C.c_int, C.c_float]
+        L.lmrs_ref_layernorm.restype = None
         L.lmrs_ref_softmax.argtypes = [C.c_void_p, C.c_int]
         L.lmrs_ref_softmax.restype = None
         for name in ("lmrs_ref_matmul_f32", "lmrs_ref_matmul_rest"):
@@ -121,6 +123,13 @@ def rmsnorm(x, w, eps, add_unit_offset=False):
     x, w = _c(x, np.float32), _c(w, np.float32)
     o = np.zeros_like(x)
     lib().lmrs_ref_rmsnorm(_p(o), _p(x), _p(w), x.size, eps, int(add_unit_offset))
+    return o
+
+
+def layernorm(x, w, b, eps):
+    x, w, b = _c(x, np.float32), _c(w, np.float32), _c(b, np.float32)
+    o = np.zeros_like(x)
+    lib().lmrs_ref_layernorm(_p(o), _p(x), _p(w), _p(b), x.size, eps)
     return o
 
 

@@ -145,6 +145,28 @@ def test_llama_1b_q8_full_shape(gpu_lib, ref, lf):
         assert np.array_equal(lg, le), f"pos {96 + i}: max abs {np.abs(lg - le).max()}"
 
 
+@pytest.mark.parametrize("name,q_type,layers", [("llama-3.2-3b", 2, 3), ("phi-3.5-mini", 1, 2), ("gemma-2-9b", 1, 2), ("llama-3.2-3b", 1, 2)])
+def test_full_shapes_of_the_other_baseline_configs(gpu_lib, ref, lf, name, q_type, layers):
+    """BASELINE configs 3-5 at their real dim / hidden / heads / head_size / vocabulary (Llama-3.2-3B Q4_0 and Q8_0,
+    Phi-3.5-mini Q8_0 with its separate lm_head, Gemma-2-9B Q8_0 with dim 3584 = 28 groups and att_dim > dim), truncated to
+    a few blocks so the CPU oracle finishes in seconds: a 40-embedding fill_kv_cache (tcgen05 GEMM path for Q8_0, per-token
+    chain for Q4_0), then decode steps.  LLAMA / PHI bit for bit, GEMMA (f64 tanh in two libms) within 1e-3."""
+    a = lf.model_args(name, q_type, n_layers=layers)
+    buf = lf.write_synthetic(a, seed=3, mode="fast")
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    exact = a.model_type != 0
+    toks = prompt_tokens(a.vocab_size, 44, seed=5)
+    eg, ec = gpu.get_embeddings(toks[:40]), cpu.get_embeddings(toks[:40])
+    assert np.array_equal(eg, ec)
+    assert gpu.fill_kv_cache(eg, 0) == cpu.fill_kv_cache(ec, 0) == 40
+    assert np.array_equal(eg, ec) if exact else float(np.abs(eg - ec).max()) <= TOL, f"{name}: residual stream"
+    for i, t in enumerate(toks[40:]):
+        lg, le = gpu.forward(int(t), 40 + i), cpu.forward(int(t), 40 + i)
+        assert np.array_equal(lg, le) if exact else float(np.abs(lg - le).max()) <= TOL, f"{name} pos {40 + i}: max abs {np.abs(lg - le).max()}"
+    gpu.close(); cpu.close()
+
+
 def test_fill_kv_cache_edge_cases(gpu_lib, ref, lf):
     """empty batch, batch crossing the shared-memory score capacity (serial fallback + HBM score scratch), out of range."""
     a = lf.model_args("tiny-llama", 1, seq_len=4096)
@@ -202,6 +224,21 @@ def test_batched_prefill_ragged_multi_tile(gpu_lib, ref, lf, name):
     for i in range(2):
         lg, le = gpu.forward(int(toks[pos + i]), pos + i), cpu.forward(int(toks[pos + i]), pos + i)
         assert np.array_equal(lg, le) if exact else float(np.abs(lg - le).max()) <= TOL, f"{name}: logits at {pos + i}"
+
+
+def test_batches_with_att_dim_below_dim(gpu_lib, ref, lf):
+    """att_dim < dim (Gemma-2-2B-like): the reference's chunking (src/transformer.rs:501-503) is well defined while
+    n * (dim - att_dim) < att_dim and panics beyond; same boundary here (3 rows run, 4 are refused)."""
+    buf = lf.write_synthetic(lf.model_args("tiny-gemma-narrow2", 1))
+    cpu = ref.RefTransformer(buf)
+    gpu, _ = gpu_lib.Transformer.new(buf)
+    toks = prompt_tokens(gpu.args.vocab_size, 5, seed=2)
+    eg, ec = gpu.get_embeddings(toks[:3]), cpu.get_embeddings(toks[:3])
+    assert gpu.fill_kv_cache(eg, 0) == cpu.fill_kv_cache(ec, 0) == 3
+    assert float(np.abs(eg - ec).max()) <= TOL
+    assert float(np.abs(gpu.forward(int(toks[3]), 3) - cpu.forward(int(toks[3]), 3)).max()) <= TOL
+    with pytest.raises(gpu_lib.LmrsError):
+        gpu.fill_kv_cache(gpu.get_embeddings(toks[:4]), 4)
 
 
 def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):

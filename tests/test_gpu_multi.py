@@ -19,10 +19,12 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True):
+def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True, pf_rows=None):
     for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     os.environ["LMRS_B200_PEER"] = "1" if peer else "0"
+    if pf_rows:
+        os.environ["LMRS_B200_PF_ROWS"] = str(pf_rows)
     import torch
     import torch.distributed as dist
     import lmrs_b200
@@ -61,6 +63,16 @@ def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True):
             le = cpu.forward(int(t), 4 + i)
             worst = max(worst, float(np.abs(lg - le).max()))
             exact = exact and np.array_equal(lg, le)
+    if peer:   # a batch large enough for the tcgen05 GEMM path (walked in chunks of LMRS_B200_PF_ROWS rows), then one more step
+        toks2 = np.random.default_rng(4).integers(0, m.args.vocab_size, 41)
+        emb2 = m.get_embeddings(toks2[:40])
+        assert m.fill_kv_cache(emb2, 10) == 50
+        lg = m.forward(int(toks2[40]), 50)
+        if rank == 0:
+            ec2 = cpu.get_embeddings(toks2[:40]); cpu.fill_kv_cache(ec2, 10)
+            le = cpu.forward(int(toks2[40]), 50)
+            worst = max(worst, float(np.abs(emb2 - ec2).max()), float(np.abs(lg - le).max()))
+            exact = exact and np.array_equal(emb2, ec2) and np.array_equal(lg, le)
     if rank == 0:
         open(os.path.join(out_dir, "worst.txt"), "w").write(repr(worst))
         open(os.path.join(out_dir, "exact.txt"), "w").write("1" if exact else "0")
@@ -80,15 +92,15 @@ def test_two_gpu_sharded_forward_matches_oracle(tmp_path):
     assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
 
 
-@pytest.mark.parametrize("world,name", [(2, "tiny-llama"), (2, "small-llama"), (4, "small-llama")])
-def test_peer_exchange_is_bit_exact_against_the_kshard_oracle(tmp_path, world, name):
+@pytest.mark.parametrize("world,name,pf_rows", [(2, "tiny-llama", None), (2, "small-llama", None), (2, "small-llama", 16), (4, "small-llama", None)])
+def test_peer_exchange_is_bit_exact_against_the_kshard_oracle(tmp_path, world, name, pf_rows):
     """Default N-GPU data path: partials pushed between the GPUs by the kernels, added in rank order -> same bits as the
     oracle in k-shard mode (fill_kv_cache residual stream and decode logits), tiny and 4-block models."""
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     import torch.multiprocessing as mp
-    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), name), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), name, None, True, pf_rows), nprocs=world, join=True)
     assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
     assert open(tmp_path / "exact.txt").read() == "1"
 
@@ -100,3 +112,50 @@ def test_two_gpu_rejects_shapes_that_split_a_quantization_group(tmp_path):
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), "tiny-phi", "multiple of 128"), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("n_gpus,name,q", [(2, "tiny-llama", 1), (2, "small-llama", 1), (2, "small-llama", 2), (4, "small-llama", 1)])
+def test_in_process_multi_gpu_handle_is_bit_exact(n_gpus, name, q):
+    """lmrs_b200_create_multi: ONE process, one handle, n GPUs (what Transformer::new needs to use several GPUs behind the
+    unchanged bins): fill_kv_cache, forward, forward_argmax, generate_greedy and read_kv against the k-shard oracle."""
+    import torch
+    if torch.cuda.device_count() < n_gpus:
+        pytest.skip(f"needs {n_gpus} GPUs")
+    for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import lmrs_b200
+    import lmrs_ref
+    from lmrs_b200 import lmrs_file as lf
+    a = lf.model_args(name, q)
+    buf = lf.write_synthetic(a)
+    lmrs_ref.set_kshards(n_gpus)
+    try:
+        cpu = lmrs_ref.RefTransformer(buf)
+        gpu, end = lmrs_b200.Transformer.new_multi(buf, n_gpus)
+        assert end == buf.size
+        toks = np.random.default_rng(3).integers(0, a.vocab_size, 16).astype(np.uint32)
+        eg, ec = gpu.get_embeddings(toks[:6]), cpu.get_embeddings(toks[:6])
+        assert gpu.fill_kv_cache(eg, 0) == cpu.fill_kv_cache(ec, 0) == 6
+        assert np.array_equal(eg, ec)
+        for i, t in enumerate(toks[6:10]):
+            assert np.array_equal(gpu.forward(int(t), 6 + i), cpu.forward(int(t), 6 + i)), f"pos {6 + i}"
+        kc, vc = cpu.kv_cache()
+        k, v = gpu.read_kv(a.n_layers - 1, 0, 10)
+        assert np.array_equal(k, kc[a.n_layers - 1, :10]) and np.array_equal(v, vc[a.n_layers - 1, :10])
+        # greedy continuation: device-side pick and feedback on every GPU vs argmax of the oracle logits
+        tok, want = int(toks[10]), []
+        for i in range(5):
+            tok = int(np.argmax(cpu.forward(tok, 10 + i))); want.append(tok)
+        assert gpu.forward_argmax(int(toks[10]), 10) == want[0]
+        got = gpu.generate_greedy(int(toks[10]), 10, 5)
+        assert got.tolist() == want
+        # a batch for the tcgen05 GEMM path (Q8_0 shapes whose shards stay 128-aligned; the per-token chain otherwise)
+        toks2 = np.random.default_rng(4).integers(0, a.vocab_size, 41).astype(np.uint32)
+        eg2, ec2 = gpu.get_embeddings(toks2[:40]), cpu.get_embeddings(toks2[:40])
+        assert gpu.fill_kv_cache(eg2, 15) == cpu.fill_kv_cache(ec2, 15) == 55
+        assert np.array_equal(eg2, ec2)
+        assert np.array_equal(gpu.forward(int(toks2[40]), 55), cpu.forward(int(toks2[40]), 55))
+        gpu.close(); cpu.close()
+    finally:
+        lmrs_ref.set_kshards(1)

@@ -130,3 +130,43 @@ def test_matmul_f32_and_matmul_rest_bit_exact(gpu_lib, ref, rows, n, o, rest):
 def test_matmul_f32_refuses_an_output_count_the_reference_would_truncate(gpu_lib):
     with pytest.raises(gpu_lib.LmrsError, match="multiple of 4"):
         gpu_lib.functional.matmul(np.zeros(6, np.float32), np.zeros(8, np.float32), np.zeros(48, np.float32), 8, 6)
+
+
+@pytest.mark.parametrize("rows,size", [(1, 1024), (577, 1024), (3, 1032), (2, 1027), (1, 8)])
+def test_layernorm_rows_bit_exact(gpu_lib, ref, rows, size):
+    """src/functional.rs:80-114 for every token row of a vision-encoder activation (CLIP hidden size 1024; sizes with a
+    size % 8 tail, which the reference leaves untouched)."""
+    rng = np.random.default_rng(size + rows)
+    x = rng.standard_normal((rows, size)).astype(np.float32) * 3 + 0.5
+    w = (1 + 0.1 * rng.standard_normal(size)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(size)).astype(np.float32)
+    exp = np.stack([ref.layernorm(x[r], w, b, 1e-5) for r in range(rows)])     # the oracle zero-fills the tail of its output
+    got = np.zeros((rows, size), np.float32)
+    gpu_lib.functional.layernorm(got, x, w, b, size, 1e-5)
+    assert np.array_equal(got, exp), f"max abs diff {np.abs(got - exp).max()}"
+
+
+@pytest.mark.parametrize("q_type,n,o,rows", [(1, 1024, 1024, 577), (1, 1024, 4096, 64), (1, 4096, 1024, 5), (1, 384, 100, 3),
+                                               (2, 1024, 1024, 3)])
+def test_resident_weights_matmul_bit_exact(gpu_lib, ref, q_type, n, o, rows):
+    """weights uploaded once (lmrs_b200_weights_upload), applied to several batches of rows (tcgen05 GEMM for >= 8 Q8_0 rows
+    of 128-aligned shapes, the matrix-vector kernel otherwise): same bits as matmul_q8 / matmul_q4 of the oracle."""
+    rng = np.random.default_rng(n + o + rows)
+    if q_type == 1:
+        wq, ws = _rand_q8(rng, o, n, 0.002)
+    else:
+        wq = rng.integers(0, 256, size=o * n // 2, dtype=np.uint8)
+        ws = (rng.uniform(0.5, 1.5, o * n // 128) * -0.003).astype(np.float32)
+    W = gpu_lib.functional.ResidentWeights(QT(wq, ws), n, o, 128, q_type)
+    for rr in (rows, 1, rows):
+        if q_type == 1:
+            xq, xs = _rand_q8(rng, rr, n, 0.01)
+            exp = ref.matmul_q8(xq, xs, wq, ws, rr, n, o, 128)
+        else:
+            xq = rng.integers(0, 256, size=rr * n // 2, dtype=np.uint8)
+            xs = (rng.uniform(0.5, 1.5, rr * n // 128) * -0.01).astype(np.float32)
+            exp = ref.matmul_q4(xq, xs, wq, ws, rr, n, o, 128)
+        got = np.full(rr * o, np.nan, np.float32)
+        W.matmul(got, QT(xq, xs))
+        assert np.array_equal(got, exp), f"rows {rr}: max abs diff {np.abs(got - exp).max()}"
+    W.close()
