@@ -140,7 +140,10 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr int STAGE_BYTES = GEMM_TILE_BYTES + B_TILE_BYTES;
     constexpr int OUT_COLS = GLU ? 64 : BNM;                              // output columns (rows of w) per CTA
     extern __shared__ uint8_t gsm_raw[];
-    uint8_t* gsm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(gsm_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment for the 128B-swizzled operand tiles, computed on the SHARED-window offset and applied as pointer
+    // arithmetic on gsm_raw: a round trip through uintptr_t makes the compiler forget the address space, and every access
+    // behind it (the per-group scale loads of the epilogue) became a generic LD.E instead of LDS in the first builds
+    uint8_t* gsm = gsm_raw + (((smem_u32(gsm_raw) + 1023u) & ~1023u) - smem_u32(gsm_raw));
     const int G = p.n / GEMM_K;
     uint8_t* tiles = gsm;                                                   // [STAGES][A 16 KB | B]
     float* ws_t = reinterpret_cast<float*>(tiles + (size_t)GEMM_STAGES * STAGE_BYTES);   // [G][BNM]
@@ -233,16 +236,18 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             const uint64_t xs2 = f2_pack(xsc, xsc);
             mbar_wait(&tfull[b], (g >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            // all of this thread's accumulator words of the group are requested back to back; once they sit in registers the
+            // TMEM buffer goes back to the MMA warp BEFORE the arithmetic, so group g+2's MMAs run under group g's epilogue
+            uint32_t v[NCH][32];
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * BNM + col_of(c)), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                gemm_epi_chunk(acc + c * 16, v, ws_t + g * BNM + col_of(c), xs2, neg_magic2, nz2);
-            }
+            for (int c = 0; c < NCH; c++)
+                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * BNM + col_of(c)), v[c]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
+#pragma unroll
+            for (int c = 0; c < NCH; c++) gemm_epi_chunk(acc + c * 16, v[c], ws_t + g * BNM + col_of(c), xs2, neg_magic2, nz2);
         }
         if (row_ok) {
             if constexpr (GLU) {

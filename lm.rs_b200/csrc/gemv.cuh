@@ -428,10 +428,10 @@ template <bool LL> LMRS_DEVINL void act_store(void* base, size_t i, float v, uin
 }
 
 // ---- prologue: build the quantized activation in shared memory (whole CTA, ends with __syncthreads) ----------------
-template <int QT, int WARPS, int PRO, bool LL>
+template <int QT, int WARPS, int PRO, bool LL, int MAXC = NORM_MAX_DIM / 4 / (WARPS * 32)>
 LMRS_DEVINL void gemv_prologue(const GemvParams& p, const GemvSmem& sm, const uint32_t seq) {
     constexpr int THREADS = WARPS * 32;
-    constexpr int NORM_MAXC = NORM_MAX_DIM / 4 / THREADS;   // float4 chunks per thread
+    constexpr int NORM_MAXC = MAXC;   // float4 chunks per thread (default: enough for dim <= NORM_MAX_DIM)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = p.n, G = n / GS;
     const bool nowait = (LL || p.px_world > 1) && p.ll_nowait;

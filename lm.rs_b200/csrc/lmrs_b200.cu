@@ -1070,9 +1070,16 @@ static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
 static int launch_rows_prologue(lmrs_b200* m, GemvParams p, int T) {
     const int n = p.n, G = n / GS;
     size_t smem = (size_t)((n + 127) / 128) * 128 + (size_t)((G * 8 + 127) / 128) * 128 + 64 * 4 + (p.pro == PRO_NORM ? (size_t)n * 4 + 128 : 0) + 128;
-    static thread_local size_t set_for = 0;
-    if (smem > set_for) { CK(cudaFuncSetAttribute(rows_prologue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); set_for = smem; }
-    rows_prologue_kernel<<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
+    if (p.pro == PRO_NORM && n > 2048) {
+        CK(smem_optin(m, (const void*)rows_prologue_kernel<PRO_NORM, 4>, smem));
+        rows_prologue_kernel<PRO_NORM, 4><<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
+    } else if (p.pro == PRO_NORM) {
+        CK(smem_optin(m, (const void*)rows_prologue_kernel<PRO_NORM, 2>, smem));
+        rows_prologue_kernel<PRO_NORM, 2><<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
+    } else {   // (the quantize-only prologue keeps nothing per thread across its loop: any n)
+        CK(smem_optin(m, (const void*)rows_prologue_kernel<PRO_QUANT, 2>, smem));
+        rows_prologue_kernel<PRO_QUANT, 2><<<T, 256, smem, m->stream>>>(p, m->pf_xq, m->pf_xs);
+    }
     m->launches++;
     CK(cudaGetLastError());
     return 0;

@@ -120,7 +120,9 @@ __global__ void __launch_bounds__(256) px_rows_sum_kernel(const PxRowsParams p) 
 // ---- batched prefill row kernels (fill_kv_cache, src/transformer.rs:672-684 -> forward_layer with sl = N) ----------
 // one CTA per token row: the GEMV prologue (residual add, exact rmsnorm, activation quantize) with its result written
 // to HBM as the int8 A operand + scales of the tcgen05 GEMM
-__global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_t* xq_out, float* xs_out) {
+// MAXC: float4 chunks of the row per thread (n <= 1024 * MAXC): the fewer, the fewer registers and the more rows per SM
+template <int PRO, int MAXC>
+__global__ void __launch_bounds__(256, MAXC <= 2 ? 3 : 2) rows_prologue_kernel(GemvParams p, uint8_t* xq_out, float* xs_out) {
     extern __shared__ __align__(128) uint8_t rsm[];
     const size_t row = blockIdx.x;
     const int n = p.n, G = n / GS;
@@ -136,8 +138,7 @@ __global__ void __launch_bounds__(256) rows_prologue_kernel(GemvParams p, uint8_
     if (p.x_out) p.x_out = reinterpret_cast<float*>(p.x_out) + row * n;
     if (p.act_in) p.act_in = reinterpret_cast<const float*>(p.act_in) + row * n;
     p.xout_all = 1;
-    if (p.pro == PRO_NORM) gemv_prologue<1, 8, PRO_NORM, false>(p, sm, 0u);
-    else gemv_prologue<1, 8, PRO_QUANT, false>(p, sm, 0u);
+    gemv_prologue<1, 8, PRO, false, MAXC>(p, sm, 0u);
     for (int i = threadIdx.x; i < n / 16; i += 256) reinterpret_cast<int4*>(xq_out + row * n)[i] = reinterpret_cast<const int4*>(sm.xq)[i];
     for (int g = threadIdx.x; g < G; g += 256) xs_out[row * G + g] = sm.xs[g];
 }

@@ -181,25 +181,30 @@ __global__ void __launch_bounds__(512) prefill_av_kernel(const PrefillAttnParams
 
 // ---- fused form: scores + softmax + a*v of a tile of token rows in ONE kernel, score rows in shared memory ----------------
 //
-// CTA = (KV head, tile of `tb` consecutive tokens): RW = tb * kv_mul <= 32 (token, query head) rows.  256 threads =
-// 32 row slots x 8 lanes.  The scores never leave shared memory, the softmax rows are warp-local (the 8 lanes of a row
-// sit in one warp: no CTA barrier between its passes), and every phase keeps several INDEPENDENT exact-order chains per
-// thread so that the kernel is bound by instruction issue, not by the 4-cycle dependent-add latency:
-//   scores   lane j of a row owns positions 4j..4j+3 of every 32-position K tile: four ascending-d chains, two packed
-//            f32x2 multiply/add pairs per step (K tile transposed to [d][position], q stored as (q, q) pairs);
-//   softmax  max over the row, exp(x - max) (glibc expf restated), SERIAL sum in ascending t by one lane per row (32 rows
-//            run their chains side by side), divide;
-//   a*v      lane j of a row owns output dims [4j, 4j+4) of each HS/8... (HS/32 float4 per lane): one product and one
-//            dependent add per position in ascending t, packed two dims per instruction.
+// CTA = (KV head, tile of `tb` consecutive tokens): RW = tb * kv_mul <= 32 (token, query head) rows, handled as 16 ROW PAIRS:
+// every f32x2 instruction carries the SAME step of the two rows' chains in its two halves (q, the score rows and the
+// accumulators are stored pair-interleaved) and the K / V operand of a step is a scalar the packed instruction broadcasts.
+// The first build of this kernel (one row per 8-lane group, q and K re-read from shared memory for every 4 multiply-adds) was
+// bound by the shared-memory pipe, not by arithmetic (ncu: short-scoreboard stalls 5x the issue slots, a 128-bit LDS costs a
+// warp four pipe cycles whatever it broadcasts; profiles/r2_ncu_prefill_attn_raw.csv), so the work is register-tiled:
+//   scores   256 threads = 8 row quads x 32 lanes; thread (quad, lane j) owns the 4 x 4 tile of rows {two pairs} x positions
+//            4j..4j+3 of every 128-position K tile (K transposed to [d][position]): per d ONE 16-byte load of the two q pairs
+//            and ONE of four K values feed 8 packed multiply/add pairs = 16 ascending-d chains;
+//   softmax  warp-local (a quad's lanes are one warp; lanes 0..15 serve its first pair, 16..31 the second): max, exp(x - max)
+//            (glibc expf restated), SERIAL sums of both rows in ascending t by one lane (two independent chains), divide;
+//            positions beyond a row's own length are set to +0.0 (adding +-0 never changes an accumulator that started from
+//            +0.0, so the longer row of a pair may drive the loops);
+//   a*v      thread (pair, lane j of 16) owns float4 chunks j, j+16, .. of the head: one packed product and one dependent packed
+//            add per position and dim, ascending t, both rows of the pair per instruction.
 // Arithmetic per chain is exactly the reference's (src/transformer.rs:507-542, src/functional.rs:122-140): results are
 // bit-identical to the decode kernels and to the two-kernel form above.  Heavy (late) token tiles are scheduled first.
-constexpr int PFF_THREADS = 256, PFF_ROWS = 32, PFF_TT = 32, PFF_KS = PFF_TT + 4;
+constexpr int PFF_THREADS = 256, PFF_ROWS = 32, PFF_TT = 128, PFF_KS = PFF_TT + 4, PFF_VT = 64;
+inline int prefill_fused_scs(int t_max) { return ((t_max + 3) & ~3) + 2; }   // (pairs per score row) even; + 2 de-phases neighbouring pairs
 inline size_t prefill_fused_smem(int hs, int rw, int scs) {
-    return ((size_t)PFF_ROWS * (hs * 2 + 4) + (size_t)2 * hs * PFF_KS + (size_t)rw * scs + 64 + 8) * 4;
+    const size_t tile = (size_t)hs * PFF_KS > (size_t)2 * PFF_VT * hs ? (size_t)hs * PFF_KS : (size_t)2 * PFF_VT * hs;
+    return ((size_t)(PFF_ROWS / 4) * (hs * 4 + 8) + tile + (size_t)2 * ((rw + 1) / 2) * scs + 64 + 8) * 4;
 }
 constexpr size_t PFF_SMEM_MAX = 216 * 1024;
-// score row stride for contexts up to t_max positions: +4 floats de-phases the rows' banks
-inline int prefill_fused_scs(int t_max) { return ((t_max + 3) & ~3) + 4; }
 // tokens per CTA for contexts up to t_max positions (0: the score rows of even one token do not fit)
 inline int prefill_fused_tb(int hs, int kv_mul, int t_max) {
     if (kv_mul > PFF_ROWS) return 0;
@@ -211,156 +216,215 @@ inline int prefill_fused_tb(int hs, int kv_mul, int t_max) {
 // a separately rounded packed product (an add consumes it): fma(a, b, -0.0) with a run-time -0.0, see gemm.cuh f2_mul_sep
 LMRS_DEVINL uint64_t pf2_mul(uint64_t a, uint64_t b, uint64_t nz2) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz2)); return r; }
 LMRS_DEVINL uint64_t pf2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-LMRS_DEVINL uint64_t pf2_dup(float a) { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }
+LMRS_DEVINL uint64_t pf2_dup(float a) { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }   // (ptxas folds it into the .F32 broadcast operand form)
 LMRS_DEVINL void pf2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 
 template <int HS>
-__global__ void __launch_bounds__(PFF_THREADS) prefill_attn_fused_kernel(const PrefillAttnParams p, const int tb, const int SCS) {
-    static_assert(HS % 32 == 0, "eight lanes x whole float4 per V row");
-    constexpr int KS = PFF_KS, TT = PFF_TT;
-    constexpr int KPT = TT * (HS / 4) / PFF_THREADS;       // float4 of a K tile staged per thread
-    constexpr int VC = HS / 32;                            // float4 of a V row owned by one lane
+__global__ void __launch_bounds__(PFF_THREADS, HS <= 128 ? 2 : 1) prefill_attn_fused_kernel(const PrefillAttnParams p, const int tb, const int SCS) {
+    static_assert(HS % 32 == 0, "whole float4 per lane");
+    constexpr int KS = PFF_KS, TT = PFF_TT, VT = PFF_VT;
+    constexpr int NQ = HS / 4, NQT = (NQ + 15) / 16;       // float4 chunks of a K / V row; V chunks per lane
+    constexpr int KE = TT * NQ / PFF_THREADS;              // float4 of a K tile staged per thread
+    constexpr int KPF = KE <= 8 ? KE : 8;                  // of those, fetched one tile ahead into registers (the rest at store time)
+    constexpr int Q4S = HS * 4 + 8;                        // floats per row-quad row of q4
+    constexpr int TILE_F = HS * KS > 2 * VT * HS ? HS * KS : 2 * VT * HS;
     extern __shared__ __align__(16) float pff[];
-    constexpr int Q2S = HS * 2 + 4;                        // row stride of q2: +16 bytes puts the four rows of a warp on distinct banks
-    float* q2 = pff;                                       // [32][HS] (q, q) pairs
-    float* tile = q2 + PFF_ROWS * Q2S;                     // [2][HS][KS] transposed K tiles / [2][TT][HS] V tiles (HS*KS >= TT*HS)
-    float* sc_s = tile + 2 * HS * KS;                      // [RW][SCS]
-    uint64_t* exp_tab = reinterpret_cast<uint64_t*>(sc_s + (size_t)tb * p.kv_mul * SCS);
+    float* q4 = pff;                                       // [8][HS] (pair A row0, row1, pair B row0, row1)
+    float* tile = q4 + (PFF_ROWS / 4) * Q4S;               // [HS][KS] transposed K tile / [2][VT][HS] V tiles
+    float* sc2 = tile + TILE_F;                            // [pairs][SCS] (score row0, score row1) pairs
     const int tid = threadIdx.x, g = blockIdx.y;
     const int ntile = (p.n + tb - 1) / tb;
     const int tix = ntile - 1 - (int)blockIdx.x;           // heavy tiles first
     const int tok0 = tix * tb;
     const int RW = tb * p.kv_mul;
-    const int r = tid >> 3, j8 = tid & 7;
-    const int tok_l = r / p.kv_mul, h_l = r - tok_l * p.kv_mul;
-    const int tok = tok0 + tok_l;
-    const bool valid = r < RW && tok < p.n;
-    const int my_T = valid ? p.pos + tok + 1 : 0;
+    uint64_t* exp_tab = reinterpret_cast<uint64_t*>(sc2 + (size_t)2 * ((RW + 1) / 2) * SCS);
+    const int rq = tid >> 5, lane = tid & 31;              // row quad (= warp), lane
+    const int jq = lane & 15, rp = 2 * rq + (lane >> 4);   // softmax / a*v roles: lane j of 16 of row pair rp
     const int cta_T = min(p.pos + p.n, p.pos + tok0 + tb);
     const uint64_t nz2 = pf2_dup(p.neg_zero);
+    auto row_T = [&](int r) { const int tk = tok0 + r / p.kv_mul; return (r < RW && tk < p.n) ? p.pos + tk + 1 : 0; };
     if (tid < 32) exp_tab[tid] = kExp2fTab[tid];
-    {   // q rows as (q, q) pairs
-        const float* qr = p.q + (size_t)(valid ? tok : 0) * p.att_dim + (size_t)(g * p.kv_mul + (valid ? h_l : 0)) * HS;
-        for (int c = j8; c < HS / 4; c += 8) {
-            const float4 v = valid ? *reinterpret_cast<const float4*>(qr + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-            float4* d = reinterpret_cast<float4*>(q2 + (size_t)r * Q2S + 8 * c);
-            d[0] = make_float4(v.x, v.x, v.y, v.y); d[1] = make_float4(v.z, v.z, v.w, v.w);
+    {   // q of the quad, interleaved (A0, A1, B0, B1) per d; lanes cover the d chunks
+        float4 qr[4];
+        for (int c = lane; c < NQ; c += 32) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const int r = 4 * rq + e, tl_ = r / p.kv_mul, h = r - tl_ * p.kv_mul, tk = tok0 + tl_;
+                qr[e] = (r < RW && tk < p.n) ? *reinterpret_cast<const float4*>(p.q + (size_t)tk * p.att_dim + (size_t)(g * p.kv_mul + h) * HS + 4 * c)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            float4* d = reinterpret_cast<float4*>(q4 + (size_t)rq * Q4S + 16 * c);
+            d[0] = make_float4(qr[0].x, qr[1].x, qr[2].x, qr[3].x); d[1] = make_float4(qr[0].y, qr[1].y, qr[2].y, qr[3].y);
+            d[2] = make_float4(qr[0].z, qr[1].z, qr[2].z, qr[3].z); d[3] = make_float4(qr[0].w, qr[1].w, qr[2].w, qr[3].w);
         }
     }
     // ---- scores ------------------------------------------------------------------------------------------------------
+    const int Tq = max(max(row_T(4 * rq), row_T(4 * rq + 1)), max(row_T(4 * rq + 2), row_T(4 * rq + 3)));   // longest row of the quad
     const int ntk = (cta_T + TT - 1) / TT;
-    float4 kreg[KPT];
-    auto load_k = [&](int tl) {   // element e: position j = e % TT (consecutive lanes: conflict-free transposing stores), chunk c = e / TT
-#pragma unroll
-        for (int u = 0; u < KPT; u++) {
-            const int e = tid + u * PFF_THREADS, j = e % TT, c = e / TT, t = tl * TT + j;
-            kreg[u] = t < cta_T ? *reinterpret_cast<const float4*>(p.kcache + (size_t)t * p.kv_dim + (size_t)g * HS + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+    float4 kreg[KPF];
+    auto k_src = [&](int tl, int u) -> float4 {   // element e: position j = e % TT (consecutive lanes: conflict-free transposing stores), chunk c = e / TT
+        const int e = tid + u * PFF_THREADS, j = e % TT, c = e / TT, t = tl * TT + j;
+        return t < cta_T ? *reinterpret_cast<const float4*>(p.kcache + (size_t)t * p.kv_dim + (size_t)g * HS + 4 * c) : make_float4(0.f, 0.f, 0.f, 0.f);
     };
-    auto store_k = [&](int b) {
-        float* kt = tile + b * HS * KS;
-#pragma unroll
-        for (int u = 0; u < KPT; u++) {
-            const int e = tid + u * PFF_THREADS, j = e % TT, c = e / TT;
-            kt[(4 * c + 0) * KS + j] = kreg[u].x; kt[(4 * c + 1) * KS + j] = kreg[u].y;
-            kt[(4 * c + 2) * KS + j] = kreg[u].z; kt[(4 * c + 3) * KS + j] = kreg[u].w;
-        }
+    auto k_put = [&](int u, const float4 v) {
+        const int e = tid + u * PFF_THREADS, j = e % TT, c = e / TT;
+        tile[(4 * c + 0) * KS + j] = v.x; tile[(4 * c + 1) * KS + j] = v.y; tile[(4 * c + 2) * KS + j] = v.z; tile[(4 * c + 3) * KS + j] = v.w;
     };
-    float mx = -INFINITY;
-    float* srow = sc_s + (size_t)(r < RW ? r : 0) * SCS;
-    load_k(0);
+#pragma unroll
+    for (int u = 0; u < KPF; u++) kreg[u] = k_src(0, u);
+    float mxr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int tl = 0; tl < ntk; tl++) {
-        store_k(tl & 1);
-        __syncthreads();                                    // tile tl visible; everybody finished tile tl-1 (the other buffer)
-        if (tl + 1 < ntk) load_k(tl + 1);                   // in flight under this tile's arithmetic
-        const int t0 = tl * TT + 4 * j8;
-        if (t0 < my_T) {
-            const float* kt = tile + (tl & 1) * HS * KS + 4 * j8;
-            const float* qq = q2 + (size_t)r * Q2S;
-            uint64_t a01 = 0ull, a23 = 0ull;               // chains of positions (t0, t0+1) and (t0+2, t0+3), ascending d
-#pragma unroll 8
-            for (int d = 0; d < HS; d += 2) {
-                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(qq + 2 * d);          // (q_d, q_d), (q_d+1, q_d+1)
-                const ulonglong2 k0 = *reinterpret_cast<const ulonglong2*>(kt + d * KS);
-                const ulonglong2 k1 = *reinterpret_cast<const ulonglong2*>(kt + (d + 1) * KS);
-                a01 = pf2_add(a01, pf2_mul(q.x, k0.x, nz2)); a23 = pf2_add(a23, pf2_mul(q.x, k0.y, nz2));
-                a01 = pf2_add(a01, pf2_mul(q.y, k1.x, nz2)); a23 = pf2_add(a23, pf2_mul(q.y, k1.y, nz2));
-            }
-            float sv[4];
-            pf2_unpack(a01, sv[0], sv[1]); pf2_unpack(a23, sv[2], sv[3]);
+        __syncthreads();                                    // everybody finished the previous tile (and q4 is written)
 #pragma unroll
-            for (int u = 0; u < 4; u++) {
-                if (t0 + u < my_T) {
-                    float score = __fdiv_rn(sv[u], p.sqrt_hs);
-                    if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
-                        score = __fdiv_rn(score, 50.0f);
-                        score = (float)tanh((double)score);
-                        score = __fmul_rn(score, 50.0f);
-                        score = __fadd_rn(score, (p.mask_base - (uint32_t)(t0 + u) <= 4096u) ? 0.0f : -2.3819763e38f);
+        for (int u = 0; u < KPF; u++) k_put(u, kreg[u]);
+#pragma unroll
+        for (int u = KPF; u < KE; u++) k_put(u, k_src(tl, u));
+        __syncthreads();
+        if (tl + 1 < ntk) {                                 // in flight under this tile's arithmetic
+#pragma unroll
+            for (int u = 0; u < KPF; u++) kreg[u] = k_src(tl + 1, u);
+        }
+        const int t0 = tl * TT + 4 * lane;
+        if (t0 < Tq) {
+            const float* kt = tile + 4 * lane;
+            const float* qq = q4 + (size_t)rq * Q4S;
+            uint64_t acc[2][4];                             // [pair][position]: (row0, row1) chains, ascending d
+#pragma unroll
+            for (int u = 0; u < 4; u++) acc[0][u] = acc[1][u] = 0ull;
+#pragma unroll 8
+            for (int d = 0; d < HS; d++) {
+                const ulonglong2 q = *reinterpret_cast<const ulonglong2*>(qq + 4 * d);        // (A0, A1), (B0, B1)
+                const float4 kk = *reinterpret_cast<const float4*>(kt + d * KS);
+                acc[0][0] = pf2_add(acc[0][0], pf2_mul(q.x, pf2_dup(kk.x), nz2)); acc[1][0] = pf2_add(acc[1][0], pf2_mul(q.y, pf2_dup(kk.x), nz2));
+                acc[0][1] = pf2_add(acc[0][1], pf2_mul(q.x, pf2_dup(kk.y), nz2)); acc[1][1] = pf2_add(acc[1][1], pf2_mul(q.y, pf2_dup(kk.y), nz2));
+                acc[0][2] = pf2_add(acc[0][2], pf2_mul(q.x, pf2_dup(kk.z), nz2)); acc[1][2] = pf2_add(acc[1][2], pf2_mul(q.y, pf2_dup(kk.z), nz2));
+                acc[0][3] = pf2_add(acc[0][3], pf2_mul(q.x, pf2_dup(kk.w), nz2)); acc[1][3] = pf2_add(acc[1][3], pf2_mul(q.y, pf2_dup(kk.w), nz2));
+            }
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const int pr_ = 2 * rq + s;
+                if (2 * pr_ >= RW) continue;
+                const int T0 = row_T(2 * pr_), T1 = row_T(2 * pr_ + 1), Tpp = max(T0, T1);
+                float* srow_w = sc2 + (size_t)pr_ * SCS * 2;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    float sv[2];
+                    pf2_unpack(acc[s][u], sv[0], sv[1]);
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        float score = __fdiv_rn(sv[e], p.sqrt_hs);
+                        if (p.gemma) {   // soft-cap 50*tanh(s/50) in f64, window mask on every layer (:518-526)
+                            score = __fdiv_rn(score, 50.0f);
+                            score = (float)tanh((double)score);
+                            score = __fmul_rn(score, 50.0f);
+                            score = __fadd_rn(score, (p.mask_base - (uint32_t)(t0 + u) <= 4096u) ? 0.0f : -2.3819763e38f);
+                        }
+                        sv[e] = score;
                     }
-                    srow[t0 + u] = score;
-                    mx = fmaxf(mx, score);
+                    if (t0 + u < T0) mxr[2 * s] = fmaxf(mxr[2 * s], sv[0]);
+                    if (t0 + u < T1) mxr[2 * s + 1] = fmaxf(mxr[2 * s + 1], sv[1]);
+                    if (t0 + u < Tpp) *reinterpret_cast<float2*>(srow_w + 2 * (t0 + u)) = make_float2(sv[0], sv[1]);
                 }
             }
         }
     }
-    // ---- softmax, row-local (the 8 lanes of a row are neighbours in one warp) -------------------------------------------
+    // ---- softmax, warp-local: lanes 0..15 of the warp take the quad's first pair, lanes 16..31 the second --------------------
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int e = 0; e < 4; e++) mxr[e] = fmaxf(mxr[e], __shfl_xor_sync(0xffffffffu, mxr[e], o));
+    const int Tr0 = row_T(2 * rp), Tr1 = row_T(2 * rp + 1), Tp = max(Tr0, Tr1);
+    const float mx0 = (lane >> 4) ? mxr[2] : mxr[0], mx1 = (lane >> 4) ? mxr[3] : mxr[1];
+    float* srow = sc2 + (size_t)(2 * rp < RW ? rp : 0) * SCS * 2;
     __syncwarp();
-    for (int t = j8; t < my_T; t += 8) srow[t] = expf_glibc_t(__fsub_rn(srow[t], mx), exp_tab);
+    for (int t = jq; t < Tp; t += 16) {
+        float2 s = *reinterpret_cast<float2*>(srow + 2 * t);
+        s.x = t < Tr0 ? expf_glibc_t(__fsub_rn(s.x, mx0), exp_tab) : 0.0f;
+        s.y = t < Tr1 ? expf_glibc_t(__fsub_rn(s.y, mx1), exp_tab) : 0.0f;
+        *reinterpret_cast<float2*>(srow + 2 * t) = s;
+    }
     __syncwarp();
-    float sum = 0.0f;
-    if (j8 == 0 && my_T > 0) sum = serial_sum_f32(srow, my_T);   // ascending t, one dependent add per element (src/functional.rs:131-134)
-    sum = __shfl_sync(0xffffffffu, sum, (tid & 31) & ~7);
-    for (int t = j8; t < my_T; t += 8) srow[t] = __fdiv_rn(srow[t], sum);
+    float sum0 = 0.0f, sum1 = 0.0f;
+    if (jq == 0 && Tp > 0) {   // ascending t, one dependent add per element and row (src/functional.rs:131-134); entries beyond a row's length are +0.0
+        const float4* s4 = reinterpret_cast<const float4*>(srow);   // (t: row0, row1, t+1: row0, row1)
+        int t = 0;
+        float4 a = s4[0], b = Tp > 2 ? s4[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (; t + 4 < Tp; t += 4) {                        // two float4 (four positions) per trip, the next two already loaded
+            const float4 a1 = s4[t / 2 + 2], b1 = t + 6 < Tp ? s4[t / 2 + 3] : make_float4(0.f, 0.f, 0.f, 0.f);
+            sum0 = __fadd_rn(sum0, a.x); sum1 = __fadd_rn(sum1, a.y); sum0 = __fadd_rn(sum0, a.z); sum1 = __fadd_rn(sum1, a.w);
+            sum0 = __fadd_rn(sum0, b.x); sum1 = __fadd_rn(sum1, b.y); sum0 = __fadd_rn(sum0, b.z); sum1 = __fadd_rn(sum1, b.w);
+            a = a1; b = b1;
+        }
+        // tail: up to four positions left in a, b; only those below Tp count (the rest of the buffer is not this step's data)
+        const float tv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            if (t + k < Tp) { sum0 = __fadd_rn(sum0, tv[2 * k]); sum1 = __fadd_rn(sum1, tv[2 * k + 1]); }
+    }
+    sum0 = __shfl_sync(0xffffffffu, sum0, lane & 16); sum1 = __shfl_sync(0xffffffffu, sum1, lane & 16);
+    for (int t = jq; t < Tp; t += 16) {
+        float2 s = *reinterpret_cast<float2*>(srow + 2 * t);
+        s.x = t < Tr0 ? __fdiv_rn(s.x, sum0) : 0.0f;
+        s.y = t < Tr1 ? __fdiv_rn(s.y, sum1) : 0.0f;
+        *reinterpret_cast<float2*>(srow + 2 * t) = s;
+    }
     __syncthreads();                                        // all K-tile reads done: the tile buffers now carry V
     // ---- a*v --------------------------------------------------------------------------------------------------------------
+    const int nvt = (cta_T + VT - 1) / VT;
     auto stage_v = [&](int tl) {
-        float* vb = tile + (tl & 1) * TT * HS;
-        for (int e = tid; e < TT * (HS / 4); e += PFF_THREADS) {
-            const int j = e / (HS / 4), c = e - j * (HS / 4), t = tl * TT + j;
+        float* vb = tile + (tl & 1) * VT * HS;
+        for (int e = tid; e < VT * NQ; e += PFF_THREADS) {
+            const int j = e / NQ, c = e - j * NQ, t = tl * VT + j;
             if (t < cta_T) cp_async16(vb + j * HS + 4 * c, p.vcache + (size_t)t * p.kv_dim + (size_t)g * HS + 4 * c);
         }
         cp_async_commit();
     };
-    uint64_t acc[VC][2];
+    uint64_t av[NQT][4];
 #pragma unroll
-    for (int c = 0; c < VC; c++) acc[c][0] = acc[c][1] = 0ull;
+    for (int i = 0; i < NQT; i++) av[i][0] = av[i][1] = av[i][2] = av[i][3] = 0ull;
     stage_v(0);
-    for (int tl = 0; tl < ntk; tl++) {
-        if (tl + 1 < ntk) stage_v(tl + 1); else cp_async_commit();
+    for (int tl = 0; tl < nvt; tl++) {
+        if (tl + 1 < nvt) stage_v(tl + 1); else cp_async_commit();
         cp_async_wait<1>();
         __syncthreads();
-        const float* vb = tile + (tl & 1) * TT * HS + 4 * j8;   // lane j owns float4 chunks j, j+8, ... of every row
-        const int rows = min(TT, my_T - tl * TT);
-        const float* pr = srow + tl * TT;
-        // one multiply and one dependent add per position, ascending t (:533-542); probabilities fetched four at a time
-        auto step = [&](int j, float a) {
-            const uint64_t a2 = pf2_dup(a);
+        const float* vb = tile + (tl & 1) * VT * HS;
+        const int rows = min(VT, Tp - tl * VT);
+        const float* pr = srow + 2 * tl * VT;
+        // one multiply and one dependent add per position and dim, ascending t (:533-542), both rows of the pair per instruction
+        auto step = [&](int j, uint64_t pp) {
 #pragma unroll
-            for (int c = 0; c < VC; c++) {
-                const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(vb + j * HS + 32 * c);
-                acc[c][0] = pf2_add(acc[c][0], pf2_mul(a2, v.x, nz2));
-                acc[c][1] = pf2_add(acc[c][1], pf2_mul(a2, v.y, nz2));
+            for (int i = 0; i < NQT; i++) {
+                const int c = jq + 16 * i;
+                if (NQ % 16 == 0 || c < NQ) {
+                    const float4 v = *reinterpret_cast<const float4*>(vb + j * HS + 4 * c);
+                    av[i][0] = pf2_add(av[i][0], pf2_mul(pp, pf2_dup(v.x), nz2)); av[i][1] = pf2_add(av[i][1], pf2_mul(pp, pf2_dup(v.y), nz2));
+                    av[i][2] = pf2_add(av[i][2], pf2_mul(pp, pf2_dup(v.z), nz2)); av[i][3] = pf2_add(av[i][3], pf2_mul(pp, pf2_dup(v.w), nz2));
+                }
             }
         };
         int j = 0;
-        for (; j + 4 <= rows; j += 4) {
-            const float4 a4 = *reinterpret_cast<const float4*>(pr + j);
-            step(j, a4.x); step(j + 1, a4.y); step(j + 2, a4.z); step(j + 3, a4.w);
+        for (; j + 2 <= rows; j += 2) {
+            const ulonglong2 pp = *reinterpret_cast<const ulonglong2*>(pr + 2 * j);
+            step(j, pp.x); step(j + 1, pp.y);
         }
-        for (; j < rows; j++) step(j, pr[j]);
+        if (j < rows) step(j, *reinterpret_cast<const uint64_t*>(pr + 2 * j));
         __syncthreads();                                    // the buffer staged two tiles from now is this one
     }
     cp_async_wait<0>();
-    if (valid) {
-        float* o = p.out + (size_t)tok * p.att_dim + (size_t)(g * p.kv_mul + h_l) * HS + 4 * j8;
 #pragma unroll
-        for (int c = 0; c < VC; c++) {
-            float4 w;
-            pf2_unpack(acc[c][0], w.x, w.y); pf2_unpack(acc[c][1], w.z, w.w);
-            *reinterpret_cast<float4*>(o + 32 * c) = w;
+    for (int e = 0; e < 2; e++) {
+        const int r = 2 * rp + e, tl_ = r / p.kv_mul, h = r - tl_ * p.kv_mul, tk = tok0 + tl_;
+        if (!(r < RW && tk < p.n)) continue;
+        float* o = p.out + (size_t)tk * p.att_dim + (size_t)(g * p.kv_mul + h) * HS;
+#pragma unroll
+        for (int i = 0; i < NQT; i++) {
+            const int c = jq + 16 * i;
+            if (NQ % 16 == 0 || c < NQ) {
+                float lo[4], hi[4];
+#pragma unroll
+                for (int k = 0; k < 4; k++) pf2_unpack(av[i][k], lo[k], hi[k]);
+                *reinterpret_cast<float4*>(o + 4 * c) = e == 0 ? make_float4(lo[0], lo[1], lo[2], lo[3]) : make_float4(hi[0], hi[1], hi[2], hi[3]);
+            }
         }
     }
 }
