@@ -123,8 +123,8 @@ def cpu_reference_run(buf, a, pos0, steps, warmup, prompt, keep_logits=0, kshard
 
 def load_gemv_traffic(model, quant):
     """dram__bytes_read.sum + dram__bytes_write.sum per gemv_kernel launch (average over a step's launches) from the
-    committed `ncu --set full` capture of this workload (profiles/r1_gemv_traffic.json); None for workloads not captured."""
-    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r1_gemv_traffic.json")
+    committed `ncu --set full` capture of this workload (profiles/r2_gemv_traffic.json); None for workloads not captured."""
+    p = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_gemv_traffic.json")
     try:
         d = json.load(open(p))
     except OSError:
@@ -132,7 +132,7 @@ def load_gemv_traffic(model, quant):
     w = d.get("workload", {})
     if w.get("model") != model or w.get("quant") != quant:
         return None, "no ncu --set full capture for this workload"
-    return d["traffic_bytes_per_launch_avg"], "profiles/r1_gemv_traffic.json (ncu --set full, per-launch average)"
+    return d["traffic_bytes_per_launch_avg"], "profiles/r2_gemv_traffic.json (ncu --set full, per-launch average)"
 
 
 def main():

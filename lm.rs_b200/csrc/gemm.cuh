@@ -9,8 +9,8 @@
 //   warp 0      TMA producer   A tile [128 tok][128 B], B tile [128 rows][128 B], 128B-swizzled, 4-stage mbarrier ring
 //   warp 1      MMA issuer     4 x tcgen05.mma.cta_group::1.kind::i8 (M128 N128 K32) per group into one of two TMEM
 //                              accumulator buffers; tcgen05.commit frees the smem stage and publishes the buffer
-//   warps 2..9  epilogue       tcgen05.ld 32x32b (thread = token row x 64 columns), s32 -> f32, * ws[col][g] * xs[row][g], added
-//                              into 64 f32 register accumulators in the reference's order -> results are bit-identical
+//   warps 2..17 epilogue       tcgen05.ld 32x32b (thread = token row x 16/32 columns), s32 -> f32, * ws[col][g] * xs[row][g], added
+//                              into f32 register accumulators in the reference's order -> results are bit-identical
 //                              to the CPU path; double-buffered TMEM lets group g+1's MMAs run under group g's epilogue.
 // The CUDA-core mini-epilogue runs after EVERY group (the scale is rank-1 per K group), so it bounds the kernel: it is written
 // with packed f32x2 arithmetic and an exact integer->float conversion without I2F (2.5 issue slots per element per group
@@ -25,7 +25,10 @@
 namespace lmrs {
 
 constexpr int GEMM_M = 128, GEMM_K = 128, GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 320;   // TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quadrant)
+// epilogue warps: four per TMEM lane quadrant for the 128-column tiles (the per-group epilogue is a latency-bound instruction
+// stream: 8 -> 16 warps measured 86 -> 68 us on the fused gate/up GEMM), two for the 64-column tiles (16 warps measured slower)
+template <int BNM> __host__ __device__ constexpr int gemm_epi_warps() { return BNM == 128 ? 16 : 8; }
+template <int BNM> __host__ __device__ constexpr int gemm_threads() { return 64 + 32 * gemm_epi_warps<BNM>(); }   // TMA warp, MMA warp, epilogue warps
 constexpr int GEMM_TILE_BYTES = GEMM_M * GEMM_K;   // 16 KB A tile (128 token rows x one quantization group)
 // BNM = accumulator columns of one MMA (output rows of w per CTA tile): 128 or 64.  Shared memory: operand ring, the tile's
 // weight scales for ALL groups transposed to [group][column], barriers.
@@ -94,6 +97,19 @@ LMRS_DEVINL void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "memory");
 }
 
+LMRS_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+template <int N> LMRS_DEVINL void tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
+    if constexpr (N == 32) tmem_ld32(taddr, v); else tmem_ld16(taddr, v);
+}
+
 // ---- packed f32x2 arithmetic (Blackwell FADD2 / FMUL2: two IEEE round-to-nearest results per issue slot) ----------------
 LMRS_DEVINL uint64_t f2_pack(float a, float b) { uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
 LMRS_DEVINL void f2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
@@ -113,12 +129,13 @@ LMRS_DEVINL uint64_t f2_mul_sep(uint64_t a, uint64_t b, uint64_t neg_zero2) {
 constexpr int GEMM_MAGIC_I = 0x4B400000;
 constexpr float GEMM_MAGIC_F = 12582912.0f;
 
-// acc[0..15] (pairs) += ((v as f32) * ws) * xs for 32 consecutive accumulator columns: src/functional.rs:207's term and the
+// acc[0 .. N/2) (pairs) += ((v as f32) * ws) * xs for N consecutive accumulator columns: src/functional.rs:207's term and the
 // ascending-group f32 accumulation, two columns per instruction
-LMRS_DEVINL void gemm_epi_chunk(uint64_t* acc, const uint32_t (&v)[32], const float* ws32, uint64_t xs2, uint64_t neg_magic2, uint64_t nz2) {
+template <int N>
+LMRS_DEVINL void gemm_epi_chunk(uint64_t* acc, const uint32_t (&v)[N], const float* ws32, uint64_t xs2, uint64_t neg_magic2, uint64_t nz2) {
     const float4* w4 = reinterpret_cast<const float4*>(ws32);
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
+    for (int j = 0; j < N / 4; j++) {
         const float4 w = w4[j];   // the same address for every lane: one broadcast LDS.128
         const uint64_t f0 = f2_add(f2_pack(__int_as_float((int)v[4 * j] + GEMM_MAGIC_I), __int_as_float((int)v[4 * j + 1] + GEMM_MAGIC_I)), neg_magic2);
         const uint64_t f1 = f2_add(f2_pack(__int_as_float((int)v[4 * j + 2] + GEMM_MAGIC_I), __int_as_float((int)v[4 * j + 3] + GEMM_MAGIC_I)), neg_magic2);
@@ -131,10 +148,11 @@ LMRS_DEVINL void gemm_epi_chunk(uint64_t* acc, const uint32_t (&v)[32], const fl
 // w1 (gate), columns 64..127 the same rows of w3 (up); the epilogue writes act(gate) * up (src/transformer.rs:607-624)
 // for 64 hidden columns, so gate/up never travel through HBM.
 template <int BNM, bool GLU>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+__global__ void __launch_bounds__(gemm_threads<BNM>(), 1)
 gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const __grid_constant__ CUtensorMap tm_b2,
                const GemmParams p) {
     static_assert(BNM == 128 || BNM == 64, "tile width");
+    constexpr int GEMM_EPI_WARPS = gemm_epi_warps<BNM>();
     static_assert(!GLU || BNM == 128, "GLU tiles pair 64 gate with 64 up columns");
     constexpr int B_TILE_BYTES = BNM * GEMM_K;
     constexpr int STAGE_BYTES = GEMM_TILE_BYTES + B_TILE_BYTES;
@@ -158,7 +176,7 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < GEMM_STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], 8); }
+        for (int b = 0; b < 2; b++) { mbar_init(&tfull[b], 1); mbar_init(&tempty[b], GEMM_EPI_WARPS); }
         fence_barrier_init();
     }
     if (warp == 1) {   // TMEM: two BNM-column s32 accumulators
@@ -203,29 +221,32 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 umma_commit(&tfull[b]);                              // accumulator complete
             }
         }
-    } else {   // ---- epilogue: warps 2..9, TMEM lane quadrant = warp % 4, thread = one token row x EC columns ----
-        constexpr int EC = GLU ? 64 : BNM / 2;                       // accumulator columns per epilogue thread
-        constexpr int NCH = EC / 32;                                 // 32-column TMEM loads per group
+    } else {   // ---- epilogue: TMEM lane quadrant = warp % 4, column slice = (warp - 2) / 4; thread = one token row x CW columns per chunk ----
+        constexpr int NSUB = GEMM_EPI_WARPS / 4;                     // column slices
+        constexpr int NCH = GLU ? 2 : 1;                             // chunks per thread and group (GLU: gate slice + matching up slice)
+        constexpr int CW = (GLU ? 64 : BNM) / NSUB;                  // columns per chunk: 32 (128-wide tiles) or 16
+        constexpr int EPI_THREADS = 32 * GEMM_EPI_WARPS;
+        static_assert(CW == 16 || CW == 32, "TMEM load shapes x16 / x32");
         const int quad = warp & 3;
-        const int chalf = (warp - 2) >> 2;
+        const int csub = (warp - 2) >> 2;
         const int row = quad * 32 + lane;
-        const int et = threadIdx.x - 64;                             // 0..255 among the epilogue threads
+        const int et = threadIdx.x - 64;                             // index among the epilogue threads
         const bool row_ok = m0 + row < p.T;
-        // chunk c of this thread covers accumulator columns col_of(c) .. +31
-        //   plain: the thread's half of the tile; GLU: 32 gate columns (c = 0) and the matching 32 up columns (c = 1)
-        auto col_of = [&](int c) { return GLU ? c * 64 + chalf * 32 : chalf * EC + c * 32; };
+        auto col_of = [&](int c) { return (GLU ? c * 64 : 0) + csub * CW; };   // first accumulator column of chunk c
         // the tile's weight scales for every group, transposed to [g][column] (file layout is [row of w][g])
-        for (int e = et; e < G * BNM; e += 256) {
+        for (int e = et; e < G * BNM; e += EPI_THREADS) {
             const int c = e / G, g = e - c * G;
             float v;
             if (GLU) v = c < 64 ? p.ws[(size_t)(n0 + c) * G + g] : p.ws2[(size_t)(n0 + c - 64) * G + g];
             else v = (n0 + c < p.o) ? p.ws[(size_t)(n0 + c) * G + g] : 0.0f;
             ws_t[g * BNM + c] = v;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        uint64_t acc[EC / 2];
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_THREADS) : "memory");
+        uint64_t acc[NCH][CW / 2];
 #pragma unroll
-        for (int j = 0; j < EC / 2; j++) acc[j] = 0ull;               // (+0.0f, +0.0f)
+        for (int c = 0; c < NCH; c++)
+#pragma unroll
+            for (int j = 0; j < CW / 2; j++) acc[c][j] = 0ull;       // (+0.0f, +0.0f)
         const uint64_t neg_magic2 = f2_pack(-GEMM_MAGIC_F, -GEMM_MAGIC_F), nz2 = f2_pack(p.neg_zero, p.neg_zero);
         const float* xs_row = p.xs + (size_t)(row_ok ? m0 + row : 0) * G;
         float xs_next = row_ok ? xs_row[0] : 0.0f;
@@ -238,25 +259,25 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             // all of this thread's accumulator words of the group are requested back to back; once they sit in registers the
             // TMEM buffer goes back to the MMA warp BEFORE the arithmetic, so group g+2's MMAs run under group g's epilogue
-            uint32_t v[NCH][32];
+            uint32_t v[NCH][CW];
 #pragma unroll
             for (int c = 0; c < NCH; c++)
-                tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * BNM + col_of(c)), v[c]);
+                tmem_ld<CW>(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(b * BNM + col_of(c)), v[c]);
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty[b]);
 #pragma unroll
-            for (int c = 0; c < NCH; c++) gemm_epi_chunk(acc + c * 16, v[c], ws_t + g * BNM + col_of(c), xs2, neg_magic2, nz2);
+            for (int c = 0; c < NCH; c++) gemm_epi_chunk<CW>(acc[c], v[c], ws_t + g * BNM + col_of(c), xs2, neg_magic2, nz2);
         }
         if (row_ok) {
             if constexpr (GLU) {
-                float4* o4 = reinterpret_cast<float4*>(p.out0 + (size_t)(m0 + row) * p.ld0 + n0 + chalf * 32);
+                float4* o4 = reinterpret_cast<float4*>(p.out0 + (size_t)(m0 + row) * p.ld0 + n0 + csub * CW);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
+                for (int j = 0; j < CW / 4; j++) {
                     float g0, g1, g2, g3, u0, u1, u2, u3;
-                    f2_unpack(acc[2 * j], g0, g1); f2_unpack(acc[2 * j + 1], g2, g3);
-                    f2_unpack(acc[16 + 2 * j], u0, u1); f2_unpack(acc[16 + 2 * j + 1], u2, u3);
+                    f2_unpack(acc[0][2 * j], g0, g1); f2_unpack(acc[0][2 * j + 1], g2, g3);
+                    f2_unpack(acc[1][2 * j], u0, u1); f2_unpack(acc[1][2 * j + 1], u2, u3);
                     o4[j] = make_float4(__fmul_rn(glu_act(p.glu_epi, g0), u0), __fmul_rn(glu_act(p.glu_epi, g1), u1),
                                         __fmul_rn(glu_act(p.glu_epi, g2), u2), __fmul_rn(glu_act(p.glu_epi, g3), u3));
                 }
@@ -265,11 +286,11 @@ gemm_q8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 if (n0 < p.c1) { dst = p.out0; ld = p.ld0; cbase = 0; }
                 else if (n0 < p.c2) { dst = p.out1; ld = p.ld1; cbase = p.c1; }
                 else { dst = p.out2; ld = p.ld2; cbase = p.c2; }
-                float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase) + chalf * EC);
+                float4* o4 = reinterpret_cast<float4*>(dst + (size_t)(m0 + row) * ld + (n0 - cbase) + csub * CW);
 #pragma unroll
-                for (int j = 0; j < EC / 4; j++) {
+                for (int j = 0; j < CW / 4; j++) {
                     float a0, a1, a2, a3;
-                    f2_unpack(acc[2 * j], a0, a1); f2_unpack(acc[2 * j + 1], a2, a3);
+                    f2_unpack(acc[0][2 * j], a0, a1); f2_unpack(acc[0][2 * j + 1], a2, a3);
                     o4[j] = make_float4(a0, a1, a2, a3);
                 }
             }

@@ -93,6 +93,7 @@ struct lmrs_b200 {
     uint8_t* pf_xq = nullptr;
     float *pf_xs = nullptr, *pf_q = nullptr, *pf_att = nullptr, *pf_wo = nullptr, *pf_g = nullptr, *pf_u = nullptr, *pf_h = nullptr, *pf_down = nullptr, *pf_scores = nullptr;
     bool use_gemm = true;
+    int pfa_quads = 4;         // fused batched-rows attention: row quads (warps) per CTA, 4 or 8 (LMRS_B200_PFA_QUADS)
     int use_pf_attn = 1;       // batched-rows attention: 1 = fused throughput kernel (prefill_attn.cuh), 2 = its two-kernel form, 0 = the per-row decode kernel
     size_t rows_cap = 0;
     StepParams* d_step = nullptr;
@@ -434,11 +435,11 @@ static int launch_gemm(lmrs_b200* m, const Mat& w, const uint8_t* xq, const floa
     if (narrow) {
         const size_t smem = gemm_smem_bytes<64>(w.n);
         CK(smem_optin(m, (const void*)gemm_q8_kernel<64, false>, smem));
-        gemm_q8_kernel<64, false><<<dim3(w.o / 64, mt), GEMM_THREADS, smem, m->stream>>>(ta, w.tmap64, w.tmap64, gp);
+        gemm_q8_kernel<64, false><<<dim3(w.o / 64, mt), gemm_threads<64>(), smem, m->stream>>>(ta, w.tmap64, w.tmap64, gp);
     } else {
         const size_t smem = gemm_smem_bytes<128>(w.n);
         CK(smem_optin(m, (const void*)gemm_q8_kernel<128, false>, smem));
-        gemm_q8_kernel<128, false><<<dim3(w.o / 128, mt), GEMM_THREADS, smem, m->stream>>>(ta, w.tmap, w.tmap, gp);
+        gemm_q8_kernel<128, false><<<dim3(w.o / 128, mt), gemm_threads<128>(), smem, m->stream>>>(ta, w.tmap, w.tmap, gp);
     }
     m->launches++;
     CK(cudaGetLastError());
@@ -452,7 +453,7 @@ static int launch_gemm_glu(lmrs_b200* m, const Mat& w1, const Mat& w3, const uin
     gp.T = T; gp.n = w1.n; gp.o = w1.o; gp.ws = w1.ds; gp.ws2 = w3.ds; gp.xs = xs; gp.out0 = h; gp.ld0 = ld; gp.glu_epi = epi; gp.neg_zero = -0.0f;
     const size_t smem = gemm_smem_bytes<128>(w1.n);
     CK(smem_optin(m, (const void*)gemm_q8_kernel<128, true>, smem));
-    gemm_q8_kernel<128, true><<<dim3(w1.o / 64, (T + GEMM_M - 1) / GEMM_M), GEMM_THREADS, smem, m->stream>>>(ta, w1.tmap64, w3.tmap64, gp);
+    gemm_q8_kernel<128, true><<<dim3(w1.o / 64, (T + GEMM_M - 1) / GEMM_M), gemm_threads<128>(), smem, m->stream>>>(ta, w1.tmap64, w3.tmap64, gp);
     m->launches++;
     CK(cudaGetLastError());
     return 0;
@@ -1022,11 +1023,18 @@ static int prefill_serial(lmrs_b200* m, size_t n, uint32_t pos) {
 template <int HS> static int launch_prefill_attn_t(lmrs_b200* m, const PrefillAttnParams& p, int n_kv_heads) {
     if (m->use_pf_attn == 1) {   // fused form: score rows in shared memory
         const int scs = prefill_fused_scs(p.pos + p.n);
-        const int tb = prefill_fused_tb(HS, p.kv_mul, p.pos + p.n);
-        const size_t smem = prefill_fused_smem(HS, tb * p.kv_mul, scs);
+        const int nqd = prefill_fused_nqd(p.kv_mul, m->pfa_quads);
+        const int tb = prefill_fused_tb(HS, nqd, p.kv_mul, p.pos + p.n);
+        const size_t smem = prefill_fused_smem(HS, nqd, tb * p.kv_mul, scs);
         if (tb > 0) {
-            CK(smem_optin(m, (const void*)prefill_attn_fused_kernel<HS>, smem));
-            prefill_attn_fused_kernel<HS><<<dim3((unsigned)((p.n + tb - 1) / tb), (unsigned)n_kv_heads), PFF_THREADS, smem, m->stream>>>(p, tb, scs);
+            const dim3 grid((unsigned)((p.n + tb - 1) / tb), (unsigned)n_kv_heads);
+            if (nqd == 4) {
+                CK(smem_optin(m, (const void*)prefill_attn_fused_kernel<HS, 4>, smem));
+                prefill_attn_fused_kernel<HS, 4><<<grid, 128, smem, m->stream>>>(p, tb, scs);
+            } else {
+                CK(smem_optin(m, (const void*)prefill_attn_fused_kernel<HS, 8>, smem));
+                prefill_attn_fused_kernel<HS, 8><<<grid, 256, smem, m->stream>>>(p, tb, scs);
+            }
             m->launches++;
             CK(cudaGetLastError());
             return 0;
@@ -1059,7 +1067,7 @@ static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
     if (!m->use_gemm || n < 8) return false;
     // attention of the batch: the fused kernel keeps whole score rows in shared memory (any context the KV cache holds for
     // the shipped shapes); the older forms stop at ATT_SC_CAP positions
-    const bool fused = m->use_pf_attn == 1 && prefill_fused_tb((int)m->args.head_size, (int)(m->args.n_heads / m->args.n_kv_heads), (int)(pos + n)) > 0;
+    const bool fused = m->use_pf_attn == 1 && prefill_fused_tb((int)m->args.head_size, prefill_fused_nqd((int)(m->args.n_heads / m->args.n_kv_heads), m->pfa_quads), (int)(m->args.n_heads / m->args.n_kv_heads), (int)(pos + n)) > 0;
     if (!fused && pos + n > (size_t)ATT_SC_CAP) return false;
     for (const Layer& Y : m->layers)
         for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
@@ -1127,7 +1135,7 @@ static int pf_begin(lmrs_b200* m, size_t n, uint32_t pos, float* rows, PfCtx& c)
     const lmrs_args_t& a = m->args;
     const int dim = a.dim, att = m->l_att_dim, hid = m->l_hidden;
     c.T = (int)n; c.pos = pos; c.rows = rows; c.delta = nullptr; c.w_post = nullptr;
-    c.fused_attn = m->use_pf_attn == 1 && prefill_fused_tb((int)a.head_size, (int)(a.n_heads / a.n_kv_heads), (int)(pos + n)) > 0;
+    c.fused_attn = m->use_pf_attn == 1 && prefill_fused_tb((int)a.head_size, prefill_fused_nqd((int)(a.n_heads / a.n_kv_heads), m->pfa_quads), (int)(a.n_heads / a.n_kv_heads), (int)(pos + n)) > 0;
     c.sc_stride = c.fused_attn ? 4 : align_up(std::min<size_t>(a.seq_len, ATT_SC_CAP), 4);   // score scratch of the unfused forms (pos + n <= ATT_SC_CAP)
     if (m->pf_cap < n) {
         for (void* p : {(void*)m->pf_xq, (void*)m->pf_xs, (void*)m->pf_q, (void*)m->pf_att, (void*)m->pf_wo, (void*)m->pf_h, (void*)m->pf_down}) cudaFree(p);
@@ -1322,6 +1330,7 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     // profiles/r2_decode_experiments.md), so it is opt-in.
     m->use_ll = env_int("LMRS_B200_LL", 0) != 0 && world == 1;
     m->use_pf_attn = env_int("LMRS_B200_PF_ATTN", 1);
+    m->pfa_quads = env_int("LMRS_B200_PFA_QUADS", 4) == 8 ? 8 : 4;
     m->l2pf = env_int("LMRS_B200_L2PF", 0);
     m->l2pf_ef = env_int("LMRS_B200_L2PF_EF", 1);
     m->l2pf_cls_mb = env_int("LMRS_B200_L2PF_CLS_MB", 24);

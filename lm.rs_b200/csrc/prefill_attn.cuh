@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(512) prefill_av_kernel(const PrefillAttnParams
 // The first build of this kernel (one row per 8-lane group, q and K re-read from shared memory for every 4 multiply-adds) was
 // bound by the shared-memory pipe, not by arithmetic (ncu: short-scoreboard stalls 5x the issue slots, a 128-bit LDS costs a
 // warp four pipe cycles whatever it broadcasts; profiles/r2_ncu_prefill_attn_raw.csv), so the work is register-tiled:
-//   scores   256 threads = 8 row quads x 32 lanes; thread (quad, lane j) owns the 4 x 4 tile of rows {two pairs} x positions
+//   scores   NQD warps = row quads x 32 lanes; thread (quad, lane j) owns the 4 x 4 tile of rows {two pairs} x positions
 //            4j..4j+3 of every 128-position K tile (K transposed to [d][position]): per d ONE 16-byte load of the two q pairs
 //            and ONE of four K values feed 8 packed multiply/add pairs = 16 ascending-d chains;
 //   softmax  warp-local (a quad's lanes are one warp; lanes 0..15 serve its first pair, 16..31 the second): max, exp(x - max)
@@ -198,20 +198,24 @@ __global__ void __launch_bounds__(512) prefill_av_kernel(const PrefillAttnParams
 //            add per position and dim, ascending t, both rows of the pair per instruction.
 // Arithmetic per chain is exactly the reference's (src/transformer.rs:507-542, src/functional.rs:122-140): results are
 // bit-identical to the decode kernels and to the two-kernel form above.  Heavy (late) token tiles are scheduled first.
-constexpr int PFF_THREADS = 256, PFF_ROWS = 32, PFF_TT = 128, PFF_KS = PFF_TT + 4, PFF_VT = 64;
+// NQD = row quads (= warps) per CTA: 8 (32 rows) or 4 (16 rows).  The causal triangle makes the late token tiles the long
+// poles of the launch (a 32-row CTA at T = 512 runs ~2x the average and as long as 3/4 of the whole kernel, ncu: SMs idle a
+// third of the time); 16-row CTAs halve the longest CTA and fit three to an SM.
+constexpr int PFF_TT = 128, PFF_KS = PFF_TT + 4, PFF_VT = 64;
 inline int prefill_fused_scs(int t_max) { return ((t_max + 3) & ~3) + 2; }   // (pairs per score row) even; + 2 de-phases neighbouring pairs
-inline size_t prefill_fused_smem(int hs, int rw, int scs) {
+inline size_t prefill_fused_smem(int hs, int nqd, int rw, int scs) {
     const size_t tile = (size_t)hs * PFF_KS > (size_t)2 * PFF_VT * hs ? (size_t)hs * PFF_KS : (size_t)2 * PFF_VT * hs;
-    return ((size_t)(PFF_ROWS / 4) * (hs * 4 + 8) + tile + (size_t)2 * ((rw + 1) / 2) * scs + 64 + 8) * 4;
+    return ((size_t)nqd * (hs * 4 + 8) + tile + (size_t)2 * ((rw + 1) / 2) * scs + 64 + 8) * 4;
 }
 constexpr size_t PFF_SMEM_MAX = 216 * 1024;
 // tokens per CTA for contexts up to t_max positions (0: the score rows of even one token do not fit)
-inline int prefill_fused_tb(int hs, int kv_mul, int t_max) {
-    if (kv_mul > PFF_ROWS) return 0;
-    int tb = PFF_ROWS / kv_mul;
-    while (tb > 1 && prefill_fused_smem(hs, tb * kv_mul, prefill_fused_scs(t_max)) > PFF_SMEM_MAX) tb--;
-    return prefill_fused_smem(hs, tb * kv_mul, prefill_fused_scs(t_max)) <= PFF_SMEM_MAX ? tb : 0;
+inline int prefill_fused_tb(int hs, int nqd, int kv_mul, int t_max) {
+    if (kv_mul > 4 * nqd) return 0;
+    int tb = 4 * nqd / kv_mul;
+    while (tb > 1 && prefill_fused_smem(hs, nqd, tb * kv_mul, prefill_fused_scs(t_max)) > PFF_SMEM_MAX) tb--;
+    return prefill_fused_smem(hs, nqd, tb * kv_mul, prefill_fused_scs(t_max)) <= PFF_SMEM_MAX ? tb : 0;
 }
+inline int prefill_fused_nqd(int kv_mul, int want) { return (want == 4 && kv_mul <= 16) ? 4 : 8; }
 
 // a separately rounded packed product (an add consumes it): fma(a, b, -0.0) with a run-time -0.0, see gemm.cuh f2_mul_sep
 LMRS_DEVINL uint64_t pf2_mul(uint64_t a, uint64_t b, uint64_t nz2) { uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(nz2)); return r; }
@@ -219,9 +223,10 @@ LMRS_DEVINL uint64_t pf2_add(uint64_t a, uint64_t b) { uint64_t r; asm("add.rn.f
 LMRS_DEVINL uint64_t pf2_dup(float a) { uint64_t r; asm("mov.b64 %0, {%1, %1};" : "=l"(r) : "f"(a)); return r; }   // (ptxas folds it into the .F32 broadcast operand form)
 LMRS_DEVINL void pf2_unpack(uint64_t v, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 
-template <int HS>
-__global__ void __launch_bounds__(PFF_THREADS, HS <= 128 ? 2 : 1) prefill_attn_fused_kernel(const PrefillAttnParams p, const int tb, const int SCS) {
+template <int HS, int NQD>
+__global__ void __launch_bounds__(32 * NQD, HS <= 128 ? (NQD == 4 ? 3 : 2) : 1) prefill_attn_fused_kernel(const PrefillAttnParams p, const int tb, const int SCS) {
     static_assert(HS % 32 == 0, "whole float4 per lane");
+    constexpr int PFF_THREADS = 32 * NQD, PFF_ROWS = 4 * NQD;
     constexpr int KS = PFF_KS, TT = PFF_TT, VT = PFF_VT;
     constexpr int NQ = HS / 4, NQT = (NQ + 15) / 16;       // float4 chunks of a K / V row; V chunks per lane
     constexpr int KE = TT * NQ / PFF_THREADS;              // float4 of a K tile staged per thread

@@ -256,7 +256,7 @@ def test_q4_prefill_uses_the_per_token_chain(gpu_lib, ref, synth):
 @pytest.mark.parametrize("env", [{"LMRS_B200_LL": "1"}, {"LMRS_B200_LL": "1", "LMRS_B200_GEMV_CFG": "0"}, {"LMRS_B200_ATT_SPLIT": "1"}, {"LMRS_B200_GRAPH": "0", "LMRS_B200_PDL": "0"},
                                  {"LMRS_B200_GRAPH": "0"}, {"LMRS_B200_GEMM": "0"}, {"LMRS_B200_GEMV_CFG": "1"}, {"LMRS_B200_GEMV_CFG": "4"},
                                  {"LMRS_B200_ATT_CLUSTER": "0"}, {"LMRS_B200_ATT_CLUSTER": "4"}, {"LMRS_B200_ATT_GROUPS": "1"},
-                                 {"LMRS_B200_PF_ATTN": "2"}, {"LMRS_B200_PF_ATTN": "0"}, {"LMRS_B200_L2PF": "1"}, {"LMRS_B200_L2PF": "2"}, {"LMRS_B200_GEMM_BN": "128"},
+                                 {"LMRS_B200_PF_ATTN": "2"}, {"LMRS_B200_PF_ATTN": "0"}, {"LMRS_B200_PFA_QUADS": "8"}, {"LMRS_B200_L2PF": "1"}, {"LMRS_B200_L2PF": "2"}, {"LMRS_B200_GEMM_BN": "128"},
                                  {"LMRS_B200_GEMM_BN": "64"}])
 def test_alternative_execution_modes_stay_bit_exact(env):
     """fence-free LL exchange between co-resident kernels instead of kernel-boundary hand-overs (16- and 8-warp rings) /
