@@ -829,6 +829,15 @@ __global__ void __launch_bounds__(WARPS * 32, WARPS <= 8 ? LMRS_GEMV_MINB : 1) l
         // this kernel's CTAs were launched early and now idle until the previous kernel completes: one otherwise unused
         // thread asks the L2 to fetch weights that later kernels of the step will stream (after this CTA's own requests)
         if (p.l2pf_bytes && threadIdx.x == (WARPS - 1) * 32 + 1) l2_prefetch_slice(p.l2pf_ptr, p.l2pf_bytes, p.l2pf_chunk);
+        // the norm weights are read once per token and have long left the L2 when their block comes round again (1.3 GB of
+        // weights stream through it per step): ask for them now, the prologue's loads after the wait then hit the L2
+        if constexpr (PRO == PRO_NORM) {
+            const int off = threadIdx.x * 32;   // floats: one 128-byte line per thread
+            if (off < p.n) {
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.w_norm + off));
+                if (p.w_post) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.w_post + off));
+            }
+        }
         // N-GPU mode, consumer of an exchanged vector: everything this kernel reads from its predecessor arrives as
         // (value, sequence) words it polls anyway, so it does not wait for the predecessor's COMPLETION (which includes the
         // NVLink round trip of that kernel's stores into the peers) -- only for the words themselves (gemv_prologue)

@@ -431,7 +431,8 @@ static int launch_gemm(lmrs_b200* m, const Mat& w, const uint8_t* xq, const floa
     gp.T = T; gp.n = w.n; gp.o = w.o; gp.ws = w.ds; gp.xs = xs; gp.neg_zero = -0.0f;
     const int mt = (T + GEMM_M - 1) / GEMM_M;
     static const int force_bn = env_int("LMRS_B200_GEMM_BN", 0);   // developer knob
-    const bool narrow = force_bn ? force_bn == 64 : (w.o / 128) * mt < m->sms;
+    // 64-column tiles also where the q | k | v output segments end on a 64- but not a 128-column boundary (KV heads of 64 on 8 GPUs)
+    const bool narrow = (gp.c1 % 128) || (gp.c2 % 128) || (force_bn ? force_bn == 64 : (w.o / 128) * mt < m->sms);
     if (narrow) {
         const size_t smem = gemm_smem_bytes<64>(w.n);
         CK(smem_optin(m, (const void*)gemm_q8_kernel<64, false>, smem));
@@ -641,6 +642,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     // ---- upload in file layout to a staging buffer, then repack every matrix into the BP16 arena ------------------
     uint8_t* d_stage = nullptr;
     CK(cudaMalloc(&d_stage, cur));
+    m->d_dense = d_stage;   // owned by the handle from here on: an error return below is cleaned up by lmrs_b200_destroy
     for (const Piece& pc : pieces) {
         if (pc.rows <= 1) CK(cudaMemcpy(d_stage + pc.dst, pc.src, pc.bytes, cudaMemcpyHostToDevice));
         else CK(cudaMemcpy2D(d_stage + pc.dst, pc.dst_stride, pc.src, pc.src_stride, pc.bytes, pc.rows, cudaMemcpyHostToDevice));
@@ -665,7 +667,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     size_t cls_pk = emb_pk;
     if (a.model_type == 2) cls_pk = pk(p_cls);
     else if (W > 1) {   // tied classifier: this rank's vocab rows are a block-aligned sub-range of the packed table
-        if (((size_t)m->vocab_off * (dim / GS)) % SG) { cudaFree(d_stage); return fail("vocab shard is not BP16 block aligned"); }
+        if (((size_t)m->vocab_off * (dim / GS)) % SG) return fail("vocab shard is not BP16 block aligned");
         cls_pk = emb_pk + ((size_t)m->vocab_off * (dim / GS) / SG) * (a.q_type == 1 ? blk_bytes<1>() : blk_bytes<2>());
     }
     const size_t rms_final_pk = pv(rms_final);
@@ -676,8 +678,7 @@ static int build_model(lmrs_b200* m, const uint8_t* file, size_t len, size_t* en
     for (const VecJob& j : vjobs) CK(cudaMemcpy(m->d_arena + j.dst, d_stage + j.src, dim * 4, cudaMemcpyDeviceToDevice));
     CK(cudaDeviceSynchronize());
     m->use_gemm = a.q_type == 1 && env_int("LMRS_B200_GEMM", 1) != 0 && (W == 1 || m->use_peer);   // N-GPU: needs the peer exchange
-    if (m->use_gemm) m->d_dense = d_stage;   // the file-layout copy doubles as the GEMM's B operand
-    else cudaFree(d_stage);
+    if (!m->use_gemm) { cudaFree(d_stage); m->d_dense = nullptr; }   // otherwise the file-layout copy doubles as the GEMM's B operand
     int tmap_err = 0;
     auto mkd = [&](Mat& x, const MatPlan& pl) {   // dense views + TMA descriptor
         if (!m->use_gemm) return;
@@ -1072,7 +1073,7 @@ static bool gemm_prefill_ok(const lmrs_b200* m, size_t n, uint32_t pos) {
     for (const Layer& Y : m->layers)
         for (const Mat* x : {&Y.qkv, &Y.wo, &Y.w1, &Y.w3, &Y.w2})
             if (!x->has_tmap) return false;
-    return m->l_att_dim % 128 == 0 && m->l_kv_dim % 128 == 0;
+    return m->l_att_dim % 128 == 0 && m->l_kv_dim % 64 == 0;
 }
 
 static int launch_rows_prologue(lmrs_b200* m, GemvParams p, int T) {

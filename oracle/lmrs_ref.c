@@ -497,6 +497,11 @@ void lmrs_ref_rope_freq(int model_type, float rope_theta, int head_size, int j, 
 }
 
 /* quantize + matmul dispatch used 4x per layer (src/transformer.rs:424-438,550-558,593-603,630-638) */
+/* test access to the k-shard accumulation order (tests/test_oracle_kat.py pins it against explicit column-slice partial sums) */
+void lmrs_ref_matmul_q8_kshards(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                                int rows, int n, int o, int gs, int shards) {
+    matmul_q8_kshards(xout, xq, xs, wq, ws, rows, n, o, gs, shards < 1 ? 1 : shards);
+}
 static int g_kshards = 1;   /* see matmul_q8_kshards: models lmrs_b200's N-GPU partial-sum order for Wo / W2 (not a reference feature) */
 void lmrs_ref_set_kshards(int n) { g_kshards = n < 1 ? 1 : n; }
 static void qmatmul_sh(const lmrs_ref_t* m, float* out, const float* in, const qt_t* w, int rows, int n, int o, int shards);

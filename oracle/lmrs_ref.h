@@ -74,6 +74,8 @@ void lmrs_ref_rope_freq(int model_type, float rope_theta, int head_size, int j, 
 /* NOT a reference feature: Wo / W2 accumulate `n` contiguous K ranges separately and add the partials in ascending
  * order -- the summation order of lmrs_b200's N-GPU row-sharded mode, so that N-GPU runs can be checked bit for bit. */
 void lmrs_ref_set_kshards(int n);
+void lmrs_ref_matmul_q8_kshards(float* xout, const int8_t* xq, const float* xs, const int8_t* wq, const float* ws,
+                                int rows, int n, int o, int gs, int shards);
 
 int lmrs_ref_num_threads(void);
 void lmrs_ref_set_num_threads(int n);

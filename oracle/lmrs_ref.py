@@ -71,6 +71,8 @@ def lib():
             # shared hosts: nproc may far exceed the cgroup's CPU quota, and oversubscribed OpenMP spin-waits are
             # catastrophic (measured 11 s/token at 128 threads); default to the quota, capped at 32
             L.lmrs_ref_set_num_threads(min(32, usable_cores()))
+        L.lmrs_ref_matmul_q8_kshards.argtypes = [C.c_void_p] * 5 + [C.c_int] * 5
+        L.lmrs_ref_matmul_q8_kshards.restype = None
         L.lmrs_ref_set_kshards.argtypes = [C.c_int]
         L.lmrs_ref_set_kshards.restype = None
         L.lmrs_ref_last_error.restype = C.c_char_p
@@ -164,6 +166,15 @@ def matmul_q8(xq, xs, wq, ws, rows, n, o, gs):
     xq, xs, wq, ws = _c(xq, np.int8), _c(xs, np.float32), _c(wq, np.int8), _c(ws, np.float32)
     out = np.zeros(rows * o, np.float32)
     lib().lmrs_ref_matmul_q8(_p(out), _p(xq), _p(xs), _p(wq), _p(ws), rows, n, o, gs)
+    return out
+
+
+def matmul_q8_kshards(xq, xs, wq, ws, rows, n, o, gs, shards):
+    """matmul_q8 with the K groups accumulated in `shards` contiguous ranges whose partials are added in ascending order
+    (the N-GPU order of lmrs_b200; not a reference feature)."""
+    xq, xs, wq, ws = _c(xq, np.int8), _c(xs, np.float32), _c(wq, np.int8), _c(ws, np.float32)
+    out = np.zeros(rows * o, np.float32)
+    lib().lmrs_ref_matmul_q8_kshards(_p(out), _p(xq), _p(xs), _p(wq), _p(ws), rows, n, o, gs, shards)
     return out
 
 

@@ -154,3 +154,27 @@ def test_oracle_forward_agrees_with_an_independent_numpy_forward(ref, lf, name, 
     for pos, tok in enumerate([3, 17, 5, 200, 9, 1]):
         a, b = cpu.forward(tok, pos).copy(), nf.forward(tok, pos)
         assert float(np.abs(a - b).max()) <= 1e-4, (name, pos)
+
+
+@pytest.mark.parametrize("shards", [2, 4, 8])
+def test_kshard_mode_is_the_rank_ordered_sum_of_column_slice_products(ref, shards):
+    """The oracle's k-shard accumulation (the order of lmrs_b200's N-GPU peer exchange; NOT a reference feature) equals what it
+    claims to be: matmul_q8 of every contiguous K range on its own (one GPU's partial), partials added in ascending order
+    starting from range 0 -- and it differs from the unsharded order in the low bits, which is why the N-GPU tests need it."""
+    rng = np.random.default_rng(shards)
+    n, o, rows = 4096, 64, 3   # 32 groups: every shard count leaves several groups per shard
+    xq = rng.integers(-127, 128, rows * n, dtype=np.int8); xs = (rng.uniform(0.5, 1.5, rows * n // 128) * 0.01).astype(np.float32)
+    wq = rng.integers(-127, 128, o * n, dtype=np.int8); ws = (rng.uniform(0.5, 1.5, o * n // 128) * 0.002).astype(np.float32)
+    got = ref.matmul_q8_kshards(xq, xs, wq, ws, rows, n, o, 128, shards)
+    ns = n // shards
+    total = None
+    for r in range(shards):
+        xq_r = np.ascontiguousarray(xq.reshape(rows, n)[:, r * ns:(r + 1) * ns]).reshape(-1)
+        xs_r = np.ascontiguousarray(xs.reshape(rows, n // 128)[:, r * ns // 128:(r + 1) * ns // 128]).reshape(-1)
+        wq_r = np.ascontiguousarray(wq.reshape(o, n)[:, r * ns:(r + 1) * ns]).reshape(-1)
+        ws_r = np.ascontiguousarray(ws.reshape(o, n // 128)[:, r * ns // 128:(r + 1) * ns // 128]).reshape(-1)
+        part = ref.matmul_q8(xq_r, xs_r, wq_r, ws_r, rows, ns, o, 128)
+        total = part if total is None else (total + part).astype(np.float32)
+    assert np.array_equal(got, total)
+    assert np.array_equal(ref.matmul_q8_kshards(xq, xs, wq, ws, rows, n, o, 128, 1), ref.matmul_q8(xq, xs, wq, ws, rows, n, o, 128))
+    assert not np.array_equal(got, ref.matmul_q8(xq, xs, wq, ws, rows, n, o, 128))
