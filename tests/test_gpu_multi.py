@@ -159,3 +159,30 @@ def test_in_process_multi_gpu_handle_is_bit_exact(n_gpus, name, q):
         gpu.close(); cpu.close()
     finally:
         lmrs_ref.set_kshards(1)
+
+
+def test_independent_handles_on_two_devices_from_one_thread():
+    """backend.rs creates one Transformer per connection; with several GPUs in one process a thread may own handles on
+    different devices.  Kernel attributes (> 48 KB shared-memory opt-in) are per device: both handles must work, the operator
+    ABI too (round-1 advisor finding: the opt-in used to be cached per thread)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import lmrs_b200
+    import lmrs_ref
+    from lmrs_b200 import lmrs_file as lf
+    buf = lf.write_synthetic(lf.model_args("small-llama", 1))
+    cpu = lmrs_ref.RefTransformer(buf)
+    g0, _ = lmrs_b200.Transformer.new(buf, 0)
+    g1, _ = lmrs_b200.Transformer.new(buf, 1)
+    toks = np.random.default_rng(5).integers(0, g0.args.vocab_size, 14).astype(np.uint32)
+    e0, e1, ec = g0.get_embeddings(toks[:10]), g1.get_embeddings(toks[:10]), cpu.get_embeddings(toks[:10])
+    assert g0.fill_kv_cache(e0, 0) == g1.fill_kv_cache(e1, 0) == cpu.fill_kv_cache(ec, 0) == 10
+    assert np.array_equal(e0, ec) and np.array_equal(e1, ec)
+    for i, t in enumerate(toks[10:]):
+        want = cpu.forward(int(t), 10 + i)
+        assert np.array_equal(g0.forward(int(t), 10 + i), want) and np.array_equal(g1.forward(int(t), 10 + i), want)
+    g0.close(); g1.close(); cpu.close()
