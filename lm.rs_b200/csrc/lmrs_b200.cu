@@ -1352,6 +1352,7 @@ static int create_common(const uint8_t* file, size_t len, int device, int rank, 
     }
     if (world > 1 && shard_init(m->shard, rank, world, nccl_id, m->args.dim)) { lmrs_b200_destroy(m); return fail(shard_error()); }
     if (m->use_peer && setup_peer_exchange(m)) { lmrs_b200_destroy(m); return 1; }
+    if (m->use_peer) shard_destroy(m->shard);   // NCCL only carried the IPC handles: no communicator is kept (or torn down at exit) in peer mode
     setup_attn_cluster(m);
     if (setup_trace(m)) { lmrs_b200_destroy(m); return 1; }
     m->ph_decode = make_phases(m, false);
@@ -1429,7 +1430,11 @@ extern "C" void lmrs_b200_destroy(lmrs_b200_t* m) {
     }
     for (int r = 0; r < m->world && r < PX_MAX_WORLD; r++)
         if (!m->in_process_group && m->xchg_peer[r] && m->xchg_peer[r] != m->d_xchg) cudaIpcCloseMemHandle(m->xchg_peer[r]);
-    cudaFree(m->d_xchg);
+    // An exchange block exported through CUDA IPC is NOT freed here: cudaFree of exported memory while another process still
+    // has it mapped is undefined behaviour, and nothing orders this rank's destroy against its peers' cudaIpcCloseMemHandle
+    // (a collective in a destructor would hang as soon as one rank has died).  The block (a few MB to ~140 MB) goes with the
+    // process; the driver reference-counts it across processes.  In-process groups free theirs normally.
+    if (m->in_process_group || m->world == 1) cudaFree(m->d_xchg);
     shard_destroy(m->shard);
     cudaFree(m->d_arena); cudaFree(m->d_dense); cudaFree(m->pf_xq); cudaFree(m->pf_xs); cudaFree(m->pf_q); cudaFree(m->pf_att); cudaFree(m->pf_wo);
     cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_h); cudaFree(m->pf_down); cudaFree(m->pf_scores); cudaFree(m->d_kcache); cudaFree(m->d_vcache); cudaFree(m->d_rope_cos); cudaFree(m->d_rope_sin);

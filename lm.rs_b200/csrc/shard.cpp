@@ -3,6 +3,7 @@
 
 #include <dlfcn.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <string>
@@ -57,6 +58,9 @@ int shard_init(Shard& s, int rank, int world, const void* unique_id, int) {
     if (load()) return 1;
     ncclUniqueId id;
     memcpy(&id, unique_id, 128);
+    // This communicator carries two all-reduces of a few KB per block (fallback data path) or a single 64-byte all-gather
+    // (peer mode): NVLink-SHARP multicast buffers buy nothing here and are one more thing to tear down at exit
+    setenv("NCCL_NVLS_ENABLE", "0", 0);
     ncclComm_t c;
     if (ck(api.CommInitRank(&c, world, id, rank), "ncclCommInitRank")) return 1;
     s.rank = rank; s.world = world; s.comm = c;

@@ -23,6 +23,7 @@ def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True, pf_r
     for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     os.environ["LMRS_B200_PEER"] = "1" if peer else "0"
+    os.environ.setdefault("NCCL_NVLS_ENABLE", "0")
     if pf_rows:
         os.environ["LMRS_B200_PF_ROWS"] = str(pf_rows)
     import torch
@@ -76,6 +77,8 @@ def _worker(rank, world, port, out_dir, name, expect_error=None, peer=True, pf_r
     if rank == 0:
         open(os.path.join(out_dir, "worst.txt"), "w").write(repr(worst))
         open(os.path.join(out_dir, "exact.txt"), "w").write("1" if exact else "0")
+    dist.barrier()
+    m.close()
     dist.barrier()
     dist.destroy_process_group()
 
