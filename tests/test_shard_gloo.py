@@ -17,7 +17,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world, port, out_dir, name="tiny-llama"):
+def _worker(rank, world, port, out_dir, name="tiny-llama", ordered=False):
     for p in (os.path.join(ROOT, "lm.rs_b200"), os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     import torch
@@ -60,6 +60,33 @@ def _worker(rank, world, port, out_dir, name="tiny-llama"):
     def allreduce(v):
         t = torch.from_numpy(v.copy()); dist.all_reduce(t); return t.numpy()
 
+    def gather(v):
+        parts = [torch.zeros(v.size) for _ in range(world)]
+        dist.all_gather(parts, torch.from_numpy(np.ascontiguousarray(v, np.float32).copy()))
+        return [p_.numpy() for p_ in parts]
+
+    def ordered_exchange(v):
+        """the peer exchange of lmrs_b200: every rank receives every partial and adds them in ascending
+        rank order starting from rank 0's -- deterministic, unlike the association inside an all-reduce"""
+        parts = gather(v)
+        total = parts[0].copy()
+        for p_ in parts[1:]:
+            total = (total + p_).astype(np.float32)
+        return total
+
+    exchange = ordered_exchange if ordered else allreduce
+    kshard_ok = True
+
+    def check_kshard(act_local, nm, l, n_full, total):
+        """rank 0: the ordered sum equals the oracle's k-shard product of the FULL matrix with the gathered activation, bit for bit"""
+        nonlocal kshard_ok
+        full_act = np.concatenate(gather(act_local))
+        if rank == 0 and ordered:
+            qo, so = offs[nm][l]
+            wq = buf[qo: qo + dim * n_full].view(np.int8); ws = buf[so: so + dim * (n_full // 128) * 4].view(np.float32)
+            xq, xs = R.quantize_q8(np.ascontiguousarray(full_act, np.float32), 128)
+            kshard_ok = kshard_ok and np.array_equal(R.matmul_q8_kshards(xq, xs, wq, ws, 1, n_full, dim, 128, world), total)
+
     K = np.zeros((a.n_layers, 64, lk), np.float32); V = np.zeros_like(K)
     full = R.RefTransformer(buf) if rank == 0 else None
     toks = [3, 77, 401, 9, 250]
@@ -90,13 +117,16 @@ def _worker(rank, world, port, out_dir, name="tiny-llama"):
                 sc = np.array([np.float32(np.dot(q[h * hs:(h + 1) * hs], kk[t])) / np.sqrt(np.float32(hs)) for t in range(pos + 1)], np.float32)
                 p = R.softmax(sc)
                 att[h * hs:(h + 1) * hs] = (p[:, None] * V[l, :pos + 1, (h // kvm) * hs:(h // kvm + 1) * hs]).sum(0)
-            wo = allreduce(qmm(att, *cols("wo", l, a.att_dim, dim, rank * la, la), la, dim))      # all-reduce #1
+            wo = exchange(qmm(att, *cols("wo", l, a.att_dim, dim, rank * la, la), la, dim))      # exchange #1
+            check_kshard(att, "wo", l, a.att_dim, wo)
             x = x + wo
             hin = R.rmsnorm(x, fv("rms_post_att", l), a.rms_norm_eps, False)
             g = qmm(hin, *rows("w1", l, dim, rank * lhid, lhid), dim, lhid)
             u = qmm(hin, *rows("w3", l, dim, rank * lhid, lhid), dim, lhid)
             hh = (g * (np.float32(1) / (np.float32(1) + np.exp(-g))) * u).astype(np.float32)
-            x = x + allreduce(qmm(hh, *cols("w2", l, hd, dim, rank * lhid, lhid), lhid, dim))      # all-reduce #2
+            dn = exchange(qmm(hh, *cols("w2", l, hd, dim, rank * lhid, lhid), lhid, dim))      # exchange #2
+            check_kshard(hh, "w2", l, hd, dn)
+            x = x + dn
         y = R.rmsnorm(x, fv("rms_final", 0), a.rms_norm_eps, False)
         part = qmm(y, *rows("emb", 0, dim, rank * lv, lv), dim, lv)
         gathered = [torch.zeros(lv) for _ in range(world)]
@@ -106,6 +136,7 @@ def _worker(rank, world, port, out_dir, name="tiny-llama"):
             worst = max(worst, float(np.abs(logits - full.forward(tok, pos)).max()))
     if rank == 0:
         open(os.path.join(out_dir, "worst.txt"), "w").write(repr(worst))
+        open(os.path.join(out_dir, "kshard.txt"), "w").write("1" if kshard_ok else "0")
     dist.destroy_process_group()
 
 
@@ -120,3 +151,16 @@ def test_row_sharding_matches_unsharded_logits(tmp_path, world, name):
     mp.spawn(_worker, args=(world, port, str(tmp_path), name), nprocs=world, join=True)
     worst = float(open(tmp_path / "worst.txt").read())
     assert worst <= 1e-3, worst      # partial sums re-associate the f32 group accumulation: tolerance, not bit-equality
+
+
+@pytest.mark.parametrize("world,name", [(2, "tiny-llama"), (4, "tiny-llama-8h")])
+def test_rank_ordered_exchange_is_the_kshard_order(tmp_path, world, name):
+    """The default N-GPU data path of lmrs_b200 replaces the all-reduce by "every rank gets every partial, adds them in rank
+    order".  With real processes (gloo): that sum equals, bit for bit, the oracle's k-shard product of the unsharded matrix
+    (what the GPU parity tests and bench.py compare N-GPU runs with), for Wo and W2 of every block and token; the logits stay
+    within the re-association tolerance of the unsharded oracle."""
+    torch = pytest.importorskip("torch")
+    import torch.multiprocessing as mp
+    mp.spawn(_worker, args=(world, _free_port(), str(tmp_path), name, True), nprocs=world, join=True)
+    assert open(tmp_path / "kshard.txt").read() == "1"
+    assert float(open(tmp_path / "worst.txt").read()) <= 1e-3
